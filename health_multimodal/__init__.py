@@ -1,0 +1,15 @@
+"""Drop-in alias: ``health_multimodal.image`` resolves to the B200-native implementation, so the reference's scripts
+(``chexpert-get-embedding.py:7``, ``test_first_emb.py:14``, ``trash/lower_bound_mcs.py:13``: ``from
+health_multimodal.image import get_biovil_resnet``) run unchanged with this repository on ``PYTHONPATH``.  Only the image
+side is provided: the text encoder (CXR-BERT) is outside the hot path and is consumed through its ``[P,128]`` outputs."""
+import importlib
+import sys
+
+__version__ = "0.1.3+b200"
+
+_IMPL = "incremental_multimodal_medical_learning_ii_b200.image"
+_SUBMODULES = ("", ".model", ".model.model", ".model.resnet", ".model.modules", ".inference_engine", ".utils",
+               ".data", ".data.transforms", ".data.io")
+for _sub in _SUBMODULES:
+    sys.modules[f"{__name__}.image{_sub}"] = importlib.import_module(_IMPL + _sub)
+image = sys.modules[f"{__name__}.image"]

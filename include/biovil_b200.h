@@ -1,0 +1,122 @@
+/*
+ * biovil_b200.h - C ABI of the B200-native BioViL image-encoder + prompt-scorer hot path.
+ *
+ * The reference (marcomistretta/incremental_multimodal_medical_learning_II) is pure Python and has no FFI:
+ * its "operator interface" for this path is the Python class surface of health_multimodal.image.  This
+ * library sits one level below a Python mirror of that surface (incremental_multimodal_medical_learning_ii_b200/
+ * image/*.py, loaded with ctypes) and replaces, per entry point:
+ *
+ *   bv_forward        ImageModel.forward                         health_multimodal/image/model/model.py:141-154
+ *                     ImageEncoder.forward                       health_multimodal/image/model/model.py:197-205
+ *                     ResNetHIML.forward (+ torchvision Bottleneck) health_multimodal/image/model/resnet.py:25-47
+ *                     MLP.forward (projector)                    health_multimodal/image/model/modules.py:43-55
+ *                     get_patchwise_projected_embeddings         health_multimodal/image/model/model.py:161-175
+ *                     patch x prompt similarity map              health_multimodal/vlp/inference_engine.py:93-108
+ *   bv_set_prompts    Trainer.bert_forward_mean (prompt side)    Trainer.py:1657-1680
+ *   bv_score          Trainer.myCosineSimilarity + label loop    Trainer.py:1682-1704, 805-837, 1019-1047
+ *   bv_conv2d_nhwc    one Conv2d+BatchNorm2d(+ReLU)(+residual)   (unit-test entry for the tcgen05 kernel)
+ *
+ * Conventions: plain pointers and sizes only; every pointer is a DEVICE pointer unless named host_*;
+ * the caller owns all buffers and the stream; calls are asynchronous on `stream`; functions return 0 on
+ * success or a negative bv_status and never throw; bv_last_error() gives the message of the calling
+ * thread's last failure.  One handle per device; a handle is not thread-safe.  There is no CPU fallback:
+ * on a machine without an sm_100 GPU every compute entry point fails with BV_ERR_NO_DEVICE.
+ */
+#ifndef BIOVIL_B200_H_
+#define BIOVIL_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct bv_handle bv_handle;
+typedef void* bv_stream; /* cudaStream_t */
+
+typedef enum {
+    BV_OK = 0,
+    BV_ERR_INVALID = -1,   /* bad argument / unsupported shape */
+    BV_ERR_NO_DEVICE = -2, /* no CUDA device of compute capability 10.x */
+    BV_ERR_CUDA = -3,      /* a CUDA runtime / driver call failed */
+    BV_ERR_WORKSPACE = -4  /* workspace too small */
+} bv_status;
+
+typedef enum { BV_DTYPE_U8 = 0, BV_DTYPE_F32 = 1 } bv_dtype;
+
+/* One convolution with eval-mode BatchNorm folded in: w is bf16 [cout][r][s][cin] (K-major), bias fp32 [cout]. */
+typedef struct {
+    const void* w;
+    const float* bias;
+    int32_t cin, cout, r, s, stride, pad;
+} bv_conv;
+
+#define BV_NUM_BLOCKS 16 /* Bottleneck blocks, layers [3,4,6,3] (resnet.py:80) */
+
+typedef struct {
+    /* Stem conv7x7/2 as a [64][K] matrix over gathered patches (k = c*49 + r*7 + s, zero padded):
+     *   stem_u8 : 1 input channel (the 3 identical ExpandChannels copies summed), 1/255 folded in, K = 64
+     *   stem_f1 : 1 input channel, float frames,                                              K = 64
+     *   stem_f3 : 3 input channels, float frames (general ImageModel.forward input),          K = 192    */
+    bv_conv stem_u8, stem_f1, stem_f3;
+    bv_conv conv1[BV_NUM_BLOCKS], conv2[BV_NUM_BLOCKS], conv3[BV_NUM_BLOCKS];
+    bv_conv downsample[BV_NUM_BLOCKS]; /* w == NULL when the block has no downsample branch */
+    bv_conv proj0;                     /* projector conv 2048->128 (+BN folded), ReLU */
+    const float* proj3_wt;             /* projector conv 128->128 TRANSPOSED: fp32 [k][d] */
+    const float* proj3_b;              /* fp32 [128] */
+} bv_weights;
+
+/* Optional outputs of bv_forward; any pointer may be NULL. */
+typedef struct {
+    float* global_emb;      /* [B,128]    un-normalised projected global embedding (what the fork's forward returns) */
+    float* patch_emb;       /* [B,H/32,W/32,128] projected patch embeddings, channel-last */
+    int32_t normalize_patch;/* L2-normalise patch_emb over the last dim (F.normalize, eps 1e-12) */
+    float* pooled;          /* [B,2048]   img_embedding: global average pool of the trunk output */
+    void* trunk_nhwc_bf16;  /* [B,H/32,W/32,2048] bf16 copy of the trunk output (patch_embedding) */
+    float* sim;             /* [B,L,2]    (pos,neg) cosine vs the prompts installed with bv_set_prompts */
+    float* prob;            /* [B,L]      sigmoid(pos-neg) */
+    uint8_t* pred;          /* [B,L]      1 iff pos > neg */
+    float* score;           /* [B,L]      (pos+1)/2 */
+    float* heat;            /* [B,H/32,W/32,L] normalised-patch . unit positive prompt */
+} bv_outputs;
+
+const char* bv_last_error(void);
+const char* bv_version(void);
+
+/* Host-side shape helpers (no GPU needed). */
+size_t bv_workspace_bytes(int32_t batch, int32_t channels, int32_t height, int32_t width);
+int32_t bv_patch_grid(int32_t size); /* size / 32 */
+
+int32_t bv_create(bv_handle** out, const bv_weights* host_weights, int32_t device);
+void bv_destroy(bv_handle* h);
+
+/* prompts: fp32 [L][2][P][128], index 0 = positive, 1 = negative, un-normalised (mean over prompts already applied
+ * by the caller when the reduction is "mean": then P == 1; P > 1 = max over per-prompt cosines).
+ * heat_text: optional fp32 [L][128] text vectors for the patch heat-maps (NULL -> positive prompt 0 of each label). */
+int32_t bv_set_prompts(bv_handle* h, const float* prompts, int32_t num_labels, int32_t prompts_per_polarity,
+                       const float* heat_text, bv_stream stream);
+
+int32_t bv_forward(bv_handle* h, const void* frames, int32_t dtype, int32_t batch, int32_t channels, int32_t height,
+                   int32_t width, void* workspace, size_t workspace_bytes, const bv_outputs* host_out,
+                   bv_stream stream);
+
+/* Score cached embeddings emb [B,128] (un-normalised) against the installed prompts. */
+int32_t bv_score(bv_handle* h, const float* emb, int32_t batch, float* sim, float* prob, uint8_t* pred, float* score,
+                 bv_stream stream);
+
+/* Number of kernels the last bv_forward launched (for launch accounting in the benchmark). */
+int32_t bv_last_forward_launches(const bv_handle* h);
+
+/* One fused convolution on NHWC bf16 through the tcgen05 implicit-GEMM kernel:
+ *   out[B,Ho,Wo,cout] = act(conv(x, c) + c.bias (+ conv(x2, c2) + c2.bias) (+ residual))
+ * x2/c2 (optional, may be NULL) is a second operand pair accumulated into the same tile (the fused
+ * downsample branch); residual is bf16 [B,Ho,Wo,cout] or NULL; out is bf16, or fp32 when out_fp32 != 0. */
+int32_t bv_conv2d_nhwc(const void* x, int32_t batch, int32_t height, int32_t width, const bv_conv* host_c,
+                       const void* x2, int32_t height2, int32_t width2, const bv_conv* host_c2, const void* residual,
+                       int32_t relu, void* out, int32_t out_fp32, bv_stream stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BIOVIL_B200_H_ */

@@ -1,0 +1,318 @@
+// HBM-bound helper kernels of the BioViL image path: stem patch gather, NHWC max-pool, global average pool,
+// projector tail (128->128 conv + patch mean + L2 norms) fused with the image x prompt cosine scorer.
+// All of them are plain CUDA-core kernels: the work is bytes, not FLOPs.
+#pragma once
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+namespace bv {
+
+constexpr int kEmbDim = 128;  // JOINT_FEATURE_SIZE, health_multimodal/image/model/model.py:25
+
+// ----------------------------------------------------------------------------------------------
+// Stem patch gather: 7x7 stride-2 pad-3 windows of the input frame -> bf16 rows of a [M, K] matrix
+// (M = B*Ho*Wo, K = 64 for one input channel [49 taps + 15 zeros], 192 for three [147 + 45 zeros]).
+// k = c*49 + r*7 + s, the flatten order of the OIHW stem weight (resnet.py:34 conv1).
+// The u8 path keeps pixel integers exact in bf16; 1/255 (ToTensor, transforms.py:37) lives in the weights.
+// ----------------------------------------------------------------------------------------------
+template <typename TIn>
+__device__ __forceinline__ float stem_px(const TIn* p) {
+    return static_cast<float>(*p);
+}
+
+template <typename TIn, int CIN>
+__global__ void __launch_bounds__(256) stem_patch_kernel(const TIn* __restrict__ x, __nv_bfloat16* __restrict__ out,
+                                                        int B, int H, int W, int Ho, int Wo) {
+    constexpr int K = (CIN == 1) ? 64 : 192;
+    constexpr int CHUNKS = K / 8;
+    const long long total = static_cast<long long>(B) * Ho * Wo * CHUNKS;
+    for (long long t = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; t < total;
+         t += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int chunk = static_cast<int>(t % CHUNKS);
+        const long long pix = t / CHUNKS;
+        const int q = static_cast<int>(pix % Wo);
+        const int pr = static_cast<int>((pix / Wo) % Ho);
+        const int b = static_cast<int>(pix / (static_cast<long long>(Wo) * Ho));
+        uint32_t packed[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            float v[2];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int k = chunk * 8 + e * 2 + u;
+                float val = 0.0f;
+                if (k < CIN * 49) {
+                    const int c = k / 49;
+                    const int tap = k - c * 49;
+                    const int r = tap / 7;
+                    const int s = tap - r * 7;
+                    const int iy = pr * 2 - 3 + r;
+                    const int ix = q * 2 - 3 + s;
+                    if (iy >= 0 && iy < H && ix >= 0 && ix < W)
+                        val = stem_px(x + ((static_cast<size_t>(b) * CIN + c) * H + iy) * W + ix);
+                }
+                v[u] = val;
+            }
+            const __nv_bfloat162 h = __floats2bfloat162_rn(v[0], v[1]);
+            packed[e] = *reinterpret_cast<const uint32_t*>(&h);
+        }
+        reinterpret_cast<uint4*>(out)[t] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+    }
+}
+
+// ----------------------------------------------------------------------------------------------
+// MaxPool2d(kernel 3, stride 2, padding 1) on NHWC bf16 (resnet.py:37).  One thread = one output pixel x 8
+// channels (16-byte vectors, coalesced over channels).  Padding never wins: inputs are post-ReLU (>= 0) and
+// the centre tap is always in range.
+// ----------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) maxpool3x3s2_nhwc_kernel(const __nv_bfloat16* __restrict__ in,
+                                                               __nv_bfloat16* __restrict__ out, int B, int H, int W,
+                                                               int C, int Ho, int Wo) {
+    const int chunks = C / 8;
+    const long long total = static_cast<long long>(B) * Ho * Wo * chunks;
+    for (long long t = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; t < total;
+         t += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int ch = static_cast<int>(t % chunks);
+        const long long pix = t / chunks;
+        const int q = static_cast<int>(pix % Wo);
+        const int pr = static_cast<int>((pix / Wo) % Ho);
+        const int b = static_cast<int>(pix / (static_cast<long long>(Wo) * Ho));
+        __nv_bfloat162 m[4];
+        bool first = true;
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            const int iy = pr * 2 - 1 + r;
+            if (iy < 0 || iy >= H) continue;
+#pragma unroll
+            for (int s = 0; s < 3; ++s) {
+                const int ix = q * 2 - 1 + s;
+                if (ix < 0 || ix >= W) continue;
+                const uint4 v = __ldg(reinterpret_cast<const uint4*>(
+                    in + ((static_cast<size_t>(b) * H + iy) * W + ix) * C + ch * 8));
+                const __nv_bfloat162* hv = reinterpret_cast<const __nv_bfloat162*>(&v);
+                if (first) {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) m[e] = hv[e];
+                    first = false;
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) m[e] = __hmax2(m[e], hv[e]);
+                }
+            }
+        }
+        uint4 o;
+        o.x = *reinterpret_cast<uint32_t*>(&m[0]);
+        o.y = *reinterpret_cast<uint32_t*>(&m[1]);
+        o.z = *reinterpret_cast<uint32_t*>(&m[2]);
+        o.w = *reinterpret_cast<uint32_t*>(&m[3]);
+        reinterpret_cast<uint4*>(out)[t] = o;
+    }
+}
+
+// ----------------------------------------------------------------------------------------------
+// adaptive_avg_pool2d(x4, (1,1)) + flatten (model.py:201): [B, P, C] bf16 -> [B, C] fp32.
+// ----------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) avgpool_nhwc_kernel(const __nv_bfloat16* __restrict__ in,
+                                                          float* __restrict__ out, int B, int P, int C) {
+    const int chunks = C / 8;
+    const long long total = static_cast<long long>(B) * chunks;
+    const float inv = 1.0f / static_cast<float>(P);
+    for (long long t = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; t < total;
+         t += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int ch = static_cast<int>(t % chunks);
+        const int b = static_cast<int>(t / chunks);
+        float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        const __nv_bfloat16* base = in + static_cast<size_t>(b) * P * C + ch * 8;
+        for (int pidx = 0; pidx < P; ++pidx) {
+            const uint4 v = __ldg(reinterpret_cast<const uint4*>(base + static_cast<size_t>(pidx) * C));
+            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                acc[2 * e] += __uint_as_float(w[e] << 16);
+                acc[2 * e + 1] += __uint_as_float(w[e] & 0xFFFF0000u);
+            }
+        }
+        float4* o = reinterpret_cast<float4*>(out + static_cast<size_t>(b) * C + ch * 8);
+        o[0] = make_float4(acc[0] * inv, acc[1] * inv, acc[2] * inv, acc[3] * inv);
+        o[1] = make_float4(acc[4] * inv, acc[5] * inv, acc[6] * inv, acc[7] * inv);
+    }
+}
+
+// ----------------------------------------------------------------------------------------------
+// Prompt preparation: y[j] / ||y[j]||_2 for every prompt vector (plain division, no eps: the semantics of
+// torchmetrics pairwise_cosine_similarity used by Trainer.myCosineSimilarity, Trainer.py:1682-1704).
+// One warp per prompt.
+// ----------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) prompt_normalize_kernel(const float* __restrict__ y, float* __restrict__ yn,
+                                                              int NP) {
+    const int j = blockIdx.x * 4 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (j >= NP) return;
+    const float4 v = reinterpret_cast<const float4*>(y + static_cast<size_t>(j) * kEmbDim)[lane];
+    float ss = v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    const float nrm = sqrtf(ss);
+    reinterpret_cast<float4*>(yn + static_cast<size_t>(j) * kEmbDim)[lane] =
+        make_float4(v.x / nrm, v.y / nrm, v.z / nrm, v.w / nrm);
+}
+
+struct ScoreOut {
+    float* sim;     // [B, L, 2]  (pos, neg) cosine
+    float* prob;    // [B, L]     sigmoid(pos - neg) = softmax over {pos, neg} at pos
+    uint8_t* pred;  // [B, L]     1 iff pos > neg (argmax([neg, pos]), ties -> 0; Trainer.py:836)
+    float* score;   // [B, L]     (pos + 1) / 2 (Trainer.py:825)
+};
+
+// One warp scores one image embedding `x` (128 fp32, 4 per lane, already divided by ||x||) against
+// yn[L][2][P][128] unit prompt vectors: cosine per prompt, max over the P prompts of a polarity
+// (P == 1 when the prompts were mean-reduced beforehand, Trainer.py:1665-1666; P > 1 is the MAX_EMB
+// variant, Trainer.py:1691-1694).
+__device__ __forceinline__ void score_image_warp(const float4 xn, const float* __restrict__ yn, int L, int P, int b,
+                                                 const ScoreOut& o, int lane) {
+    for (int l = 0; l < L; ++l) {
+        float best[2];
+#pragma unroll
+        for (int pol = 0; pol < 2; ++pol) {
+            float m = -INFINITY;
+            bool any_nan = false;
+            for (int pp = 0; pp < P; ++pp) {
+                const float4 y =
+                    reinterpret_cast<const float4*>(yn + (static_cast<size_t>(l * 2 + pol) * P + pp) * kEmbDim)[lane];
+                float d = xn.x * y.x + xn.y * y.y + xn.z * y.z + xn.w * y.w;
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) d += __shfl_xor_sync(0xffffffffu, d, off);
+                any_nan |= (d != d);
+                m = fmaxf(m, d);
+            }
+            best[pol] = any_nan ? __int_as_float(0x7fc00000) : m;
+        }
+        if (lane == 0) {
+            const float pos = best[0], neg = best[1];
+            const size_t i = static_cast<size_t>(b) * L + l;
+            if (o.sim) {
+                o.sim[2 * i] = pos;
+                o.sim[2 * i + 1] = neg;
+            }
+            if (o.prob) o.prob[i] = 1.0f / (1.0f + expf(-(pos - neg)));
+            if (o.pred) o.pred[i] = (pos > neg) ? 1 : 0;
+            if (o.score) o.score[i] = (pos + 1.0f) * 0.5f;
+        }
+    }
+}
+
+// Stand-alone scorer for cached embeddings (the Trainer.val/test path): emb [B,128] un-normalised.
+__global__ void __launch_bounds__(256) score_kernel(const float* __restrict__ emb, const float* __restrict__ yn, int B,
+                                                   int L, int P, ScoreOut o) {
+    const int warps = (gridDim.x * blockDim.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    for (int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; b < B; b += warps) {
+        float4 x = reinterpret_cast<const float4*>(emb + static_cast<size_t>(b) * kEmbDim)[lane];
+        float ss = x.x * x.x + x.y * x.y + x.z * x.z + x.w * x.w;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, off);
+        const float nrm = sqrtf(ss);
+        x = make_float4(x.x / nrm, x.y / nrm, x.z / nrm, x.w / nrm);
+        score_image_warp(x, yn, L, P, b, o, lane);
+    }
+}
+
+// ----------------------------------------------------------------------------------------------
+// Projector tail + embeddings + scoring, one CTA (256 threads) per image.
+//   hid [B*P, 128] fp32  = ReLU(BN(conv1x1_2048->128(x4)))   (written by the tcgen05 GEMM, modules.py:43-46)
+//   proj[p, d] = b2[d] + sum_k hid[p, k] * W2[d, k]            (modules.py:47, fp32 FMA)
+//   global[d]  = mean_p proj[p, d]                             (model.py:145)  -> global_out [B,128] un-normalised
+//   patch_out [B, P, 128] = proj or proj / max(||proj||, 1e-12) (model.py:172-174, F.normalize eps)
+//   heat_out  [B, P, L]   = normalised patch . unit prompt(l, pos, first prompt)  (vlp/inference_engine.py:107)
+//   scores of the global embedding against the prepared prompts (Trainer.py:805-837).
+// ----------------------------------------------------------------------------------------------
+struct HeadParams {
+    const float* hid;
+    const float* w2t;  // [128 k][128 d] fp32: W2 transposed so that thread d reads consecutive addresses
+    const float* b2;
+    int B, P;
+    float* global_out;
+    float* patch_out;
+    int normalize_patch;
+    const float* yn;  // prepared prompts or nullptr
+    int L, NPP;       // labels, prompts per polarity
+    ScoreOut score;
+    float* heat_out;      // [B, P, L] or nullptr
+    const float* heat_t;  // [L, 128] unit text vectors for heat-maps
+};
+
+__global__ void __launch_bounds__(256) head_kernel(const HeadParams hp) {
+    extern __shared__ float hsm[];
+    float* w2t = hsm;                         // 128*128
+    float* hrow = w2t + kEmbDim * kEmbDim;    // 2 * 128 (two patches in flight)
+    float* red = hrow + 2 * kEmbDim;          // 2 * 4 partial sums of squares
+    float* gsum = red + 8;                    // 2 * 128
+    float* prow = gsum + 2 * kEmbDim;         // 2 * 128 projected rows (for heat-maps)
+    const int b = blockIdx.x;
+    const int tid = threadIdx.x;
+    const int half = tid >> 7;  // which of the two patches in flight
+    const int d = tid & 127;
+    const int lane = tid & 31;
+    const int wq = (tid >> 5) & 3;  // warp within the half
+    for (int i = tid; i < kEmbDim * kEmbDim; i += 256) w2t[i] = __ldg(hp.w2t + i);
+    const float bias = __ldg(hp.b2 + d);
+    float gacc = 0.0f;
+    __syncthreads();
+    for (int p0 = 0; p0 < hp.P; p0 += 2) {
+        const int pidx = p0 + half;
+        const bool ok = pidx < hp.P;
+        hrow[tid] = ok ? __ldg(hp.hid + (static_cast<size_t>(b) * hp.P + pidx) * kEmbDim + d) : 0.0f;
+        __syncthreads();
+        float acc = bias;
+        const float* hr = hrow + half * kEmbDim;
+#pragma unroll 8
+        for (int k = 0; k < kEmbDim; ++k) acc = fmaf(hr[k], w2t[k * kEmbDim + d], acc);
+        if (ok) gacc += acc;
+        const bool need_norm = (hp.patch_out && hp.normalize_patch) || hp.heat_out;
+        float inv = 1.0f;
+        if (need_norm) {
+            float ss = acc * acc;
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, off);
+            if (lane == 0) red[half * 4 + wq] = ss;
+            __syncthreads();
+            const float tot = red[half * 4] + red[half * 4 + 1] + red[half * 4 + 2] + red[half * 4 + 3];
+            inv = 1.0f / fmaxf(sqrtf(tot), 1e-12f);
+        }
+        if (ok && hp.patch_out)
+            hp.patch_out[(static_cast<size_t>(b) * hp.P + pidx) * kEmbDim + d] = hp.normalize_patch ? acc * inv : acc;
+        if (hp.heat_out) {
+            prow[tid] = acc * inv;
+            __syncthreads();
+            // 8 warps: warp w of half h handles labels wq, wq+4, ...
+            for (int l = wq; l < hp.L; l += 4) {
+                const float4 pv = reinterpret_cast<const float4*>(prow + half * kEmbDim)[lane];
+                const float4 tv = reinterpret_cast<const float4*>(hp.heat_t + static_cast<size_t>(l) * kEmbDim)[lane];
+                float dsum = pv.x * tv.x + pv.y * tv.y + pv.z * tv.z + pv.w * tv.w;
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) dsum += __shfl_xor_sync(0xffffffffu, dsum, off);
+                if (lane == 0 && ok) hp.heat_out[(static_cast<size_t>(b) * hp.P + pidx) * hp.L + l] = dsum;
+            }
+        }
+        __syncthreads();
+    }
+    gsum[tid] = gacc;
+    __syncthreads();
+    if (tid < kEmbDim) {
+        const float g = (gsum[tid] + gsum[tid + kEmbDim]) / static_cast<float>(hp.P);
+        gsum[tid] = g;
+        if (hp.global_out) hp.global_out[static_cast<size_t>(b) * kEmbDim + tid] = g;
+    }
+    __syncthreads();
+    if (hp.yn != nullptr && tid < 32) {
+        float4 x = reinterpret_cast<const float4*>(gsum)[lane];
+        float ss = x.x * x.x + x.y * x.y + x.z * x.z + x.w * x.w;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, off);
+        const float nrm = sqrtf(ss);
+        x = make_float4(x.x / nrm, x.y / nrm, x.z / nrm, x.w / nrm);
+        score_image_warp(x, hp.yn, hp.L, hp.NPP, b, hp.score, lane);
+    }
+}
+
+}  // namespace bv

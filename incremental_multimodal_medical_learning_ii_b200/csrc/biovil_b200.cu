@@ -1,0 +1,545 @@
+// Host side of the C ABI declared in include/biovil_b200.h: weight table, per-shape launch plan (activation
+// buffers carved from the caller's workspace, TMA tensor maps, kernel parameters) and the launches.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cudaTypedefs.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/biovil_b200.h"
+#include "aux_kernels.cuh"
+#include "conv_gemm.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define BV_CUDA(expr)                                                                                   \
+    do {                                                                                                \
+        cudaError_t e__ = (expr);                                                                       \
+        if (e__ != cudaSuccess)                                                                         \
+            return fail(BV_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, \
+                        __LINE__);                                                                      \
+    } while (0)
+
+// ---- driver entry points for tensor-map encoding (resolved lazily so the library loads without libcuda) ----
+PFN_cuTensorMapEncodeTiled_v12000 g_encode_tiled = nullptr;
+PFN_cuTensorMapEncodeIm2col_v12000 g_encode_im2col = nullptr;
+
+int resolve_driver() {
+    if (g_encode_tiled && g_encode_im2col) return BV_OK;
+    cudaDriverEntryPointQueryResult qres;
+    void* fn = nullptr;
+    BV_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    if (!fn || qres != cudaDriverEntryPointSuccess) return fail(BV_ERR_CUDA, "cuTensorMapEncodeTiled not available");
+    g_encode_tiled = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
+    fn = nullptr;
+    BV_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &fn, cudaEnableDefault, &qres));
+    if (!fn || qres != cudaDriverEntryPointSuccess) return fail(BV_ERR_CUDA, "cuTensorMapEncodeIm2col not available");
+    g_encode_im2col = reinterpret_cast<PFN_cuTensorMapEncodeIm2col_v12000>(fn);
+    return BV_OK;
+}
+
+int make_tmap_2d(CUtensorMap* tm, const void* base, uint64_t inner, uint64_t outer, uint32_t box_inner,
+                 uint32_t box_outer) {
+    cuuint64_t dims[2] = {inner, outer};
+    cuuint64_t strides[1] = {inner * 2};
+    cuuint32_t box[2] = {box_inner, box_outer};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = g_encode_tiled(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box,
+                                estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS)
+        return fail(BV_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) inner=%llu outer=%llu box=%ux%u", (int)r,
+                    (unsigned long long)inner, (unsigned long long)outer, box_inner, box_outer);
+    return BV_OK;
+}
+
+// NHWC activation tensor [N][H][W][C] seen by TMA as (C, W, H, N); 128 output pixels x 64 channels per load.
+int make_tmap_im2col(CUtensorMap* tm, const void* base, int N, int H, int W, int C, int R, int S, int stride,
+                     int pad) {
+    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+    cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+    int lower[2] = {-pad, -pad};
+    int upper[2] = {pad - (S - 1), pad - (R - 1)};
+    cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
+    CUresult r = g_encode_im2col(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides,
+                                 lower, upper, bv::kBlockK, bv::kBlockM, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                 CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS)
+        return fail(BV_ERR_CUDA, "cuTensorMapEncodeIm2col failed (%d) N=%d H=%d W=%d C=%d R=%d S=%d stride=%d pad=%d",
+                    (int)r, N, H, W, C, R, S, stride, pad);
+    return BV_OK;
+}
+
+bool env_flag(const char* name) {
+    const char* v = getenv(name);
+    return v && v[0] && v[0] != '0';
+}
+
+struct ConvOperand {
+    const void* x;  // NHWC bf16 [B][H][W][cin]
+    int H, W;
+    bv_conv c;
+};
+
+struct ConvLaunch {
+    bv::ConvGemmParams p;
+    int bn;
+    int grid;
+};
+
+int g_num_sms = 0;
+bool g_attr_set = false;
+
+int device_setup() {
+    if (g_num_sms > 0) return BV_OK;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) {
+        cudaGetLastError();
+        return fail(BV_ERR_NO_DEVICE, "no CUDA device available (this library has no CPU fallback)");
+    }
+    cudaDeviceProp prop;
+    BV_CUDA(cudaGetDeviceProperties(&prop, dev));
+    if (prop.major != 10)
+        return fail(BV_ERR_NO_DEVICE, "device %s is sm_%d%d; this library is built for sm_100a only", prop.name,
+                    prop.major, prop.minor);
+    int rc = resolve_driver();
+    if (rc) return rc;
+    if (!g_attr_set) {
+        BV_CUDA(cudaFuncSetAttribute(bv::conv_gemm_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     bv::ConvGemmCfg<64>::kSmemBytes));
+        BV_CUDA(cudaFuncSetAttribute(bv::conv_gemm_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     bv::ConvGemmCfg<128>::kSmemBytes));
+        BV_CUDA(cudaFuncSetAttribute(bv::conv_gemm_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     bv::ConvGemmCfg<256>::kSmemBytes));
+        BV_CUDA(cudaFuncSetAttribute(bv::head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
+        g_attr_set = true;
+    }
+    g_num_sms = prop.multiProcessorCount;
+    return BV_OK;
+}
+
+int conv_out_dim(int in, int k, int stride, int pad) { return (in + 2 * pad - k) / stride + 1; }
+
+// Build the kernel parameters (tensor maps included) for one fused convolution.
+int build_conv(ConvLaunch* L, int B, const ConvOperand* ops, int nops, const void* residual, int relu, void* out,
+               int out_fp32) {
+    if (nops < 1 || nops > 2) return fail(BV_ERR_INVALID, "conv needs 1 or 2 operand pairs");
+    memset(&L->p, 0, sizeof(L->p));
+    bv::ConvGemmParams& p = L->p;
+    const bv_conv& c0 = ops[0].c;
+    const int Ho = conv_out_dim(ops[0].H, c0.r, c0.stride, c0.pad);
+    const int Wo = conv_out_dim(ops[0].W, c0.s, c0.stride, c0.pad);
+    const int N = c0.cout;
+    if (N % 64 != 0) return fail(BV_ERR_INVALID, "cout=%d must be a multiple of 64", N);
+    const int bn = (N % 256 == 0) ? 256 : ((N % 128 == 0) ? 128 : 64);
+    const long long M = (long long)B * Ho * Wo;
+    if (M <= 0 || M > 0x7fffffffLL - 256) return fail(BV_ERR_INVALID, "M=%lld out of range", M);
+    const bool force_im2col = env_flag("BV_FORCE_IM2COL");
+    for (int i = 0; i < nops; ++i) {
+        const bv_conv& c = ops[i].c;
+        if (c.cout != N) return fail(BV_ERR_INVALID, "operand %d cout mismatch", i);
+        if (c.cin % 64 != 0) return fail(BV_ERR_INVALID, "cin=%d must be a multiple of 64", c.cin);
+        if (conv_out_dim(ops[i].H, c.r, c.stride, c.pad) != Ho || conv_out_dim(ops[i].W, c.s, c.stride, c.pad) != Wo)
+            return fail(BV_ERR_INVALID, "operand %d output size mismatch", i);
+        bv::ConvSeg& sg = p.seg[i];
+        sg.cblocks = c.cin / 64;
+        sg.kblocks = c.r * c.s * sg.cblocks;
+        sg.S = c.s;
+        sg.stride = c.stride;
+        sg.lower = -c.pad;
+        const bool plain = (c.r == 1 && c.s == 1 && c.stride == 1 && c.pad == 0);
+        sg.mode = (plain && !force_im2col) ? bv::kSegTiled : bv::kSegIm2col;
+        int rc;
+        if (sg.mode == bv::kSegTiled) {
+            rc = make_tmap_2d(&p.tmA[i], ops[i].x, (uint64_t)c.cin, (uint64_t)M, bv::kBlockK, bv::kBlockM);
+        } else {
+            rc = make_tmap_im2col(&p.tmA[i], ops[i].x, B, ops[i].H, ops[i].W, c.cin, c.r, c.s, c.stride, c.pad);
+        }
+        if (rc) return rc;
+        rc = make_tmap_2d(&p.tmB[i], c.w, (uint64_t)c.r * c.s * c.cin, (uint64_t)N, bv::kBlockK, (uint32_t)bn);
+        if (rc) return rc;
+        p.bias[i] = c.bias;
+    }
+    p.nseg = nops;
+    p.Ho = Ho;
+    p.Wo = Wo;
+    p.M = (int)M;
+    p.N = N;
+    p.num_m_blocks = (int)((M + bv::kBlockM - 1) / bv::kBlockM);
+    p.num_n_blocks = N / bn;
+    p.residual = reinterpret_cast<const __nv_bfloat16*>(residual);
+    p.out = out;
+    p.relu = relu;
+    p.out_fp32 = out_fp32;
+    L->bn = bn;
+    const long long tiles = (long long)p.num_m_blocks * p.num_n_blocks;
+    L->grid = (int)std::min<long long>(tiles, g_num_sms);
+    return BV_OK;
+}
+
+int launch_conv(const ConvLaunch& L, cudaStream_t st) {
+    switch (L.bn) {
+        case 64:
+            bv::conv_gemm_kernel<64><<<L.grid, bv::kGemmThreads, bv::ConvGemmCfg<64>::kSmemBytes, st>>>(L.p);
+            break;
+        case 128:
+            bv::conv_gemm_kernel<128><<<L.grid, bv::kGemmThreads, bv::ConvGemmCfg<128>::kSmemBytes, st>>>(L.p);
+            break;
+        default:
+            bv::conv_gemm_kernel<256><<<L.grid, bv::kGemmThreads, bv::ConvGemmCfg<256>::kSmemBytes, st>>>(L.p);
+            break;
+    }
+    BV_CUDA(cudaGetLastError());
+    return BV_OK;
+}
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// Activation buffers inside the caller's workspace.
+struct Layout {
+    size_t buf_a, buf_b, t1, t2, tds, hid, total;
+};
+
+const int kLayerBlocks[4] = {3, 4, 6, 3};
+const int kLayerWidth[4] = {64, 128, 256, 512};
+
+Layout make_layout(int B, int C, int H, int W) {
+    Layout l{};
+    const size_t hw = (size_t)H * W;
+    const size_t K = (C == 3) ? 192 : 64;
+    const size_t patches = (size_t)B * (hw / 4) * K * 2;      // [B*H/2*W/2, K] bf16
+    const size_t stem_out = (size_t)B * (hw / 4) * 64 * 2;    // [B,H/2,W/2,64]
+    const size_t block_out = (size_t)B * (hw / 16) * 256 * 2;  // layer1 output, the largest block output
+    const size_t t1 = (size_t)B * (hw / 16) * 128 * 2;         // layer2.0 conv1 output
+    const size_t t2 = (size_t)B * (hw / 16) * 64 * 2;          // layer1 conv2 output
+    const size_t tds = block_out;                              // un-fused downsample output (debug path)
+    const size_t hid = (size_t)B * (hw / 1024) * 128 * 4;      // projector hidden, fp32
+    size_t off = 0;
+    l.buf_a = off; off += align_up(std::max(patches, block_out), 1024);
+    l.buf_b = off; off += align_up(std::max(stem_out, block_out), 1024);
+    l.t1 = off; off += align_up(t1, 1024);
+    l.t2 = off; off += align_up(t2, 1024);
+    l.hid = off; off += align_up(hid, 1024);
+    l.tds = off;
+    if (env_flag("BV_NO_FUSE_DS")) off += align_up(tds, 1024);
+    l.total = off + 1024;  // slack to align the caller's base pointer
+    return l;
+}
+
+}  // namespace
+
+struct bv_handle {
+    bv_weights w;
+    int device;
+    // prompts
+    float* yn = nullptr;      // [L][2][P][128] unit vectors
+    float* heat_t = nullptr;  // [L][128]
+    int L = 0, P = 0;
+    // cached plan
+    struct Key {
+        void* workspace;
+        int dtype, B, C, H, W;
+        bool operator==(const Key& o) const {
+            return workspace == o.workspace && dtype == o.dtype && B == o.B && C == o.C &&
+                   H == o.H && W == o.W;
+        }
+    } key{};
+    bool plan_valid = false;
+    std::vector<ConvLaunch> convs;  // in execution order (stem GEMM first)
+    const void* trunk = nullptr;    // final [B,h,w,2048] bf16
+    int last_launches = 0;
+};
+
+extern "C" {
+
+const char* bv_last_error(void) { return g_err.c_str(); }
+const char* bv_version(void) { return "biovil_b200 0.1 (sm_100a, tcgen05 implicit-GEMM)"; }
+
+int32_t bv_patch_grid(int32_t size) { return size / 32; }
+
+size_t bv_workspace_bytes(int32_t B, int32_t C, int32_t H, int32_t W) {
+    if (B <= 0 || H <= 0 || W <= 0 || H % 32 || W % 32 || (C != 1 && C != 3)) return 0;
+    return make_layout(B, C, H, W).total;
+}
+
+int32_t bv_create(bv_handle** out, const bv_weights* w, int32_t device) {
+    if (!out || !w) return fail(BV_ERR_INVALID, "null argument");
+    if (cudaSetDevice(device) != cudaSuccess) {
+        cudaGetLastError();
+        return fail(BV_ERR_NO_DEVICE, "cudaSetDevice(%d) failed: no usable CUDA device (no CPU fallback)", device);
+    }
+    int rc = device_setup();
+    if (rc) return rc;
+    bv_handle* h = new bv_handle();
+    h->w = *w;
+    h->device = device;
+    *out = h;
+    return BV_OK;
+}
+
+void bv_destroy(bv_handle* h) {
+    if (!h) return;
+    if (h->yn) cudaFree(h->yn);
+    if (h->heat_t) cudaFree(h->heat_t);
+    delete h;
+}
+
+int32_t bv_set_prompts(bv_handle* h, const float* prompts, int32_t L, int32_t P, const float* heat_text,
+                       bv_stream stream) {
+    if (!h || !prompts || L <= 0 || P <= 0) return fail(BV_ERR_INVALID, "bad prompt arguments");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (h->yn) cudaFree(h->yn);
+    if (h->heat_t) cudaFree(h->heat_t);
+    h->yn = h->heat_t = nullptr;
+    const int NP = L * 2 * P;
+    BV_CUDA(cudaMalloc(&h->yn, (size_t)NP * bv::kEmbDim * sizeof(float)));
+    BV_CUDA(cudaMalloc(&h->heat_t, (size_t)L * bv::kEmbDim * sizeof(float)));
+    bv::prompt_normalize_kernel<<<(NP + 3) / 4, 128, 0, st>>>(prompts, h->yn, NP);
+    BV_CUDA(cudaGetLastError());
+    if (heat_text) {
+        bv::prompt_normalize_kernel<<<(L + 3) / 4, 128, 0, st>>>(heat_text, h->heat_t, L);
+        BV_CUDA(cudaGetLastError());
+    } else {
+        // positive prompt 0 of each label: rows l*2*P of yn
+        BV_CUDA(cudaMemcpy2DAsync(h->heat_t, bv::kEmbDim * sizeof(float), h->yn,
+                                  (size_t)2 * P * bv::kEmbDim * sizeof(float), bv::kEmbDim * sizeof(float), L,
+                                  cudaMemcpyDeviceToDevice, st));
+    }
+    h->L = L;
+    h->P = P;
+    return BV_OK;
+}
+
+int32_t bv_score(bv_handle* h, const float* emb, int32_t B, float* sim, float* prob, uint8_t* pred, float* score,
+                 bv_stream stream) {
+    if (!h || !emb || B <= 0) return fail(BV_ERR_INVALID, "bad score arguments");
+    if (!h->yn) return fail(BV_ERR_INVALID, "bv_set_prompts has not been called");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    bv::ScoreOut o{sim, prob, pred, score};
+    const int blocks = std::min((B + 7) / 8, 148 * 8);
+    bv::score_kernel<<<blocks, 256, 0, st>>>(emb, h->yn, B, h->L, h->P, o);
+    BV_CUDA(cudaGetLastError());
+    return BV_OK;
+}
+
+int32_t bv_last_forward_launches(const bv_handle* h) { return h ? h->last_launches : 0; }
+
+static int build_plan(bv_handle* h, const void* frames, int dtype, int B, int C, int H, int W, uint8_t* ws) {
+    const Layout lay = make_layout(B, C, H, W);
+    h->convs.clear();
+    const bool fuse_ds = !env_flag("BV_NO_FUSE_DS");
+    uint8_t* buf_a = ws + lay.buf_a;
+    uint8_t* buf_b = ws + lay.buf_b;
+    uint8_t* t1 = ws + lay.t1;
+    uint8_t* t2 = ws + lay.t2;
+    uint8_t* tds = ws + lay.tds;
+    const int H2 = H / 2, W2 = W / 2;
+    // stem GEMM: patches [B*H2*W2, K] (buf_a) x stem weights -> stem_out (buf_b), bias + ReLU
+    {
+        const bv_conv& sc = (dtype == BV_DTYPE_U8) ? h->w.stem_u8 : (C == 3 ? h->w.stem_f3 : h->w.stem_f1);
+        bv_conv g = sc;  // viewed as a 1x1 conv over the gathered patch matrix
+        g.r = g.s = 1;
+        g.stride = 1;
+        g.pad = 0;
+        ConvOperand op{buf_a, H2, W2, g};
+        ConvLaunch L;
+        int rc = build_conv(&L, B, &op, 1, nullptr, 1, buf_b, 0);
+        if (rc) return rc;
+        h->convs.push_back(L);
+    }
+    // max-pool writes x0 into buf_a; blocks ping-pong buf_a <-> buf_b
+    uint8_t* cur = buf_a;
+    uint8_t* nxt = buf_b;
+    int ch = H / 4, cw = W / 4;
+    int blk = 0;
+    for (int li = 0; li < 4; ++li) {
+        for (int bi = 0; bi < kLayerBlocks[li]; ++bi, ++blk) {
+            const bv_conv& c1 = h->w.conv1[blk];
+            const bv_conv& c2 = h->w.conv2[blk];
+            const bv_conv& c3 = h->w.conv3[blk];
+            const bv_conv& ds = h->w.downsample[blk];
+            const int oh = conv_out_dim(ch, c2.r, c2.stride, c2.pad);
+            const int ow = conv_out_dim(cw, c2.s, c2.stride, c2.pad);
+            ConvLaunch L;
+            int rc;
+            ConvOperand o1{cur, ch, cw, c1};
+            if ((rc = build_conv(&L, B, &o1, 1, nullptr, 1, t1, 0))) return rc;
+            h->convs.push_back(L);
+            ConvOperand o2{t1, ch, cw, c2};
+            if ((rc = build_conv(&L, B, &o2, 1, nullptr, 1, t2, 0))) return rc;
+            h->convs.push_back(L);
+            if (ds.w != nullptr) {
+                if (fuse_ds) {
+                    ConvOperand o3[2] = {{t2, oh, ow, c3}, {cur, ch, cw, ds}};
+                    if ((rc = build_conv(&L, B, o3, 2, nullptr, 1, nxt, 0))) return rc;
+                    h->convs.push_back(L);
+                } else {
+                    ConvOperand od{cur, ch, cw, ds};
+                    if ((rc = build_conv(&L, B, &od, 1, nullptr, 0, tds, 0))) return rc;
+                    h->convs.push_back(L);
+                    ConvOperand o3{t2, oh, ow, c3};
+                    if ((rc = build_conv(&L, B, &o3, 1, tds, 1, nxt, 0))) return rc;
+                    h->convs.push_back(L);
+                }
+            } else {
+                ConvOperand o3{t2, oh, ow, c3};
+                if ((rc = build_conv(&L, B, &o3, 1, cur, 1, nxt, 0))) return rc;
+                h->convs.push_back(L);
+            }
+            std::swap(cur, nxt);
+            ch = oh;
+            cw = ow;
+        }
+    }
+    h->trunk = cur;
+    // projector conv 2048 -> 128 (+BN, ReLU), fp32 output for the fp32 tail
+    {
+        ConvOperand op{cur, ch, cw, h->w.proj0};
+        ConvLaunch L;
+        int rc = build_conv(&L, B, &op, 1, nullptr, 1, ws + lay.hid, 1);
+        if (rc) return rc;
+        h->convs.push_back(L);
+    }
+    (void)frames;
+    return BV_OK;
+}
+
+int32_t bv_forward(bv_handle* h, const void* frames, int32_t dtype, int32_t B, int32_t C, int32_t H, int32_t W,
+                   void* workspace, size_t workspace_bytes, const bv_outputs* out, bv_stream stream) {
+    if (!h || !frames || !workspace || !out) return fail(BV_ERR_INVALID, "null argument");
+    if (B <= 0 || H <= 0 || W <= 0 || H % 32 || W % 32)
+        return fail(BV_ERR_INVALID, "frames must be [B,C,H,W] with H, W multiples of 32 (got %dx%dx%dx%d)", B, C, H, W);
+    if (!((dtype == BV_DTYPE_U8 && C == 1) || (dtype == BV_DTYPE_F32 && (C == 1 || C == 3))))
+        return fail(BV_ERR_INVALID, "unsupported input: dtype=%d channels=%d (u8 x1, f32 x1, f32 x3)", dtype, C);
+    const Layout lay = make_layout(B, C, H, W);
+    uint8_t* ws = reinterpret_cast<uint8_t*>(align_up(reinterpret_cast<size_t>(workspace), 1024));
+    if (workspace_bytes < lay.total)
+        return fail(BV_ERR_WORKSPACE, "workspace too small: %zu < %zu", workspace_bytes, lay.total);
+    if ((out->sim || out->prob || out->pred || out->score || out->heat) && !h->yn)
+        return fail(BV_ERR_INVALID, "scores requested but bv_set_prompts has not been called");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    int rc = device_setup();
+    if (rc) return rc;
+    bv_handle::Key key{ws, dtype, B, C, H, W};
+    if (!h->plan_valid || !(h->key == key)) {
+        h->plan_valid = false;
+        rc = build_plan(h, frames, dtype, B, C, H, W, ws);
+        if (rc) return rc;
+        h->key = key;
+        h->plan_valid = true;
+    }
+    int launches = 0;
+    const int H2 = H / 2, W2 = W / 2, H4 = H / 4, W4 = W / 4;
+    __nv_bfloat16* patches = reinterpret_cast<__nv_bfloat16*>(ws + lay.buf_a);
+    // 1. stem patch gather
+    {
+        const long long total = (long long)B * H2 * W2 * ((C == 3) ? 24 : 8);
+        const int blocks = (int)std::min<long long>((total + 255) / 256, (long long)g_num_sms * 16);
+        if (dtype == BV_DTYPE_U8)
+            bv::stem_patch_kernel<uint8_t, 1><<<blocks, 256, 0, st>>>(reinterpret_cast<const uint8_t*>(frames), patches,
+                                                                    B, H, W, H2, W2);
+        else if (C == 1)
+            bv::stem_patch_kernel<float, 1><<<blocks, 256, 0, st>>>(reinterpret_cast<const float*>(frames), patches, B,
+                                                                  H, W, H2, W2);
+        else
+            bv::stem_patch_kernel<float, 3><<<blocks, 256, 0, st>>>(reinterpret_cast<const float*>(frames), patches, B,
+                                                                  H, W, H2, W2);
+        BV_CUDA(cudaGetLastError());
+        ++launches;
+    }
+    // 2. stem GEMM (+bias, ReLU)
+    if ((rc = launch_conv(h->convs[0], st))) return rc;
+    ++launches;
+    // 3. max-pool into buf_a
+    {
+        const long long total = (long long)B * H4 * W4 * 8;
+        const int blocks = (int)std::min<long long>((total + 255) / 256, (long long)g_num_sms * 16);
+        bv::maxpool3x3s2_nhwc_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(ws + lay.buf_b),
+                                                             reinterpret_cast<__nv_bfloat16*>(ws + lay.buf_a), B, H2,
+                                                             W2, 64, H4, W4);
+        BV_CUDA(cudaGetLastError());
+        ++launches;
+    }
+    // 4. bottleneck convs + projector conv
+    for (size_t i = 1; i < h->convs.size(); ++i) {
+        if ((rc = launch_conv(h->convs[i], st))) return rc;
+        ++launches;
+    }
+    const int gh = H / 32, gw = W / 32, P = gh * gw;
+    // 5. optional trunk outputs
+    if (out->pooled) {
+        const long long total = (long long)B * (2048 / 8);
+        bv::avgpool_nhwc_kernel<<<(int)((total + 255) / 256), 256, 0, st>>>(
+            reinterpret_cast<const __nv_bfloat16*>(h->trunk), out->pooled, B, P, 2048);
+        BV_CUDA(cudaGetLastError());
+        ++launches;
+    }
+    if (out->trunk_nhwc_bf16) {
+        BV_CUDA(cudaMemcpyAsync(out->trunk_nhwc_bf16, h->trunk, (size_t)B * P * 2048 * 2, cudaMemcpyDeviceToDevice, st));
+    }
+    // 6. projector tail + embeddings + scores
+    {
+        bv::HeadParams hp{};
+        hp.hid = reinterpret_cast<const float*>(ws + lay.hid);
+        hp.w2t = h->w.proj3_wt;
+        hp.b2 = h->w.proj3_b;
+        hp.B = B;
+        hp.P = P;
+        hp.global_out = out->global_emb;
+        hp.patch_out = out->patch_emb;
+        hp.normalize_patch = out->normalize_patch;
+        const bool want_score = out->sim || out->prob || out->pred || out->score;
+        hp.yn = want_score ? h->yn : nullptr;
+        hp.L = h->L;
+        hp.NPP = h->P;
+        hp.score = bv::ScoreOut{out->sim, out->prob, out->pred, out->score};
+        hp.heat_out = out->heat;
+        hp.heat_t = h->heat_t;
+        const size_t smem = (size_t)(bv::kEmbDim * bv::kEmbDim + 2 * bv::kEmbDim + 8 + 4 * bv::kEmbDim) * sizeof(float);
+        bv::head_kernel<<<B, 256, smem, st>>>(hp);
+        BV_CUDA(cudaGetLastError());
+        ++launches;
+    }
+    h->last_launches = launches;
+    return BV_OK;
+}
+
+int32_t bv_conv2d_nhwc(const void* x, int32_t B, int32_t H, int32_t W, const bv_conv* c, const void* x2, int32_t H2,
+                       int32_t W2, const bv_conv* c2, const void* residual, int32_t relu, void* out, int32_t out_fp32,
+                       bv_stream stream) {
+    if (!x || !c || !out) return fail(BV_ERR_INVALID, "null argument");
+    int rc = device_setup();
+    if (rc) return rc;
+    ConvOperand ops[2];
+    ops[0] = ConvOperand{x, H, W, *c};
+    int nops = 1;
+    if (x2 && c2) {
+        ops[1] = ConvOperand{x2, H2, W2, *c2};
+        nops = 2;
+    }
+    ConvLaunch L;
+    rc = build_conv(&L, B, ops, nops, residual, relu, out, out_fp32);
+    if (rc) return rc;
+    return launch_conv(L, reinterpret_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

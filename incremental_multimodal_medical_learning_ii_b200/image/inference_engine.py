@@ -1,0 +1,64 @@
+"""``ImageInferenceEngine`` (reference ``health_multimodal/image/inference_engine.py:21-87``) on the B200 model,
+plus batched tensor-input variants used by the extraction driver and the benchmark."""
+from __future__ import annotations
+
+from pathlib import Path
+from typing import Callable, Tuple
+
+import torch
+import torch.nn.functional as F
+from torchvision.transforms import Compose
+
+from .data.io import load_image
+from .data.transforms import infer_resize_params
+from .model.model import ImageModel
+
+TypeShape2D = Tuple[int, int]
+
+
+class ImageInferenceEngine:
+    """Encapsulates inference-time operations on an image model."""
+
+    def __init__(self, image_model: ImageModel, transform: Compose):
+        assert isinstance(image_model, ImageModel), f"Expected an ImageModel, got {type(image_model)}"
+        self.model = image_model
+        self.transform = transform
+        self.model.eval()
+        self.resize_size, self.crop_size = infer_resize_params(self.transform.transforms)
+        self.to = self.model.to
+
+    def load_and_transform_input_image(self, image_path: Path, transform: Callable) -> Tuple[torch.Tensor, TypeShape2D]:
+        """Read, transform, add the batch dimension, move to the model's device; also returns (width, height)."""
+        image = load_image(image_path)
+        device = next(self.model.parameters()).device
+        transformed_image = transform(image).unsqueeze(0).to(device)
+        return transformed_image, image.size
+
+    @torch.no_grad()
+    def get_projected_patch_embeddings(self, image_path: Path) -> Tuple[torch.Tensor, TypeShape2D]:
+        """``([H', W', 128] L2-normalised patch embeddings, (width, height) of the original image)``."""
+        input_image, img_shape = self.load_and_transform_input_image(image_path, self.transform)
+        projected_img_emb = self.model.get_patchwise_projected_embeddings(input_image, normalize=True)
+        assert projected_img_emb.shape[0] == 1
+        return projected_img_emb[0], img_shape
+
+    @torch.no_grad()
+    def get_projected_global_embedding(self, image_path: Path) -> torch.Tensor:
+        """``[128]`` L2-normalised global embedding of one image file."""
+        input_image, _ = self.load_and_transform_input_image(image_path, self.transform)
+        projected_img_emb = self.model.forward(input_image).projected_global_embedding
+        projected_img_emb = F.normalize(projected_img_emb, dim=-1)
+        assert projected_img_emb.shape[0] == 1
+        assert projected_img_emb.ndim == 2
+        return projected_img_emb[0]
+
+    # ---- batched variants (frames already decoded: uint8 [B,1,H,W] or float [B,1|3,H,W] on the model's device) ----
+    @torch.no_grad()
+    def get_projected_global_embedding_from_tensor(self, frames: torch.Tensor) -> torch.Tensor:
+        """``[B,128]`` L2-normalised global embeddings."""
+        return F.normalize(self.model.forward(frames).projected_global_embedding, dim=-1)
+
+    @torch.no_grad()
+    def get_projected_patch_embeddings_from_tensor(self, frames: torch.Tensor) -> torch.Tensor:
+        """``[B,H',W',128]`` L2-normalised patch embeddings."""
+        return self.model.get_patchwise_projected_embeddings(frames, normalize=True)

@@ -1,0 +1,154 @@
+"""End-to-end parity of the B200 ``ImageModel`` against the reference's outputs (tests/golden, produced by the
+reference itself in oracle/make_golden.py) and against the oracle at small frame sizes.
+
+Tolerances (BASELINE.json north_star): per-embedding cosine >= 0.999, zero-shot probabilities within 1e-3, predicted
+labels identical.  Because random-init embeddings are nearly colinear the cosine bound alone is weak,
+so relative L2 and the cosine of batch-centred embeddings are asserted too.
+"""
+import os
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda:0"
+
+
+def _model(randomize_bn):
+    import weights as Wt
+    from incremental_multimodal_medical_learning_ii_b200.image import get_biovil_resnet
+    sd = Wt.make_state_dict(27, randomize_bn=randomize_bn)
+    m = get_biovil_resnet(None)
+    m.load_state_dict(sd)
+    m.train(mode=False, my_freeze=True)
+    m.eval()
+    m.to(DEV)
+    return m, sd
+
+
+@pytest.fixture(scope="module", params=["default", "bnrand"])
+def setup(request, golden):
+    m, sd = _model(request.param == "bnrand")
+    return request.param, m, sd, golden
+
+
+def _metrics(a, ref):
+    a, ref = a.float().cpu(), ref.float().cpu()
+    cos = F.cosine_similarity(a, ref, dim=-1).min().item()
+    rel = ((a - ref).norm() / ref.norm()).item()
+    ac, rc = a - a.mean(0, keepdim=True), ref - ref.mean(0, keepdim=True)
+    ccos = F.cosine_similarity(ac, rc, dim=-1).min().item()
+    return cos, rel, ccos
+
+
+@pytest.mark.parametrize("kind", ["iid", "structured"])
+def test_global_embedding_vs_reference(setup, kind):
+    from incremental_multimodal_medical_learning_ii_b200 import frames as FR
+    import weights as Wt
+    variant, m, sd, golden = setup
+    g = golden[f"{variant}/{kind}"]
+    assert abs(Wt.state_dict_checksum(sd) - g["weights_checksum"]) <= 1e-6 * g["weights_checksum"]
+    fr = FR.synthetic_frames_u8(0, 8, 480, kind=kind, seed=0)
+    assert int(fr.long().sum()) == g["frames_checksum"]
+    out = m(fr.to(DEV))
+    assert out.shape == (8, 128) and out.dtype == torch.float32 and not out.requires_grad
+    cos, rel, ccos = _metrics(out, g["global"])
+    print(f"[{variant}/{kind}] cosine {cos:.6f} rel-L2 {rel:.3e} centred-cosine {ccos:.4f}")
+    assert cos >= 0.999
+    assert rel <= 2e-2
+    if kind == "structured":
+        assert ccos >= 0.98
+    # float [B,3,H,W] input as the reference's transforms produce it (exact k/255 detection -> same result)
+    out3 = m(FR.frames_as_reference_input(fr).to(DEV))
+    assert torch.equal(out3.cpu(), out.cpu())
+    # torch.cat usability (chexpert-get-embedding.py:79) and upstream attribute access (inference_engine.py:81)
+    cat = torch.cat([torch.empty(0, 128, device=DEV), out])
+    assert type(cat) is torch.Tensor and cat.shape == (8, 128)
+    assert torch.equal(out.projected_global_embedding, cat)
+
+
+def test_patch_pooled_and_scores_vs_reference(setup):
+    from incremental_multimodal_medical_learning_ii_b200 import frames as FR
+    variant, m, sd, golden = setup
+    g = golden[f"{variant}/structured"]
+    fr = FR.synthetic_frames_u8(0, 8, 480, kind="structured", seed=0).to(DEV)
+    patch = m.get_patchwise_projected_embeddings(fr[:2], normalize=True)
+    assert patch.shape == (2, 15, 15, 128)
+    pc = F.cosine_similarity(patch.cpu().reshape(-1, 128), g["patch_norm_first2"].reshape(-1, 128), dim=-1)
+    print(f"[{variant}] patch cosine min {pc.min().item():.6f}")
+    assert pc.min().item() >= 0.999
+    assert (patch.norm(dim=-1) - 1).abs().max().item() < 1e-4
+    raw = m.get_patchwise_projected_embeddings(fr[:2], normalize=False)
+    rel = ((raw.cpu() - g["patch_raw_first2"]).norm() / g["patch_raw_first2"].norm()).item()
+    assert rel <= 2e-2
+    out = m(fr)
+    pooled = out.img_embedding
+    rel = ((pooled.cpu() - g["pooled"]).norm() / g["pooled"].norm()).item()
+    print(f"[{variant}] pooled rel-L2 {rel:.3e}")
+    assert rel <= 2e-2
+    assert out.projected_patch_embeddings.shape == (8, 128, 15, 15)
+    assert out.patch_embedding.shape == (8, 2048, 15, 15)
+    assert out.class_logits is None
+    enc_patch, enc_pooled = m.encoder(fr[:2], return_patch_embeddings=True)
+    assert enc_patch.shape == (2, 2048, 15, 15) and enc_pooled.shape == (2, 2048)
+    # zero-shot scores: 14 labels, 1 and 5 prompts per polarity, mean and max reduction
+    for pname, P in (("p1", 1), ("p5", 5)):
+        prompts = FR.synthetic_prompt_embeddings(14, P, 128, seed=29)
+        for reduce in ("mean", "max"):
+            gs = g[f"score_{pname}_{reduce}"]
+            m.set_prompts(prompts, reduce=reduce)
+            res = m.embed_and_score(fr, heat=(pname == "p5" and reduce == "mean"))
+            dsim = (res["sim"].cpu() - gs["sim"]).abs().max().item()
+            dprob = (res["prob"].cpu() - gs["prob"]).abs().max().item()
+            margin = (gs["sim"][..., 0] - gs["sim"][..., 1]).abs()
+            flips = (res["pred"].cpu() != gs["pred"])
+            print(f"[{variant}] {pname}/{reduce}: max|dsim| {dsim:.2e} max|dprob| {dprob:.2e} flips {int(flips.sum())} "
+                  f"(min margin {margin.min().item():.1e})")
+            assert dprob <= 1e-3
+            assert not bool((flips & (margin > 1e-3)).any()), "label flipped outside the arithmetic noise floor"
+            # scoring the reference's own embeddings must reproduce its labels exactly
+            res2 = m.score_embeddings(g["global"].to(DEV))
+            assert torch.equal(res2["pred"].cpu(), gs["pred"])
+            assert (res2["prob"].cpu() - gs["prob"]).abs().max().item() <= 1e-5
+            assert (res2["sim"].cpu() - gs["sim"]).abs().max().item() <= 1e-5
+            assert (res2["score"].cpu() - gs["score"]).abs().max().item() <= 1e-5
+            if "heat" in res:
+                dh = (res["heat"][:2].cpu() - g["heat_first2_p5"]).abs().max().item()
+                print(f"[{variant}] heat-map max abs diff {dh:.2e}")
+                assert dh <= 1e-3 * 5
+
+
+def test_small_sizes_and_float_paths_vs_oracle(setup):
+    """Ragged / small cases against the CPU oracle: 1 frame, non-square frames, general float inputs."""
+    import biovil_oracle as O
+    variant, m, sd, golden = setup
+    gen = torch.Generator().manual_seed(3)
+    for (B, H, W) in ((1, 64, 64), (3, 96, 160), (5, 128, 96)):
+        x3 = torch.rand(B, 3, H, W, generator=gen)                      # general float, three different channels
+        ref = O.image_model_forward(sd, x3)["projected_global_embedding"]
+        out = m(x3.to(DEV))
+        cos, rel, _ = _metrics(out, ref)
+        print(f"[{variant}] f3 {B}x{H}x{W}: cosine {cos:.6f} rel {rel:.3e}")
+        assert cos >= 0.999 and rel <= 3e-2
+        x1 = torch.rand(B, 1, H, W, generator=gen)                      # general float, one channel
+        ref = O.image_model_forward(sd, x1.repeat(1, 3, 1, 1))["projected_global_embedding"]
+        out = m(x1.to(DEV))
+        cos, rel, _ = _metrics(out, ref)
+        print(f"[{variant}] f1 {B}x{H}x{W}: cosine {cos:.6f} rel {rel:.3e}")
+        assert cos >= 0.999 and rel <= 3e-2
+
+
+def test_guards(setup):
+    variant, m, sd, golden = setup
+    with pytest.raises(ValueError):
+        m(torch.zeros(1, 3, 50, 64, device=DEV))
+    with pytest.raises(ValueError):
+        m(torch.zeros(1, 2, 64, 64, device=DEV))
+    m.train()
+    with pytest.raises(RuntimeError):
+        m(torch.zeros(1, 3, 64, 64, device=DEV))
+    with pytest.raises(AssertionError):
+        m.get_patchwise_projected_embeddings(torch.zeros(1, 3, 64, 64, device=DEV), normalize=True)
+    m.eval()
