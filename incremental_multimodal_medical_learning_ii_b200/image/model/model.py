@@ -335,8 +335,10 @@ class ImageModel(nn.Module):
         one = x[:, :1]
         same = x.shape[1] == 1 or bool((one == x).all())
         if same:
-            k = torch.round(one * 255.0)
-            if bool(((k / 255.0) == one).all()) and bool(((k >= 0) & (k <= 255)).all()):
+            k255 = one * 255.0
+            k = torch.round(k255)
+            # |x*255 - k| far below one grey level: the frame is 8-bit data (ToTensor's k/255 up to fp32 rounding)
+            if bool(((k255 - k).abs() <= 1e-3).all()) and bool(((k >= 0) & (k <= 255)).all()):
                 return k.to(torch.uint8).contiguous()
             return one.contiguous()
         return x.contiguous()

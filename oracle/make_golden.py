@@ -43,7 +43,7 @@ def main() -> None:
     assert ref.training is False
 
     out = {"meta": {"n_frames": N_FRAMES, "size": SIZE, "frame_seed": 0, "weight_seed": 27, "bn_seed": 28,
-                    "prompt_seed": 29, "torch": torch.__version__}}
+                    "prompt_seed": 29, "torch": str(torch.__version__)}}
     for variant, rbn in (("default", False), ("bnrand", True)):
         sd = Wt.make_state_dict(27, randomize_bn=rbn)
         missing = set(ref.state_dict()) ^ set(sd)
