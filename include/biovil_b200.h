@@ -14,6 +14,7 @@
  *                     patch x prompt similarity map              health_multimodal/vlp/inference_engine.py:93-108
  *   bv_set_prompts    Trainer.bert_forward_mean (prompt side)    Trainer.py:1657-1680
  *   bv_score          Trainer.myCosineSimilarity + label loop    Trainer.py:1682-1704, 805-837, 1019-1047
+ *   bv_set_profile / bv_get_profile   (measurement only; no reference counterpart)
  *   bv_conv2d_nhwc    one Conv2d+BatchNorm2d(+ReLU)(+residual)   (unit-test entry for the tcgen05 kernel)
  *
  * Conventions: plain pointers and sizes only; every pointer is a DEVICE pointer unless named host_*;
@@ -107,6 +108,18 @@ int32_t bv_score(bv_handle* h, const float* emb, int32_t batch, float* sim, floa
 
 /* Number of kernels the last bv_forward launched (for launch accounting in the benchmark). */
 int32_t bv_last_forward_launches(const bv_handle* h);
+
+/* Per-launch timing of bv_forward with cudaEvents recorded on the launch stream (measurement only; adds one
+ * event record per launch).  bv_get_profile synchronises on the last event and fills up to `capacity` records of
+ * the most recent bv_forward; returns the number of launches or a negative bv_status. */
+typedef struct {
+    char name[64];
+    double flops; /* 2*M*N*K actually issued to the tensor cores (0 for non-GEMM kernels) */
+    double bytes; /* algorithmic HBM bytes of the launch */
+    float ms;
+} bv_launch_info;
+int32_t bv_set_profile(bv_handle* h, int32_t enable);
+int32_t bv_get_profile(bv_handle* h, bv_launch_info* host_out, int32_t capacity);
 
 /* One fused convolution on NHWC bf16 through the tcgen05 implicit-GEMM kernel:
  *   out[B,Ho,Wo,cout] = act(conv(x, c) + c.bias (+ conv(x2, c2) + c2.bias) (+ residual))

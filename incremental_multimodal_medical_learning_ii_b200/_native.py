@@ -56,10 +56,16 @@ class BvOutputs(Structure):
                 ("pred", c_void_p), ("score", c_void_p), ("heat", c_void_p)]
 
 
+class BvLaunchInfo(Structure):
+    _fields_ = [("name", ctypes.c_char * 64), ("flops", ctypes.c_double), ("bytes", ctypes.c_double),
+                ("ms", c_float)]
+
+
 # Every symbol include/biovil_b200.h declares (tests check the library exports all of them).
 EXPORTED_SYMBOLS = (
     "bv_last_error", "bv_version", "bv_workspace_bytes", "bv_patch_grid", "bv_create", "bv_destroy",
-    "bv_set_prompts", "bv_forward", "bv_score", "bv_last_forward_launches", "bv_conv2d_nhwc",
+    "bv_set_prompts", "bv_forward", "bv_score", "bv_last_forward_launches", "bv_set_profile", "bv_get_profile",
+    "bv_conv2d_nhwc",
 )
 
 _lib = None
@@ -118,6 +124,10 @@ def lib() -> ctypes.CDLL:
     l.bv_score.argtypes = [c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
     l.bv_last_forward_launches.restype = c_int32
     l.bv_last_forward_launches.argtypes = [c_void_p]
+    l.bv_set_profile.restype = c_int32
+    l.bv_set_profile.argtypes = [c_void_p, c_int32]
+    l.bv_get_profile.restype = c_int32
+    l.bv_get_profile.argtypes = [c_void_p, POINTER(BvLaunchInfo), c_int32]
     l.bv_conv2d_nhwc.restype = c_int32
     l.bv_conv2d_nhwc.argtypes = [c_void_p, c_int32, c_int32, c_int32, POINTER(BvConv), c_void_p, c_int32, c_int32,
                                  POINTER(BvConv), c_void_p, c_int32, c_void_p, c_int32, c_void_p]

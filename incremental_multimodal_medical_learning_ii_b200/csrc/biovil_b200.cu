@@ -267,7 +267,48 @@ struct bv_handle {
     std::vector<ConvLaunch> convs;  // in execution order (stem GEMM first)
     const void* trunk = nullptr;    // final [B,h,w,2048] bf16
     int last_launches = 0;
+    // optional per-launch timing (cudaEvents on the launch stream)
+    bool profile = false;
+    std::vector<cudaEvent_t> events;
+    std::vector<bv_launch_info> infos;
+    int n_events = 0;
 };
+
+namespace {
+// Record a timestamp on the launch stream when profiling is on (one event before the first launch, one after each).
+void prof_mark(bv_handle* h, cudaStream_t st, const char* name, double flops, double bytes) {
+    if (!h->profile) return;
+    if ((int)h->events.size() <= h->n_events) {
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        h->events.push_back(e);
+    }
+    cudaEventRecord(h->events[h->n_events++], st);
+    if (name) {
+        bv_launch_info info{};
+        snprintf(info.name, sizeof(info.name), "%s", name);
+        info.flops = flops;
+        info.bytes = bytes;
+        info.ms = 0.f;
+        h->infos.push_back(info);
+    }
+}
+
+void conv_cost(const ConvLaunch& L, double* flops, double* bytes, char* name, size_t n) {
+    const bv::ConvGemmParams& p = L.p;
+    double k = 0, abytes = 0;
+    for (int i = 0; i < p.nseg; ++i) {
+        k += (double)p.seg[i].kblocks * 64;
+        // algorithmic A traffic: every input element once (taps and strides re-read through L2, not HBM)
+        const double rows = (p.seg[i].mode == bv::kSegTiled) ? (double)p.M : (double)p.M * p.seg[i].stride * p.seg[i].stride;
+        abytes += rows * p.seg[i].cblocks * 64 * 2;
+    }
+    *flops = 2.0 * p.M * p.N * k;
+    *bytes = abytes + (double)p.M * p.N * (p.out_fp32 ? 4 : 2) + (p.residual ? (double)p.M * p.N * 2 : 0) + k * p.N * 2;
+    snprintf(name, n, "conv_gemm<%d> M=%d N=%d K=%d%s%s", L.bn, p.M, p.N, (int)k, p.nseg > 1 ? " +ds" : "",
+             p.residual ? " +res" : "");
+}
+}  // namespace
 
 extern "C" {
 
@@ -342,6 +383,26 @@ int32_t bv_score(bv_handle* h, const float* emb, int32_t B, float* sim, float* p
 }
 
 int32_t bv_last_forward_launches(const bv_handle* h) { return h ? h->last_launches : 0; }
+
+int32_t bv_set_profile(bv_handle* h, int32_t enable) {
+    if (!h) return fail(BV_ERR_INVALID, "null handle");
+    h->profile = enable != 0;
+    return BV_OK;
+}
+
+int32_t bv_get_profile(bv_handle* h, bv_launch_info* out, int32_t capacity) {
+    if (!h) return fail(BV_ERR_INVALID, "null handle");
+    const int n = (int)h->infos.size();
+    if (h->n_events != n + 1 && n > 0) return fail(BV_ERR_INVALID, "profile is incomplete");
+    if (n > 0) BV_CUDA(cudaEventSynchronize(h->events[n]));
+    for (int i = 0; i < n && i < capacity; ++i) {
+        float ms = 0.f;
+        BV_CUDA(cudaEventElapsedTime(&ms, h->events[i], h->events[i + 1]));
+        out[i] = h->infos[i];
+        out[i].ms = ms;
+    }
+    return n;
+}
 
 static int build_plan(bv_handle* h, const void* frames, int dtype, int B, int C, int H, int W, uint8_t* ws) {
     const Layout lay = make_layout(B, C, H, W);
@@ -448,6 +509,11 @@ int32_t bv_forward(bv_handle* h, const void* frames, int32_t dtype, int32_t B, i
         h->plan_valid = true;
     }
     int launches = 0;
+    h->n_events = 0;
+    h->infos.clear();
+    prof_mark(h, st, nullptr, 0, 0);
+    char pname[64];
+    double pflops = 0, pbytes = 0;
     const int H2 = H / 2, W2 = W / 2, H4 = H / 4, W4 = W / 4;
     __nv_bfloat16* patches = reinterpret_cast<__nv_bfloat16*>(ws + lay.buf_a);
     // 1. stem patch gather
@@ -465,10 +531,14 @@ int32_t bv_forward(bv_handle* h, const void* frames, int32_t dtype, int32_t B, i
                                                                   H, W, H2, W2);
         BV_CUDA(cudaGetLastError());
         ++launches;
+        const double px = (double)B * H2 * W2;
+        prof_mark(h, st, "stem_patch_gather", 0, (double)B * C * H * W * (dtype == BV_DTYPE_U8 ? 1 : 4) + px * ((C == 3) ? 192 : 64) * 2);
     }
     // 2. stem GEMM (+bias, ReLU)
     if ((rc = launch_conv(h->convs[0], st))) return rc;
     ++launches;
+    conv_cost(h->convs[0], &pflops, &pbytes, pname, sizeof(pname));
+    prof_mark(h, st, pname, pflops, pbytes);
     // 3. max-pool into buf_a
     {
         const long long total = (long long)B * H4 * W4 * 8;
@@ -478,11 +548,16 @@ int32_t bv_forward(bv_handle* h, const void* frames, int32_t dtype, int32_t B, i
                                                              W2, 64, H4, W4);
         BV_CUDA(cudaGetLastError());
         ++launches;
+        prof_mark(h, st, "maxpool3x3s2", 0, (double)B * H2 * W2 * 64 * 2 + (double)B * H4 * W4 * 64 * 2);
     }
     // 4. bottleneck convs + projector conv
     for (size_t i = 1; i < h->convs.size(); ++i) {
         if ((rc = launch_conv(h->convs[i], st))) return rc;
         ++launches;
+        if (h->profile) {
+            conv_cost(h->convs[i], &pflops, &pbytes, pname, sizeof(pname));
+            prof_mark(h, st, pname, pflops, pbytes);
+        }
     }
     const int gh = H / 32, gw = W / 32, P = gh * gw;
     // 5. optional trunk outputs
@@ -492,6 +567,7 @@ int32_t bv_forward(bv_handle* h, const void* frames, int32_t dtype, int32_t B, i
             reinterpret_cast<const __nv_bfloat16*>(h->trunk), out->pooled, B, P, 2048);
         BV_CUDA(cudaGetLastError());
         ++launches;
+        prof_mark(h, st, "avgpool", 0, (double)B * P * 2048 * 2);
     }
     if (out->trunk_nhwc_bf16) {
         BV_CUDA(cudaMemcpyAsync(out->trunk_nhwc_bf16, h->trunk, (size_t)B * P * 2048 * 2, cudaMemcpyDeviceToDevice, st));
@@ -518,6 +594,7 @@ int32_t bv_forward(bv_handle* h, const void* frames, int32_t dtype, int32_t B, i
         bv::head_kernel<<<B, 256, smem, st>>>(hp);
         BV_CUDA(cudaGetLastError());
         ++launches;
+        prof_mark(h, st, "head_score", 2.0 * B * P * 128 * 128, (double)B * P * 128 * 4);
     }
     h->last_launches = launches;
     return BV_OK;

@@ -166,6 +166,17 @@ class _Engine:
     def launches(self) -> int:
         return int(self.lib.bv_last_forward_launches(self.handle))
 
+    def set_profile(self, enable: bool) -> None:
+        N.check(self.lib.bv_set_profile(self.handle, 1 if enable else 0))
+
+    def get_profile(self):
+        """Per-launch ``(name, flops, bytes, ms)`` of the most recent forward (needs ``set_profile(True)``)."""
+        buf = (N.BvLaunchInfo * 128)()
+        n = self.lib.bv_get_profile(self.handle, buf, 128)
+        if n < 0:
+            N.check(n)
+        return [(buf[i].name.decode(), buf[i].flops, buf[i].bytes, buf[i].ms) for i in range(n)]
+
 
 class ImageEncoder(nn.Module):
     """Image encoder trunk (reference model.py:178-228).  ``forward`` returns the pooled embedding, or
