@@ -100,8 +100,15 @@ struct ConvOperand {
     bv_conv c;
 };
 
+// Kernel configurations <BN, STAGES, NBUF> (see ConvGemmCfg): picked per layer by arithmetic intensity.
+enum ConvCfg { kCfg256Deep = 0, kCfg256Res, kCfg128Res, kCfg128Deep, kCfg64, kNumCfg };
+#define BV_FOR_EACH_CFG(X) X(kCfg256Deep, 256, 4, 2) X(kCfg256Res, 256, 3, 4) X(kCfg128Res, 128, 3, 7) \
+                           X(kCfg128Deep, 128, 6, 2) X(kCfg64, 64, 8, 2)
+const int kCfgBN[kNumCfg] = {256, 256, 128, 128, 64};
+
 struct ConvLaunch {
     bv::ConvGemmParams p;
+    int cfg;
     int bn;
     int grid;
 };
@@ -124,12 +131,11 @@ int device_setup() {
     int rc = resolve_driver();
     if (rc) return rc;
     if (!g_attr_set) {
-        BV_CUDA(cudaFuncSetAttribute(bv::conv_gemm_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     bv::ConvGemmCfg<64>::kSmemBytes));
-        BV_CUDA(cudaFuncSetAttribute(bv::conv_gemm_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     bv::ConvGemmCfg<128>::kSmemBytes));
-        BV_CUDA(cudaFuncSetAttribute(bv::conv_gemm_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     bv::ConvGemmCfg<256>::kSmemBytes));
+#define BV_SET_ATTR(id, BN, ST, NB)                                                                            \
+    BV_CUDA(cudaFuncSetAttribute(bv::conv_gemm_kernel<BN, ST, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                 bv::ConvGemmCfg<BN, ST, NB>::kSmemBytes));
+        BV_FOR_EACH_CFG(BV_SET_ATTR)
+#undef BV_SET_ATTR
         BV_CUDA(cudaFuncSetAttribute(bv::head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
         g_attr_set = true;
     }
@@ -150,7 +156,21 @@ int build_conv(ConvLaunch* L, int B, const ConvOperand* ops, int nops, const voi
     const int Wo = conv_out_dim(ops[0].W, c0.s, c0.stride, c0.pad);
     const int N = c0.cout;
     if (N % 64 != 0) return fail(BV_ERR_INVALID, "cout=%d must be a multiple of 64", N);
-    const int bn = (N % 256 == 0) ? 256 : ((N % 128 == 0) ? 128 : 64);
+    int total_kblocks = 0;
+    for (int i = 0; i < nops; ++i) total_kblocks += ops[i].c.r * ops[i].c.s * (ops[i].c.cin / 64);
+    // Compute-bound shapes (long K loop) take the 256-wide tile; short-K shapes are HBM-bound and take the
+    // 128-wide tile with either a deep A ring (no residual) or many staging tiles (residual stream).
+    int cfg;
+    const bool res_stream = residual && !out_fp32;
+    if (N % 128 != 0) cfg = kCfg64;
+    else if (N % 256 != 0) cfg = kCfg128Deep;
+    else if (total_kblocks >= 8) cfg = res_stream ? kCfg256Res : kCfg256Deep;
+    else cfg = res_stream ? kCfg128Res : kCfg256Res;  // short K: HBM-bound, wants staging depth
+    if (const char* force = getenv("BV_FORCE_CFG")) {
+        const int f = atoi(force);
+        if (f >= 0 && f < kNumCfg && N % kCfgBN[f] == 0) cfg = f;
+    }
+    const int bn = kCfgBN[cfg];
     const long long M = (long long)B * Ho * Wo;
     if (M <= 0 || M > 0x7fffffffLL - 256) return fail(BV_ERR_INVALID, "M=%lld out of range", M);
     const bool force_im2col = env_flag("BV_FORCE_IM2COL");
@@ -179,6 +199,14 @@ int build_conv(ConvLaunch* L, int B, const ConvOperand* ops, int nops, const voi
         if (rc) return rc;
         p.bias[i] = c.bias;
     }
+    if (!out_fp32) {
+        int rc = make_tmap_2d(&p.tmOut, out, (uint64_t)N, (uint64_t)M, bv::kChunkCols, bv::kBlockM);
+        if (rc) return rc;
+        if (residual) {
+            rc = make_tmap_2d(&p.tmRes, residual, (uint64_t)N, (uint64_t)M, bv::kChunkCols, bv::kBlockM);
+            if (rc) return rc;
+        }
+    }
     p.nseg = nops;
     p.Ho = Ho;
     p.Wo = Wo;
@@ -191,22 +219,23 @@ int build_conv(ConvLaunch* L, int B, const ConvOperand* ops, int nops, const voi
     p.relu = relu;
     p.out_fp32 = out_fp32;
     L->bn = bn;
+    L->cfg = cfg;
     const long long tiles = (long long)p.num_m_blocks * p.num_n_blocks;
     L->grid = (int)std::min<long long>(tiles, g_num_sms);
     return BV_OK;
 }
 
 int launch_conv(const ConvLaunch& L, cudaStream_t st) {
-    switch (L.bn) {
-        case 64:
-            bv::conv_gemm_kernel<64><<<L.grid, bv::kGemmThreads, bv::ConvGemmCfg<64>::kSmemBytes, st>>>(L.p);
-            break;
-        case 128:
-            bv::conv_gemm_kernel<128><<<L.grid, bv::kGemmThreads, bv::ConvGemmCfg<128>::kSmemBytes, st>>>(L.p);
-            break;
+    switch (L.cfg) {
+#define BV_LAUNCH(id, BN, ST, NB)                                                                                  \
+    case id:                                                                                                       \
+        bv::conv_gemm_kernel<BN, ST, NB><<<L.grid, bv::kGemmThreads, bv::ConvGemmCfg<BN, ST, NB>::kSmemBytes, st>>>( \
+            L.p);                                                                                                  \
+        break;
+        BV_FOR_EACH_CFG(BV_LAUNCH)
+#undef BV_LAUNCH
         default:
-            bv::conv_gemm_kernel<256><<<L.grid, bv::kGemmThreads, bv::ConvGemmCfg<256>::kSmemBytes, st>>>(L.p);
-            break;
+            return fail(BV_ERR_INVALID, "unknown conv configuration %d", L.cfg);
     }
     BV_CUDA(cudaGetLastError());
     return BV_OK;
@@ -305,7 +334,7 @@ void conv_cost(const ConvLaunch& L, double* flops, double* bytes, char* name, si
     }
     *flops = 2.0 * p.M * p.N * k;
     *bytes = abytes + (double)p.M * p.N * (p.out_fp32 ? 4 : 2) + (p.residual ? (double)p.M * p.N * 2 : 0) + k * p.N * 2;
-    snprintf(name, n, "conv_gemm<%d> M=%d N=%d K=%d%s%s", L.bn, p.M, p.N, (int)k, p.nseg > 1 ? " +ds" : "",
+    snprintf(name, n, "conv_gemm<%d/c%d> M=%d N=%d K=%d%s%s", L.bn, L.cfg, p.M, p.N, (int)k, p.nseg > 1 ? " +ds" : "",
              p.residual ? " +res" : "");
 }
 }  // namespace

@@ -15,10 +15,15 @@
 // Bottleneck.forward under health_multimodal/image/model/resnet.py:34-42 and the projector's first conv,
 // health_multimodal/image/model/modules.py:43-46.  BatchNorm (eval) is folded into W / bias on the host.
 //
-// Warp roles (192 threads, 1 CTA / SM, persistent over tiles):
+// Warp roles (352 threads, 1 CTA / SM, persistent over tiles):
 //   warp 0     : TMA producer (one elected lane)           smem ring  full[]/empty[]
 //   warp 1     : TMEM allocator + tcgen05.mma issuer        TMEM ring  tmem_full[]/tmem_empty[] (2 accumulators)
-//   warps 2..5 : epilogue, TMEM -> registers -> bias/residual/ReLU -> global
+//   warps 2..9 : epilogue math: TMEM -> registers -> bias/residual/ReLU -> bf16, IN PLACE in a 128B-swizzled
+//                staging tile of 128 rows x 64 channels (the residual was TMA-loaded into that same tile);
+//                two warps per TMEM lane quarter, each taking 32 of the 64 channels of a sub-tile
+//   warp 10    : epilogue DMA (one lane): TMA-loads the residual sub-tile ahead of the math warps and TMA-stores
+//                finished sub-tiles, so global traffic of the epilogue is full 128-byte rows, never per-thread rows
+// (fp32 output, used only by the tiny projector conv, keeps a direct per-thread store path.)
 #pragma once
 #include "ptx.cuh"
 
@@ -26,7 +31,11 @@ namespace bv {
 
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;  // 64 bf16 = one 128-byte swizzle span
-constexpr int kGemmThreads = 192;
+constexpr int kGemmThreads = 352;
+constexpr int kDmaWarp = 10;
+constexpr int kEpiWarps = 8;
+constexpr int kChunkCols = 64;                       // bf16 columns per staging sub-tile (128 bytes per row)
+constexpr int kStagingBytes = kBlockM * kChunkCols * 2;  // 16 KB
 constexpr int kABytes = kBlockM * kBlockK * 2;
 
 enum : int { kSegTiled = 0, kSegIm2col = 1 };
@@ -43,6 +52,8 @@ struct ConvSeg {
 struct ConvGemmParams {
     CUtensorMap tmA[2];
     CUtensorMap tmB[2];  // per-segment weights [N, taps*Cin], K-major
+    CUtensorMap tmOut;   // bf16 output [M, N], box 64 x 128, 128B swizzle (unused for fp32 output)
+    CUtensorMap tmRes;   // bf16 residual [M, N], same box (unused without residual)
     ConvSeg seg[2];
     int nseg;
     int Ho, Wo;  // output spatial size, to split m into (image, p, q)
@@ -55,30 +66,42 @@ struct ConvGemmParams {
     int out_fp32;
 };
 
-template <int BN>
+// BN = output channels per tile; STAGES = depth of the A/B smem ring; NBUF = epilogue staging tiles.
+// Memory-bound layers want bytes in flight (Little's law: ~2 us loaded latency x 44 GB/s per SM ~ 100 KB):
+// without a residual that is a deep A ring, with a residual (4x the A bytes) it is many staging tiles.
+template <int BN, int STAGES, int NBUF>
 struct ConvGemmCfg {
     static constexpr int kBBytes = BN * kBlockK * 2;
     static constexpr int kStageBytes = kABytes + kBBytes;
-    static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+    static constexpr int kStages = STAGES;
+    static constexpr int kBufs = NBUF;
     static constexpr int kTmemCols = 2 * BN;
-    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+    static constexpr int kNumBars = 2 * STAGES + 4 + 2 * NBUF;
+    static constexpr int kSmemBytes =
+        kStages * kStageBytes + NBUF * kStagingBytes + 1024 /*align slack*/ + kNumBars * 8 + 16;
+    static_assert(kSmemBytes <= 232448, "exceeds the 227 KB of shared memory a CTA may use");
 };
 
-template <int BN>
+template <int BN, int STAGES, int NBUF>
 __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
-    using Cfg = ConvGemmCfg<BN>;
+    using Cfg = ConvGemmCfg<BN, STAGES, NBUF>;
     constexpr int kStages = Cfg::kStages;
+    constexpr int kBufs = NBUF;
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* smem_a = smem;
     uint8_t* smem_b = smem + kStages * kABytes;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * Cfg::kStageBytes);
+    uint8_t* staging = smem + kStages * Cfg::kStageBytes;  // NBUF x 16 KB, 1024-byte aligned
+    uint64_t* bars = reinterpret_cast<uint64_t*>(staging + kBufs * kStagingBytes);
     uint64_t* full_bar = bars;
     uint64_t* empty_bar = bars + kStages;
     uint64_t* tmem_full = bars + 2 * kStages;
     uint64_t* tmem_empty = bars + 2 * kStages + 2;
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+    uint64_t* buf_ready = bars + 2 * kStages + 4;            // staging tile free (+ residual landed)  DMA -> math
+    uint64_t* buf_written = bars + 2 * kStages + 4 + kBufs;  // staging tile holds finished outputs   math -> DMA
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + Cfg::kNumBars);
+    constexpr int kChunks = BN / kChunkCols;
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -96,7 +119,11 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tmem_full[i], 1);
-            mbar_init(&tmem_empty[i], 4);  // one arrival per epilogue warp
+            mbar_init(&tmem_empty[i], kEpiWarps);  // one arrival per epilogue warp
+        }
+        for (int i = 0; i < kBufs; ++i) {
+            mbar_init(&buf_ready[i], 1);
+            mbar_init(&buf_written[i], kEpiWarps);
         }
         fence_barrier_init();
     }
@@ -187,8 +214,130 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
                 umma_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
             }
         }
+    } else if (warp == kDmaWarp) {
+        // ===================== epilogue DMA (residual prefetch + output stores) =====================
+        if (lane == 0 && !p.out_fp32) {
+            const bool has_res = p.residual != nullptr;
+            tma_prefetch_desc(&p.tmOut);
+            if (has_res) tma_prefetch_desc(&p.tmRes);
+            const int my_tiles = (num_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) /
+                                 static_cast<int>(gridDim.x);
+            const int total = my_tiles * kChunks;  // sub-tiles this CTA produces
+            auto coords = [&](int g, int& row0, int& col0) {
+                const int tile = static_cast<int>(blockIdx.x) + (g / kChunks) * static_cast<int>(gridDim.x);
+                const int m_blk = tile / p.num_n_blocks;
+                const int n_blk = tile - m_blk * p.num_n_blocks;
+                row0 = m_blk * kBlockM;
+                col0 = n_blk * BN + (g % kChunks) * kChunkCols;
+            };
+            auto prepare = [&](int g) {  // staging tile (g % NBUF) is free here: hand it to the math warps
+                const int b = g % kBufs;
+                if (has_res) {
+                    int row0, col0;
+                    coords(g, row0, col0);
+                    mbar_arrive_expect_tx(&buf_ready[b], kStagingBytes);
+                    tma_load_2d(&p.tmRes, &buf_ready[b], staging + b * kStagingBytes, col0, row0, kEvictFirst);
+                } else {
+                    mbar_arrive(&buf_ready[b]);
+                }
+            };
+            for (int g = 0; g < kBufs && g < total; ++g) prepare(g);
+            for (int g = 0; g < total; ++g) {
+                const int b = g % kBufs;
+                mbar_wait(&buf_written[b], (g / kBufs) & 1u);
+                int row0, col0;
+                coords(g, row0, col0);
+                tma_store_2d(&p.tmOut, staging + b * kStagingBytes, col0, row0);
+                tma_store_commit();
+                // Re-arm a staging tile once its store has finished READING smem.  With more than two tiles the
+                // re-arm lags one store behind, so this thread never waits on the store it has just issued.
+                constexpr int kLag = (kBufs > 2) ? 1 : 0;
+                if (g >= kLag && g - kLag + kBufs < total) {
+                    tma_store_wait_read<kLag>();
+                    prepare(g - kLag + kBufs);
+                }
+            }
+            tma_store_wait_all<0>();  // all global writes complete before the CTA may exit
+        }
+    } else if (!p.out_fp32) {
+        // ===================== epilogue math (warps 2..9), staged bf16 output =====================
+        const int quarter = warp & 3;        // TMEM lane quarter this warp may access
+        const int half = (warp - 2) >> 2;    // which 32 of the sub-tile's 64 channels this warp converts
+        const int r_in_tile = quarter * 32 + lane;
+        const bool has_res = p.residual != nullptr;
+        int it = 0;
+        int g = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+            const int m_blk = tile / p.num_n_blocks;
+            const int n_blk = tile - m_blk * p.num_n_blocks;
+            const int acc = it & 1;
+            const uint32_t acc_phase = (it >> 1) & 1u;
+            mbar_wait(&tmem_full[acc], acc_phase);
+            tc_fence_after();
+            const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
+                                   static_cast<uint32_t>(acc * BN);
+#pragma unroll 1
+            for (int c = 0; c < kChunks; ++c, ++g) {
+                const int b = g % kBufs;
+                uint8_t* row_ptr = staging + b * kStagingBytes + r_in_tile * 128;
+                mbar_wait(&buf_ready[b], (g / kBufs) & 1u);
+                {
+                    uint32_t v[32];
+                    tmem_ld_32x32(t_row + static_cast<uint32_t>(c * kChunkCols + half * 32), v);
+                    tmem_ld_wait();
+                    const int col = n_blk * BN + c * kChunkCols + half * 32;
+                    const float4* bp = reinterpret_cast<const float4*>(p.bias[0] + col);
+                    const float4* bp2 = (p.nseg > 1) ? reinterpret_cast<const float4*>(p.bias[1] + col) : nullptr;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {  // 16-byte group = 8 channels
+                        float f[8];
+#pragma unroll
+                        for (int q = 0; q < 2; ++q) {
+                            float4 bb = __ldg(bp + 2 * j + q);
+                            if (bp2) {
+                                const float4 b2 = __ldg(bp2 + 2 * j + q);
+                                bb.x += b2.x; bb.y += b2.y; bb.z += b2.z; bb.w += b2.w;
+                            }
+                            f[4 * q + 0] = __uint_as_float(v[8 * j + 4 * q + 0]) + bb.x;
+                            f[4 * q + 1] = __uint_as_float(v[8 * j + 4 * q + 1]) + bb.y;
+                            f[4 * q + 2] = __uint_as_float(v[8 * j + 4 * q + 2]) + bb.z;
+                            f[4 * q + 3] = __uint_as_float(v[8 * j + 4 * q + 3]) + bb.w;
+                        }
+                        // 128B swizzle: 16-byte group jj of row r lives at group position jj ^ (r & 7)
+                        const int jj = half * 4 + j;
+                        uint4* sp = reinterpret_cast<uint4*>(row_ptr + ((jj ^ (r_in_tile & 7)) << 4));
+                        if (has_res) {
+                            const uint4 rv = *sp;
+                            const uint32_t w[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                f[2 * e + 0] += __uint_as_float(w[e] << 16);
+                                f[2 * e + 1] += __uint_as_float(w[e] & 0xFFFF0000u);
+                            }
+                        }
+                        if (p.relu) {
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) f[e] = fmaxf(f[e], 0.0f);
+                        }
+                        uint32_t w[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const __nv_bfloat162 h2 = __floats2bfloat162_rn(f[2 * e], f[2 * e + 1]);
+                            w[e] = *reinterpret_cast<const uint32_t*>(&h2);
+                        }
+                        *sp = make_uint4(w[0], w[1], w[2], w[3]);
+                    }
+                }
+                fence_proxy_async_smem();  // generic-proxy writes -> visible to the TMA store (async proxy)
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&buf_written[b]);
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+        }
     } else {
-        // ===================== epilogue (warps 2..5) =====================
+        // ===================== epilogue, direct fp32 stores: warp pair splits the BN/32 column chunks =====
         const int quarter = warp & 3;  // TMEM lane quarter this warp may access
         int it = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
@@ -204,7 +353,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
             const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
                                    static_cast<uint32_t>(acc * BN);
 #pragma unroll 1
-            for (int c = 0; c < BN / 32; ++c) {
+            for (int c = (warp - 2) >> 2; c < BN / 32; c += 2) {
                 uint32_t v[32];
                 tmem_ld_32x32(t_row + static_cast<uint32_t>(c * 32), v);
                 // residual loads overlap the TMEM read

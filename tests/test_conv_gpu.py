@@ -100,12 +100,16 @@ def test_single_conv(env, case, integer):
         torch.testing.assert_close(out16.float(), ref16.float(), rtol=1e-2, atol=1e-2)
 
 
+@pytest.mark.parametrize("shape", [(2, 15, 512, 2048), (3, 30, 64, 256), (2, 30, 128, 512), (5, 30, 256, 1024)],
+                         ids=["k512n2048", "k64n256", "k128n512", "k256n1024"])
 @pytest.mark.parametrize("integer", [True, False], ids=["int", "gauss"])
-def test_residual_relu(env, integer):
+def test_residual_relu(env, integer, shape):
+    """conv3 + identity + ReLU: the residual tile is TMA-loaded into the staging buffer and updated in place.
+    The shapes select both residual kernel configurations (long-K 256-wide and short-K 128-wide tiles)."""
     N, lib, packing = env
     gen = torch.Generator().manual_seed(5)
     dev = torch.device("cuda:0")
-    B, H, cin, cout = 2, 15, 512, 2048
+    B, H, cin, cout = shape
     x = _make(gen, (B, H, H, cin), integer).to(torch.bfloat16).to(dev)
     w = (torch.randint(-1, 2, (cout, cin, 1, 1), generator=gen).float() if integer
          else torch.randn(cout, cin, 1, 1, generator=gen) * cin ** -0.5).to(torch.bfloat16)
@@ -118,6 +122,29 @@ def test_residual_relu(env, integer):
         assert torch.equal(out, ref)
     else:
         torch.testing.assert_close(out, ref, rtol=1e-4, atol=1e-4)
+    out16 = _conv_native(lib, N, x, conv, residual=res, relu=True, out_fp32=False)
+    if integer:
+        assert torch.equal(out16, ref.to(torch.bfloat16))
+    else:
+        torch.testing.assert_close(out16.float(), ref.to(torch.bfloat16).float(), rtol=1e-2, atol=1e-2)
+
+
+@pytest.mark.parametrize("cfg", [0, 1, 2, 3, 4])
+def test_every_kernel_configuration(env, cfg, monkeypatch):
+    """Force each <BN, STAGES, NBUF> instantiation on one shape (N=256 fits all tile widths), with a residual."""
+    N, lib, packing = env
+    monkeypatch.setenv("BV_FORCE_CFG", str(cfg))
+    gen = torch.Generator().manual_seed(13)
+    dev = torch.device("cuda:0")
+    B, H, cin, cout = 4, 30, 192, 256
+    x = torch.randint(-2, 3, (B, H, H, cin), generator=gen).float().to(torch.bfloat16).to(dev)
+    w = torch.randint(-1, 2, (cout, cin, 3, 3), generator=gen).float().to(torch.bfloat16)
+    b = torch.randint(-2, 3, (cout,), generator=gen).float()
+    res = torch.randint(-2, 3, (B, H, H, cout), generator=gen).float().to(torch.bfloat16).to(dev)
+    conv = packing.pack_single_conv(w, b, 1, 1, dev)
+    ref = torch.relu(_ref(x, w.to(dev), b.to(dev), 1, 1) + res.float()).to(torch.bfloat16)
+    out = _conv_native(lib, N, x, conv, residual=res, relu=True, out_fp32=False)
+    assert torch.equal(out, ref)
 
 
 @pytest.mark.parametrize("stride", [1, 2])
