@@ -516,6 +516,8 @@ static int build_plan(bv_handle* h, const void* frames, int dtype, int B, int C,
 int32_t bv_forward(bv_handle* h, const void* frames, int32_t dtype, int32_t B, int32_t C, int32_t H, int32_t W,
                    void* workspace, size_t workspace_bytes, const bv_outputs* out, bv_stream stream) {
     if (!h || !frames || !workspace || !out) return fail(BV_ERR_INVALID, "null argument");
+    if (!h->w.proj3_wt || !h->w.proj0.w || !h->w.stem_u8.w)
+        return fail(BV_ERR_INVALID, "this handle was created without image-model weights (scoring only)");
     if (B <= 0 || H <= 0 || W <= 0 || H % 32 || W % 32)
         return fail(BV_ERR_INVALID, "frames must be [B,C,H,W] with H, W multiples of 32 (got %dx%dx%dx%d)", B, C, H, W);
     if (!((dtype == BV_DTYPE_U8 && C == 1) || (dtype == BV_DTYPE_F32 && (C == 1 || C == 3))))
