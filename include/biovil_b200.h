@@ -66,6 +66,8 @@ typedef struct {
     bv_conv proj0;                     /* projector conv 2048->128 (+BN folded), ReLU */
     const float* proj3_wt;             /* projector conv 128->128 TRANSPOSED: fp32 [k][d] */
     const float* proj3_b;              /* fp32 [128] */
+    bv_conv stem_u8_k8;                /* stem for the fused 8-bit kernel: [64][64], k = r*8 + s (s = 7 and r = 7 zero),
+                                          1/255 folded in; w == NULL -> bv_forward uses gather + GEMM + max-pool */
 } bv_weights;
 
 /* Optional outputs of bv_forward; any pointer may be NULL. */

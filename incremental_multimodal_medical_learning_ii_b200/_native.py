@@ -47,7 +47,7 @@ class BvWeights(Structure):
     _fields_ = [("stem_u8", BvConv), ("stem_f1", BvConv), ("stem_f3", BvConv),
                 ("conv1", BvConv * BV_NUM_BLOCKS), ("conv2", BvConv * BV_NUM_BLOCKS),
                 ("conv3", BvConv * BV_NUM_BLOCKS), ("downsample", BvConv * BV_NUM_BLOCKS),
-                ("proj0", BvConv), ("proj3_wt", c_void_p), ("proj3_b", c_void_p)]
+                ("proj0", BvConv), ("proj3_wt", c_void_p), ("proj3_b", c_void_p), ("stem_u8_k8", BvConv)]
 
 
 class BvOutputs(Structure):

@@ -15,6 +15,7 @@
 #include "../../include/biovil_b200.h"
 #include "aux_kernels.cuh"
 #include "conv_gemm.cuh"
+#include "stem_fused.cuh"
 
 namespace {
 
@@ -137,6 +138,8 @@ int device_setup() {
         BV_FOR_EACH_CFG(BV_SET_ATTR)
 #undef BV_SET_ATTR
         BV_CUDA(cudaFuncSetAttribute(bv::head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
+        BV_CUDA(cudaFuncSetAttribute(bv::stem_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     bv::kStemSmemRequest));
         g_attr_set = true;
     }
     g_num_sms = prop.multiProcessorCount;
@@ -294,6 +297,8 @@ struct bv_handle {
     } key{};
     bool plan_valid = false;
     std::vector<ConvLaunch> convs;  // in execution order (stem GEMM first)
+    bv::StemParams stem{};          // fused 8-bit stem (valid when use_fused_stem)
+    bool use_fused_stem = false;
     const void* trunk = nullptr;    // final [B,h,w,2048] bf16
     int last_launches = 0;
     // optional per-launch timing (cudaEvents on the launch stream)
@@ -509,6 +514,20 @@ static int build_plan(bv_handle* h, const void* frames, int dtype, int B, int C,
         if (rc) return rc;
         h->convs.push_back(L);
     }
+    h->use_fused_stem = (dtype == BV_DTYPE_U8) && h->w.stem_u8_k8.w != nullptr && !env_flag("BV_NO_FUSED_STEM");
+    if (h->use_fused_stem) {
+        static_assert(bv::kStemSmemBytes <= bv::kStemSmemRequest, "stem smem request too small");
+        memset(&h->stem, 0, sizeof(h->stem));
+        int rc = make_tmap_2d(&h->stem.tmW, h->w.stem_u8_k8.w, 64, 64, 64, 64);
+        if (rc) return rc;
+        h->stem.bias = h->w.stem_u8_k8.bias;
+        h->stem.out = reinterpret_cast<__nv_bfloat16*>(buf_a);
+        h->stem.B = B;
+        h->stem.H = H;
+        h->stem.W = W;
+        h->stem.tiles_x = (W / 4) / bv::kStemPool;
+        h->stem.tiles_y = (H / 4) / bv::kStemPool;
+    }
     (void)frames;
     return BV_OK;
 }
@@ -547,39 +566,51 @@ int32_t bv_forward(bv_handle* h, const void* frames, int32_t dtype, int32_t B, i
     double pflops = 0, pbytes = 0;
     const int H2 = H / 2, W2 = W / 2, H4 = H / 4, W4 = W / 4;
     __nv_bfloat16* patches = reinterpret_cast<__nv_bfloat16*>(ws + lay.buf_a);
-    // 1. stem patch gather
-    {
-        const long long total = (long long)B * H2 * W2 * ((C == 3) ? 24 : 8);
-        const int blocks = (int)std::min<long long>((total + 255) / 256, (long long)g_num_sms * 16);
-        if (dtype == BV_DTYPE_U8)
-            bv::stem_patch_kernel<uint8_t, 1><<<blocks, 256, 0, st>>>(reinterpret_cast<const uint8_t*>(frames), patches,
-                                                                    B, H, W, H2, W2);
-        else if (C == 1)
-            bv::stem_patch_kernel<float, 1><<<blocks, 256, 0, st>>>(reinterpret_cast<const float*>(frames), patches, B,
-                                                                  H, W, H2, W2);
-        else
-            bv::stem_patch_kernel<float, 3><<<blocks, 256, 0, st>>>(reinterpret_cast<const float*>(frames), patches, B,
-                                                                  H, W, H2, W2);
+    if (h->use_fused_stem) {
+        // 1-3 fused: conv7x7/2 + BN + ReLU + max-pool in one kernel, frame bytes in, layer1 input out
+        h->stem.frames = reinterpret_cast<const uint8_t*>(frames);
+        const int tiles = B * h->stem.tiles_x * h->stem.tiles_y;
+        const int grid = std::min(tiles, 2 * g_num_sms);
+        bv::stem_fused_kernel<<<grid, bv::kStemThreads, bv::kStemSmemRequest, st>>>(h->stem);
         BV_CUDA(cudaGetLastError());
         ++launches;
-        const double px = (double)B * H2 * W2;
-        prof_mark(h, st, "stem_patch_gather", 0, (double)B * C * H * W * (dtype == BV_DTYPE_U8 ? 1 : 4) + px * ((C == 3) ? 192 : 64) * 2);
-    }
-    // 2. stem GEMM (+bias, ReLU)
-    if ((rc = launch_conv(h->convs[0], st))) return rc;
-    ++launches;
-    conv_cost(h->convs[0], &pflops, &pbytes, pname, sizeof(pname));
-    prof_mark(h, st, pname, pflops, pbytes);
-    // 3. max-pool into buf_a
-    {
-        const long long total = (long long)B * H4 * W4 * 8;
-        const int blocks = (int)std::min<long long>((total + 255) / 256, (long long)g_num_sms * 16);
-        bv::maxpool3x3s2_nhwc_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(ws + lay.buf_b),
-                                                             reinterpret_cast<__nv_bfloat16*>(ws + lay.buf_a), B, H2,
-                                                             W2, 64, H4, W4);
-        BV_CUDA(cudaGetLastError());
+        prof_mark(h, st, "stem_fused conv7x7+bn+relu+maxpool", 2.0 * B * H2 * W2 * 64 * 49,
+                  (double)B * H * W + (double)B * H4 * W4 * 64 * 2);
+    } else {
+        // 1. stem patch gather
+        {
+            const long long total = (long long)B * H2 * W2 * ((C == 3) ? 24 : 8);
+            const int blocks = (int)std::min<long long>((total + 255) / 256, (long long)g_num_sms * 16);
+            if (dtype == BV_DTYPE_U8)
+                bv::stem_patch_kernel<uint8_t, 1><<<blocks, 256, 0, st>>>(reinterpret_cast<const uint8_t*>(frames), patches,
+                                                                        B, H, W, H2, W2);
+            else if (C == 1)
+                bv::stem_patch_kernel<float, 1><<<blocks, 256, 0, st>>>(reinterpret_cast<const float*>(frames), patches, B,
+                                                                      H, W, H2, W2);
+            else
+                bv::stem_patch_kernel<float, 3><<<blocks, 256, 0, st>>>(reinterpret_cast<const float*>(frames), patches, B,
+                                                                      H, W, H2, W2);
+            BV_CUDA(cudaGetLastError());
+            ++launches;
+            const double px = (double)B * H2 * W2;
+            prof_mark(h, st, "stem_patch_gather", 0, (double)B * C * H * W * (dtype == BV_DTYPE_U8 ? 1 : 4) + px * ((C == 3) ? 192 : 64) * 2);
+        }
+        // 2. stem GEMM (+bias, ReLU)
+        if ((rc = launch_conv(h->convs[0], st))) return rc;
         ++launches;
-        prof_mark(h, st, "maxpool3x3s2", 0, (double)B * H2 * W2 * 64 * 2 + (double)B * H4 * W4 * 64 * 2);
+        conv_cost(h->convs[0], &pflops, &pbytes, pname, sizeof(pname));
+        prof_mark(h, st, pname, pflops, pbytes);
+        // 3. max-pool into buf_a
+        {
+            const long long total = (long long)B * H4 * W4 * 8;
+            const int blocks = (int)std::min<long long>((total + 255) / 256, (long long)g_num_sms * 16);
+            bv::maxpool3x3s2_nhwc_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(ws + lay.buf_b),
+                                                                 reinterpret_cast<__nv_bfloat16*>(ws + lay.buf_a), B, H2,
+                                                                 W2, 64, H4, W4);
+            BV_CUDA(cudaGetLastError());
+            ++launches;
+            prof_mark(h, st, "maxpool3x3s2", 0, (double)B * H2 * W2 * 64 * 2 + (double)B * H4 * W4 * 64 * 2);
+        }
     }
     // 4. bottleneck convs + projector conv
     for (size_t i = 1; i < h->convs.size(); ++i) {

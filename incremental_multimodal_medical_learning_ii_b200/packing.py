@@ -57,6 +57,10 @@ class PackedWeights:
         self.struct.stem_f3 = self._matrix(torch.nn.functional.pad(w3, (0, 192 - 147)), b, cin=192)
         self.struct.stem_f1 = self._matrix(torch.nn.functional.pad(w1, (0, 64 - 49)), b, cin=64)
         self.struct.stem_u8 = self._matrix(torch.nn.functional.pad(w1 / 255.0, (0, 64 - 49)), b, cin=64)
+        # fused stem kernel: k = r*8 + s, window column s = 7 and row r = 7 carry zero weights
+        w8 = torch.zeros(64, 8, 8, dtype=w.dtype)
+        w8[:, :7, :7] = w.sum(dim=1) / 255.0
+        self.struct.stem_u8_k8 = self._matrix(w8.reshape(64, 64), b, cin=64)
 
         # ---- bottlenecks ------------------------------------------------------------------------------------
         for i, (p, stride) in enumerate(block_names()):

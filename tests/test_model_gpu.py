@@ -152,3 +152,25 @@ def test_guards(setup):
     with pytest.raises(AssertionError):
         m.get_patchwise_projected_embeddings(torch.zeros(1, 3, 64, 64, device=DEV), normalize=True)
     m.eval()
+
+
+def test_fused_stem_matches_unfused_path(setup, monkeypatch):
+    """The fused 8-bit stem kernel (conv7x7 + BN + ReLU + max-pool on tcgen05) against the gather + GEMM + max-pool
+    path it replaces: same bf16 rounding points, only the fp32 summation order differs."""
+    from incremental_multimodal_medical_learning_ii_b200 import frames as FR
+    variant, m, sd, golden = setup
+    for (B, H, W, kind) in ((3, 96, 160, "structured"), (2, 480, 480, "iid"), (1, 32, 32, "iid")):
+        fr = FR.synthetic_frames_u8(7, B, max(H, W), kind=kind, seed=2)[:, :, :H, :W].contiguous().to(DEV)
+        m._engine = None
+        fused = m(fr).projected_global_embedding.clone()
+        trunk_f = m(fr).patch_embedding.clone()
+        monkeypatch.setenv("BV_NO_FUSED_STEM", "1")
+        m._engine = None
+        plain = m(fr).projected_global_embedding.clone()
+        trunk_p = m(fr).patch_embedding.clone()
+        monkeypatch.delenv("BV_NO_FUSED_STEM")
+        m._engine = None
+        rel = ((fused - plain).norm() / plain.norm()).item()
+        relt = ((trunk_f - trunk_p).norm() / trunk_p.norm()).item()
+        print(f"[{variant}] fused vs unfused stem {B}x{H}x{W}: embedding rel {rel:.2e}, trunk rel {relt:.2e}")
+        assert rel <= 2e-3 and relt <= 5e-3

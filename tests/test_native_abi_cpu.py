@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol(native_lib):
 def test_struct_layouts_match_header(native_lib):
     from incremental_multimodal_medical_learning_ii_b200 import _native as N
     assert ctypes.sizeof(N.BvConv) == 40
-    assert ctypes.sizeof(N.BvWeights) == 40 * (3 + 4 * 16 + 1) + 16
+    assert ctypes.sizeof(N.BvWeights) == 40 * (3 + 4 * 16 + 1) + 16 + 40
     assert ctypes.sizeof(N.BvOutputs) == 80
     assert ctypes.sizeof(N.BvLaunchInfo) == 88
 
