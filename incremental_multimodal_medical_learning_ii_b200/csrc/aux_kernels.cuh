@@ -241,6 +241,43 @@ struct HeadParams {
     const float* heat_t;  // [L, 128] unit text vectors for heat-maps
 };
 
+// Global-embedding-only variant: the projector's last conv and the patch mean are both linear, so
+//   mean_p (W2 h_p + b2) = W2 (mean_p h_p) + b2
+// and the 225 matrix-vector products collapse into one (model.py:144-145 computed per patch only because the
+// reference materialises the patch embeddings).  Used when neither patch embeddings nor heat-maps are requested.
+__global__ void __launch_bounds__(128) head_global_kernel(const HeadParams hp) {
+    __shared__ float hbar[kEmbDim];
+    __shared__ float gvec[kEmbDim];
+    const int b = blockIdx.x;
+    const int d = threadIdx.x;
+    const int lane = d & 31;
+    const float* hp_b = hp.hid + static_cast<size_t>(b) * hp.P * kEmbDim + d;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    int pidx = 0;
+    for (; pidx + 4 <= hp.P; pidx += 4) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) acc[u] += __ldg(hp_b + static_cast<size_t>(pidx + u) * kEmbDim);
+    }
+    for (; pidx < hp.P; ++pidx) acc[0] += __ldg(hp_b + static_cast<size_t>(pidx) * kEmbDim);
+    hbar[d] = ((acc[0] + acc[1]) + (acc[2] + acc[3])) / static_cast<float>(hp.P);
+    __syncthreads();
+    float g = __ldg(hp.b2 + d);
+#pragma unroll 8
+    for (int k = 0; k < kEmbDim; ++k) g = fmaf(hbar[k], __ldg(hp.w2t + k * kEmbDim + d), g);
+    if (hp.global_out) hp.global_out[static_cast<size_t>(b) * kEmbDim + d] = g;
+    gvec[d] = g;
+    __syncthreads();
+    if (hp.yn != nullptr && d < 32) {
+        float4 x = reinterpret_cast<const float4*>(gvec)[lane];
+        float ss = x.x * x.x + x.y * x.y + x.z * x.z + x.w * x.w;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, off);
+        const float nrm = sqrtf(ss);
+        x = make_float4(x.x / nrm, x.y / nrm, x.z / nrm, x.w / nrm);
+        score_image_warp(x, hp.yn, hp.L, hp.NPP, b, hp.score, lane);
+    }
+}
+
 __global__ void __launch_bounds__(256) head_kernel(const HeadParams hp) {
     extern __shared__ float hsm[];
     float* w2t = hsm;                         // 128*128

@@ -74,14 +74,16 @@ int make_tmap_2d(CUtensorMap* tm, const void* base, uint64_t inner, uint64_t out
 
 // NHWC activation tensor [N][H][W][C] seen by TMA as (C, W, H, N); 128 output pixels x 64 channels per load.
 int make_tmap_im2col(CUtensorMap* tm, const void* base, int N, int H, int W, int C, int R, int S, int stride,
-                     int pad) {
+                     int pad, bool wide = false) {
     cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
     cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
     int lower[2] = {-pad, -pad};
     int upper[2] = {pad - (S - 1), pad - (R - 1)};
+    if (wide) upper[0] = pad;  // window origins -pad .. W-1+pad: the zero-padded image row, linear in memory order
     cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
     CUresult r = g_encode_im2col(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides,
-                                 lower, upper, bv::kBlockK, bv::kBlockM, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                 lower, upper, bv::kBlockK, wide ? bv::kWideRows : bv::kBlockM, estr,
+                                 CU_TENSOR_MAP_INTERLEAVE_NONE,
                                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS)
@@ -102,10 +104,12 @@ struct ConvOperand {
 };
 
 // Kernel configurations <BN, STAGES, NBUF> (see ConvGemmCfg): picked per layer by arithmetic intensity.
-enum ConvCfg { kCfg256Deep = 0, kCfg256Res, kCfg128Res, kCfg128Deep, kCfg64, kNumCfg };
-#define BV_FOR_EACH_CFG(X) X(kCfg256Deep, 256, 4, 2) X(kCfg256Res, 256, 3, 4) X(kCfg128Res, 128, 3, 7) \
-                           X(kCfg128Deep, 128, 6, 2) X(kCfg64, 64, 8, 2)
-const int kCfgBN[kNumCfg] = {256, 256, 128, 128, 64};
+enum ConvCfg { kCfg256Deep = 0, kCfg256Res, kCfg128Res, kCfg128Deep, kCfg64, kCfg64BRes, kCfg64Wide, kNumCfg };
+#define BV_FOR_EACH_CFG(X)                                                                                        \
+    X(kCfg256Deep, 256, 4, 2, false, false) X(kCfg256Res, 256, 3, 4, false, false)                                \
+    X(kCfg128Res, 128, 3, 7, false, false) X(kCfg128Deep, 128, 6, 2, false, false) X(kCfg64, 64, 8, 2, false, false) \
+    X(kCfg64BRes, 64, 6, 2, true, false) X(kCfg64Wide, 64, 6, 2, true, true)
+const int kCfgBN[kNumCfg] = {256, 256, 128, 128, 64, 64, 64};
 
 struct ConvLaunch {
     bv::ConvGemmParams p;
@@ -132,9 +136,10 @@ int device_setup() {
     int rc = resolve_driver();
     if (rc) return rc;
     if (!g_attr_set) {
-#define BV_SET_ATTR(id, BN, ST, NB)                                                                            \
-    BV_CUDA(cudaFuncSetAttribute(bv::conv_gemm_kernel<BN, ST, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                 bv::ConvGemmCfg<BN, ST, NB>::kSmemBytes));
+#define BV_SET_ATTR(id, BN, ST, NB, BR, WD)                                                         \
+    BV_CUDA(cudaFuncSetAttribute(bv::conv_gemm_kernel<BN, ST, NB, BR, WD>,                          \
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize,                       \
+                                 bv::ConvGemmCfg<BN, ST, NB, BR, WD>::kSmemBytes));
         BV_FOR_EACH_CFG(BV_SET_ATTR)
 #undef BV_SET_ATTR
         BV_CUDA(cudaFuncSetAttribute(bv::head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
@@ -165,16 +170,23 @@ int build_conv(ConvLaunch* L, int B, const ConvOperand* ops, int nops, const voi
     // 128-wide tile with either a deep A ring (no residual) or many staging tiles (residual stream).
     int cfg;
     const bool res_stream = residual && !out_fp32;
-    if (N % 128 != 0) cfg = kCfg64;
+    if (N % 128 != 0) cfg = (N == 64 && total_kblocks <= bv::kMaxResidentKB && !env_flag("BV_NO_BRES")) ? kCfg64BRes : kCfg64;
     else if (N % 256 != 0) cfg = kCfg128Deep;
     else if (total_kblocks >= 8) cfg = res_stream ? kCfg256Res : kCfg256Deep;
     else cfg = res_stream ? kCfg128Res : kCfg256Res;  // short K: HBM-bound, wants staging depth
+    const bool wide_ok = nops == 1 && c0.r == 3 && c0.s == 3 && c0.stride == 1 && c0.pad == 1 && !residual &&
+                         !out_fp32 && N == 64 && total_kblocks <= bv::kMaxResidentKB;
+    if (cfg == kCfg64BRes && wide_ok && !env_flag("BV_NO_WIDE")) cfg = kCfg64Wide;
     if (const char* force = getenv("BV_FORCE_CFG")) {
         const int f = atoi(force);
-        if (f >= 0 && f < kNumCfg && N % kCfgBN[f] == 0) cfg = f;
+        if (f >= 0 && f < kNumCfg && N % kCfgBN[f] == 0 &&
+            (f != kCfg64BRes || (N == 64 && total_kblocks <= bv::kMaxResidentKB)))
+            cfg = f;
     }
+    if (cfg == kCfg64Wide && !wide_ok) cfg = kCfg64;
+    const bool wide = cfg == kCfg64Wide;
     const int bn = kCfgBN[cfg];
-    const long long M = (long long)B * Ho * Wo;
+    const long long M = wide ? (long long)B * Ho * (Wo + 2) : (long long)B * Ho * Wo;
     if (M <= 0 || M > 0x7fffffffLL - 256) return fail(BV_ERR_INVALID, "M=%lld out of range", M);
     const bool force_im2col = env_flag("BV_FORCE_IM2COL");
     for (int i = 0; i < nops; ++i) {
@@ -190,19 +202,20 @@ int build_conv(ConvLaunch* L, int B, const ConvOperand* ops, int nops, const voi
         sg.stride = c.stride;
         sg.lower = -c.pad;
         const bool plain = (c.r == 1 && c.s == 1 && c.stride == 1 && c.pad == 0);
-        sg.mode = (plain && !force_im2col) ? bv::kSegTiled : bv::kSegIm2col;
+        sg.mode = wide ? bv::kSegWide : ((plain && !force_im2col) ? bv::kSegTiled : bv::kSegIm2col);
         int rc;
         if (sg.mode == bv::kSegTiled) {
             rc = make_tmap_2d(&p.tmA[i], ops[i].x, (uint64_t)c.cin, (uint64_t)M, bv::kBlockK, bv::kBlockM);
         } else {
-            rc = make_tmap_im2col(&p.tmA[i], ops[i].x, B, ops[i].H, ops[i].W, c.cin, c.r, c.s, c.stride, c.pad);
+            rc = make_tmap_im2col(&p.tmA[i], ops[i].x, B, ops[i].H, ops[i].W, c.cin, c.r, c.s, c.stride, c.pad, wide);
         }
         if (rc) return rc;
         rc = make_tmap_2d(&p.tmB[i], c.w, (uint64_t)c.r * c.s * c.cin, (uint64_t)N, bv::kBlockK, (uint32_t)bn);
         if (rc) return rc;
         p.bias[i] = c.bias;
     }
-    if (!out_fp32) {
+    p.Wwide = wide ? Wo + 2 : 0;
+    if (!out_fp32 && !wide) {
         int rc = make_tmap_2d(&p.tmOut, out, (uint64_t)N, (uint64_t)M, bv::kChunkCols, bv::kBlockM);
         if (rc) return rc;
         if (residual) {
@@ -223,6 +236,12 @@ int build_conv(ConvLaunch* L, int B, const ConvOperand* ops, int nops, const voi
     p.out_fp32 = out_fp32;
     L->bn = bn;
     L->cfg = cfg;
+    // K steps (16 wide) per tile = 4 * total_kblocks; use every accumulator the TMEM stage offers unless the K
+    // loop is too short to need it (each extra accumulator costs one more TMEM read per output in the epilogue).
+    int nacc = 256 / bn;
+    if (total_kblocks < 2) nacc = std::min(nacc, 2);
+    if (const char* f = getenv("BV_FORCE_NACC")) nacc = std::max(1, std::min(256 / bn, atoi(f)));
+    p.nacc = nacc;
     const long long tiles = (long long)p.num_m_blocks * p.num_n_blocks;
     L->grid = (int)std::min<long long>(tiles, g_num_sms);
     return BV_OK;
@@ -230,10 +249,10 @@ int build_conv(ConvLaunch* L, int B, const ConvOperand* ops, int nops, const voi
 
 int launch_conv(const ConvLaunch& L, cudaStream_t st) {
     switch (L.cfg) {
-#define BV_LAUNCH(id, BN, ST, NB)                                                                                  \
-    case id:                                                                                                       \
-        bv::conv_gemm_kernel<BN, ST, NB><<<L.grid, bv::kGemmThreads, bv::ConvGemmCfg<BN, ST, NB>::kSmemBytes, st>>>( \
-            L.p);                                                                                                  \
+#define BV_LAUNCH(id, BN, ST, NB, BR, WD)                                                                 \
+    case id:                                                                                              \
+        bv::conv_gemm_kernel<BN, ST, NB, BR, WD>                                                          \
+            <<<L.grid, bv::kGemmThreads, bv::ConvGemmCfg<BN, ST, NB, BR, WD>::kSmemBytes, st>>>(L.p);     \
         break;
         BV_FOR_EACH_CFG(BV_LAUNCH)
 #undef BV_LAUNCH
@@ -653,7 +672,10 @@ int32_t bv_forward(bv_handle* h, const void* frames, int32_t dtype, int32_t B, i
         hp.heat_out = out->heat;
         hp.heat_t = h->heat_t;
         const size_t smem = (size_t)(bv::kEmbDim * bv::kEmbDim + 2 * bv::kEmbDim + 8 + 4 * bv::kEmbDim) * sizeof(float);
-        bv::head_kernel<<<B, 256, smem, st>>>(hp);
+        if (!out->patch_emb && !out->heat)
+            bv::head_global_kernel<<<B, 128, 0, st>>>(hp);
+        else
+            bv::head_kernel<<<B, 256, smem, st>>>(hp);
         BV_CUDA(cudaGetLastError());
         ++launches;
         prof_mark(h, st, "head_score", 2.0 * B * P * 128 * 128, (double)B * P * 128 * 4);

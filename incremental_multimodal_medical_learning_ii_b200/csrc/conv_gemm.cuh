@@ -11,6 +11,13 @@
 // downsample branch is folded into conv3 (weights concatenated along K, biases summed), which removes the
 // identity tensor's write + read.
 //
+// kSegWide (3x3, stride 1, pad 1): the nine taps of a tile are NOT nine loads.  The im2col bounding box is widened by
+// the padding on both sides, so the GEMM rows enumerate (image, row, column -1 .. W) and consecutive rows are
+// consecutive pixels of the zero-padded image row.  One 130-pixel load per filter ROW then serves its three
+// horizontal taps: tap s is the same smem tile read through a descriptor whose start is shifted by s pixel rows
+// (128 B each; the swizzle follows absolute smem address bits, so base_offset stays 0).  A-tile fill traffic drops 3x; the two extra columns per image
+// row are computed and dropped in the epilogue.
+//
 // Replaces (reference): torch.nn.Conv2d + BatchNorm2d + ReLU (+ residual add) as executed by torchvision
 // Bottleneck.forward under health_multimodal/image/model/resnet.py:34-42 and the projector's first conv,
 // health_multimodal/image/model/modules.py:43-46.  BatchNorm (eval) is folded into W / bias on the host.
@@ -38,7 +45,9 @@ constexpr int kChunkCols = 64;                       // bf16 columns per staging
 constexpr int kStagingBytes = kBlockM * kChunkCols * 2;  // 16 KB
 constexpr int kABytes = kBlockM * kBlockK * 2;
 
-enum : int { kSegTiled = 0, kSegIm2col = 1 };
+enum : int { kSegTiled = 0, kSegIm2col = 1, kSegWide = 2 };
+constexpr int kWideRows = kBlockM + 2;                 // pixels per wide A tile: 128 outputs + 2 for the horizontal taps
+constexpr int kWideABytes = 17 * 1024;                 // 130 x 128 B rounded up to the 1024-byte swizzle period
 
 struct ConvSeg {
     int kblocks;  // taps * (Cin / 64)
@@ -57,42 +66,58 @@ struct ConvGemmParams {
     ConvSeg seg[2];
     int nseg;
     int Ho, Wo;  // output spatial size, to split m into (image, p, q)
-    int M, N;
+    int M, N;    // GEMM rows (for kSegWide: rows of the WIDENED pixel space, Wo + 2 per image row) and columns
+    int Wwide;   // Wo + 2 in kSegWide mode, else 0
     int num_m_blocks, num_n_blocks;
     const float* bias[2];           // per-segment [N] fp32 (summed)
     const __nv_bfloat16* residual;  // [M, N] or nullptr
     void* out;                      // [M, N] bf16 (or fp32 when out_fp32)
     int relu;
     int out_fp32;
+    int nacc;  // independent TMEM accumulators the K steps are dealt over (1 .. 256/BN); summed in the epilogue
 };
 
 // BN = output channels per tile; STAGES = depth of the A/B smem ring; NBUF = epilogue staging tiles.
 // Memory-bound layers want bytes in flight (Little's law: ~2 us loaded latency x 44 GB/s per SM ~ 100 KB):
 // without a residual that is a deep A ring, with a residual (4x the A bytes) it is many staging tiles.
-template <int BN, int STAGES, int NBUF>
+// BRES = the whole weight panel of the tile column (<= kMaxResidentKB k-blocks) is loaded into smem ONCE per CTA and
+// only A tiles stream through the ring: for the narrow layer1 convs the per-tile weight re-fetch is a third of
+// the L2->SM traffic, and those layers are L2-bandwidth-bound.
+constexpr int kMaxResidentKB = 9;
+
+template <int BN, int STAGES, int NBUF, bool BRES = false, bool WIDE = false>
 struct ConvGemmCfg {
+    static_assert(!WIDE || BRES, "the wide 3x3 mode keeps the weights resident");
     static constexpr int kBBytes = BN * kBlockK * 2;
-    static constexpr int kStageBytes = kABytes + kBBytes;
+    static constexpr int kAStage = WIDE ? kWideABytes : kABytes;
+    static constexpr int kStageBytes = kAStage + (BRES ? 0 : kBBytes);
+    static constexpr int kResidentBytes = BRES ? kMaxResidentKB * kBBytes : 0;
     static constexpr int kStages = STAGES;
     static constexpr int kBufs = NBUF;
-    static constexpr int kTmemCols = 2 * BN;
-    static constexpr int kNumBars = 2 * STAGES + 4 + 2 * NBUF;
+    // Back-to-back tcgen05.mma into the SAME accumulator serialise on the accumulate latency (~120 cycles), which
+    // is 4x the work of a 128x64x16 MMA.  The 512 TMEM columns are therefore always fully used: two accumulator
+    // stages of 256 columns, each holding 256/BN partial accumulators that take the K steps round-robin.
+    static constexpr int kMaxAcc = 256 / BN;
+    static constexpr int kAccStageCols = 256;
+    static constexpr int kTmemCols = 512;
+    static constexpr int kNumBars = 2 * STAGES + 4 + 2 * NBUF + 1;
     static constexpr int kSmemBytes =
-        kStages * kStageBytes + NBUF * kStagingBytes + 1024 /*align slack*/ + kNumBars * 8 + 16;
+        kStages * kStageBytes + kResidentBytes + NBUF * kStagingBytes + 1024 /*align slack*/ + kNumBars * 8 + 16;
     static_assert(kSmemBytes <= 232448, "exceeds the 227 KB of shared memory a CTA may use");
 };
 
-template <int BN, int STAGES, int NBUF>
+template <int BN, int STAGES, int NBUF, bool BRES = false, bool WIDE = false>
 __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
-    using Cfg = ConvGemmCfg<BN, STAGES, NBUF>;
+    using Cfg = ConvGemmCfg<BN, STAGES, NBUF, BRES, WIDE>;
+    constexpr int kAStage = Cfg::kAStage;
     constexpr int kStages = Cfg::kStages;
     constexpr int kBufs = NBUF;
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* smem_a = smem;
-    uint8_t* smem_b = smem + kStages * kABytes;
-    uint8_t* staging = smem + kStages * Cfg::kStageBytes;  // NBUF x 16 KB, 1024-byte aligned
+    uint8_t* smem_b = smem + kStages * kAStage;  // per-stage B tiles, or the resident weight panel when BRES
+    uint8_t* staging = smem + kStages * Cfg::kStageBytes + Cfg::kResidentBytes;  // NBUF x 16 KB, 1024-byte aligned
     uint64_t* bars = reinterpret_cast<uint64_t*>(staging + kBufs * kStagingBytes);
     uint64_t* full_bar = bars;
     uint64_t* empty_bar = bars + kStages;
@@ -100,13 +125,16 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
     uint64_t* tmem_empty = bars + 2 * kStages + 2;
     uint64_t* buf_ready = bars + 2 * kStages + 4;            // staging tile free (+ residual landed)  DMA -> math
     uint64_t* buf_written = bars + 2 * kStages + 4 + kBufs;  // staging tile holds finished outputs   math -> DMA
+    uint64_t* bres_bar = bars + 2 * kStages + 4 + 2 * kBufs;  // resident weight panel landed (BRES only)
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + Cfg::kNumBars);
     constexpr int kChunks = BN / kChunkCols;
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int num_tiles = p.num_m_blocks * p.num_n_blocks;
-    const int total_kb = p.seg[0].kblocks + (p.nseg > 1 ? p.seg[1].kblocks : 0);
+    // ring stages consumed per tile (kSegWide: one per filter row and channel block) / resident weight k-blocks
+    const int total_kb = WIDE ? 3 * p.seg[0].cblocks : p.seg[0].kblocks + (p.nseg > 1 ? p.seg[1].kblocks : 0);
+    const int total_wkb = p.seg[0].kblocks + (p.nseg > 1 ? p.seg[1].kblocks : 0);
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&p.tmA[0]);
@@ -125,6 +153,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
             mbar_init(&buf_ready[i], 1);
             mbar_init(&buf_written[i], kEpiWarps);
         }
+        mbar_init(bres_bar, 1);
         fence_barrier_init();
     }
     if (warp == 1) {
@@ -138,88 +167,160 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
 
     if (warp == 0) {
         // ===================== TMA producer =====================
-        if (lane == 0) {
-            int stage = 0;
-            uint32_t phase = 0;
-            const int hw = p.Ho * p.Wo;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                const int m_blk = tile / p.num_n_blocks;
-                const int n_blk = tile - m_blk * p.num_n_blocks;
-                const int m0 = m_blk * kBlockM;
-                const int img = m0 / hw;
-                const int rem = m0 - img * hw;
-                const int op = rem / p.Wo;
-                const int oq = rem - op * p.Wo;
-                for (int s = 0; s < p.nseg; ++s) {
-                    const ConvSeg sg = p.seg[s];
-                    int tap = 0, cb = 0, kofs = 0;
-                    for (int kb = 0; kb < sg.kblocks; ++kb) {
+        // The whole warp runs the loop (all values stay warp-uniform, so the TMA operands live in uniform
+        // registers); one elected lane issues.  Running the loop under `if (lane == 0)` instead makes the
+        // compiler wrap every UTMALDG / UTCHMMA in an ELECT + R2UR.BROADCAST + BRA.U.ANY waterfall.
+        int stage = 0;
+        uint32_t phase = 0;
+        const int hw = p.Ho * p.Wo;
+        if constexpr (BRES) {
+            // every tile of this CTA uses the same weight panel (the host only picks BRES when N == BN)
+            if (elect_one()) {
+                mbar_arrive_expect_tx(bres_bar, static_cast<uint32_t>(total_wkb) * Cfg::kBBytes);
+                int slot = 0;
+                for (int s = 0; s < p.nseg; ++s)
+                    for (int kb = 0; kb < p.seg[s].kblocks; ++kb, ++slot)
+                        tma_load_2d(&p.tmB[s], bres_bar, smem_b + slot * Cfg::kBBytes, kb * kBlockK, 0, kEvictLast);
+            }
+            __syncwarp();
+        }
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            const int m_blk = tile / p.num_n_blocks;
+            const int n_blk = tile - m_blk * p.num_n_blocks;
+            const int m0 = m_blk * kBlockM;
+            if constexpr (WIDE) {
+                // rows enumerate (image, p, q') with q' = -1 .. Wo: window origin of row m0 is (q' - 1, p - 1)
+                const int hww = p.Ho * p.Wwide;
+                const int img = m0 / hww;
+                const int rem = m0 - img * hww;
+                const int op = rem / p.Wwide;
+                const int oq = rem - op * p.Wwide;
+                const int cblocks = p.seg[0].cblocks;
+                for (int tr = 0; tr < 3; ++tr) {
+                    for (int cb = 0; cb < cblocks; ++cb) {
                         mbar_wait(&empty_bar[stage], phase ^ 1u);
-                        mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
-                        void* dst_a = smem_a + stage * kABytes;
-                        if (sg.mode == kSegTiled) {
-                            tma_load_2d(&p.tmA[s], &full_bar[stage], dst_a, cb * kBlockK, m0, kEvictNormal);
-                        } else {
-                            const int r = tap / sg.S;
-                            const int ss = tap - r * sg.S;
-                            tma_load_im2col_4d(&p.tmA[s], &full_bar[stage], dst_a, cb * kBlockK,
-                                               sg.lower + oq * sg.stride, sg.lower + op * sg.stride, img,
-                                               static_cast<uint16_t>(ss), static_cast<uint16_t>(r), kEvictNormal);
+                        if (elect_one()) {
+                            mbar_arrive_expect_tx(&full_bar[stage], kWideRows * 128);
+                            tma_load_im2col_4d(&p.tmA[0], &full_bar[stage], smem_a + stage * kAStage, cb * kBlockK,
+                                               oq - 1, op - 1, img, 0, static_cast<uint16_t>(tr), kEvictNormal);
                         }
-                        tma_load_2d(&p.tmB[s], &full_bar[stage], smem_b + stage * Cfg::kBBytes, kofs, n_blk * BN,
-                                    kEvictLast);
-                        kofs += kBlockK;
-                        if (++cb == sg.cblocks) {
-                            cb = 0;
-                            ++tap;
-                        }
+                        __syncwarp();
                         if (++stage == kStages) {
                             stage = 0;
                             phase ^= 1u;
                         }
                     }
                 }
+                continue;
             }
-        }
-    } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        if (lane == 0) {
-            constexpr uint32_t idesc = umma_idesc_bf16_f32(kBlockM, BN);
-            int stage = 0;
-            uint32_t phase = 0;
-            int it = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-                const int acc = it & 1;
-                const uint32_t acc_phase = (it >> 1) & 1u;
-                mbar_wait(&tmem_empty[acc], acc_phase ^ 1u);
-                tc_fence_after();
-                const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
-                for (int kb = 0; kb < total_kb; ++kb) {
-                    mbar_wait(&full_bar[stage], phase);
-                    tc_fence_after();
-                    const uint64_t adesc = umma_desc_k_sw128(smem_u32(smem_a + stage * kABytes));
-                    const uint64_t bdesc = umma_desc_k_sw128(smem_u32(smem_b + stage * Cfg::kBBytes));
-#pragma unroll
-                    for (int k = 0; k < kBlockK / 16; ++k) {
-                        // +32 bytes per UMMA_K=16 step inside the 128-byte swizzle span (>>4 encoded => +2)
-                        umma_bf16_ss(d_tmem, adesc + static_cast<uint64_t>(2 * k), bdesc + static_cast<uint64_t>(2 * k),
-                                     idesc, (kb | k) != 0 ? 1u : 0u);
+            const int img = m0 / hw;
+            const int rem = m0 - img * hw;
+            const int op = rem / p.Wo;
+            const int oq = rem - op * p.Wo;
+            for (int s = 0; s < p.nseg; ++s) {
+                const ConvSeg sg = p.seg[s];
+                int tap = 0, cb = 0, kofs = 0, tr = 0, ts = 0;
+                for (int kb = 0; kb < sg.kblocks; ++kb) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1u);
+                    if (elect_one()) {
+                        mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+                        void* dst_a = smem_a + stage * kAStage;
+                        if (sg.mode == kSegTiled) {
+                            tma_load_2d(&p.tmA[s], &full_bar[stage], dst_a, cb * kBlockK, m0, kEvictNormal);
+                        } else {
+                            tma_load_im2col_4d(&p.tmA[s], &full_bar[stage], dst_a, cb * kBlockK,
+                                               sg.lower + oq * sg.stride, sg.lower + op * sg.stride, img,
+                                               static_cast<uint16_t>(ts), static_cast<uint16_t>(tr), kEvictNormal);
+                        }
+                        if constexpr (!BRES)
+                            tma_load_2d(&p.tmB[s], &full_bar[stage], smem_b + stage * Cfg::kBBytes, kofs, n_blk * BN,
+                                        kEvictLast);
                     }
-                    umma_commit(&empty_bar[stage]);  // frees this smem stage once the MMAs have read it
+                    __syncwarp();
+                    kofs += kBlockK;
+                    if (++cb == sg.cblocks) {  // next filter tap (tr, ts)
+                        cb = 0;
+                        ++tap;
+                        if (++ts == sg.S) {
+                            ts = 0;
+                            ++tr;
+                        }
+                    }
                     if (++stage == kStages) {
                         stage = 0;
                         phase ^= 1u;
                     }
                 }
-                umma_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (warp-convergent loop, one elected lane issues) =====================
+        constexpr uint32_t idesc = umma_idesc_bf16_f32(kBlockM, BN);
+        const uint32_t a_base = smem_u32(smem_a);
+        const uint32_t b_base = smem_u32(smem_b);
+        const int nacc = p.nacc;       // power of two <= 256 / BN
+        const int amask = nacc - 1;
+        int stage = 0;
+        uint32_t phase = 0;
+        int it = 0;
+        if constexpr (BRES) mbar_wait(bres_bar, 0);
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+            const int acc = it & 1;
+            const uint32_t acc_phase = (it >> 1) & 1u;
+            mbar_wait(&tmem_empty[acc], acc_phase ^ 1u);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * Cfg::kAccStageCols);
+            for (int kb = 0; kb < total_kb; ++kb) {
+                mbar_wait(&full_bar[stage], phase);
+                tc_fence_after();
+                if constexpr (WIDE) {
+                    if (elect_one()) {
+                        const int cblocks = p.seg[0].cblocks;
+                        const int tr = kb / cblocks, cb = kb - tr * cblocks;
+#pragma unroll
+                        for (int ts = 0; ts < 3; ++ts) {
+                            // tap (tr, ts): same tile, start shifted by ts pixel rows (128 B each).  The 128B swizzle is
+                            // a function of the absolute smem address bits, so a start that is not 1024-byte aligned
+                            // needs no correction: base_offset stays 0 (measured: setting it to ts reads wrong chunks).
+                            const uint64_t adesc =
+                                umma_desc_k_sw128(a_base + static_cast<uint32_t>(stage * kAStage + ts * 128));
+                            const uint64_t bdesc = umma_desc_k_sw128(
+                                b_base + static_cast<uint32_t>(((tr * 3 + ts) * cblocks + cb) * Cfg::kBBytes));
+#pragma unroll
+                            for (int k = 0; k < kBlockK / 16; ++k)
+                                umma_bf16_ss(d_tmem + static_cast<uint32_t>((k & amask) * BN),
+                                             adesc + static_cast<uint64_t>(2 * k), bdesc + static_cast<uint64_t>(2 * k),
+                                             idesc, (kb != 0 || ts != 0 || k >= nacc) ? 1u : 0u);
+                        }
+                        umma_commit(&empty_bar[stage]);
+                        if (kb == total_kb - 1) umma_commit(&tmem_full[acc]);
+                    }
+                } else if (elect_one()) {
+                    const uint64_t adesc = umma_desc_k_sw128(a_base + static_cast<uint32_t>(stage * kAStage));
+                    const uint64_t bdesc =
+                        umma_desc_k_sw128(b_base + static_cast<uint32_t>((BRES ? kb : stage) * Cfg::kBBytes));
+#pragma unroll
+                    for (int k = 0; k < kBlockK / 16; ++k) {
+                        // K step ks = 4*kb + k goes to partial accumulator (ks & amask); its first visit overwrites.
+                        // +32 bytes per UMMA_K=16 step inside the 128-byte swizzle span (>>4 encoded => +2).
+                        umma_bf16_ss(d_tmem + static_cast<uint32_t>((k & amask) * BN),
+                                     adesc + static_cast<uint64_t>(2 * k), bdesc + static_cast<uint64_t>(2 * k), idesc,
+                                     (kb != 0 || k >= nacc) ? 1u : 0u);
+                    }
+                    umma_commit(&empty_bar[stage]);  // frees this smem stage once the MMAs have read it
+                    if (kb == total_kb - 1) umma_commit(&tmem_full[acc]);  // accumulators complete -> epilogue
+                }
+                __syncwarp();
+                if (++stage == kStages) {
+                    stage = 0;
+                    phase ^= 1u;
+                }
             }
         }
     } else if (warp == kDmaWarp) {
         // ===================== epilogue DMA (residual prefetch + output stores) =====================
-        if (lane == 0 && !p.out_fp32) {
+        if (!p.out_fp32 && !WIDE) {
             const bool has_res = p.residual != nullptr;
-            tma_prefetch_desc(&p.tmOut);
-            if (has_res) tma_prefetch_desc(&p.tmRes);
             const int my_tiles = (num_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) /
                                  static_cast<int>(gridDim.x);
             const int total = my_tiles * kChunks;  // sub-tiles this CTA produces
@@ -230,6 +331,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
                 row0 = m_blk * kBlockM;
                 col0 = n_blk * BN + (g % kChunks) * kChunkCols;
             };
+            // every lane runs the loop; lane 0 (always the same lane: bulk async-groups are per thread) issues
             auto prepare = [&](int g) {  // staging tile (g % NBUF) is free here: hand it to the math warps
                 const int b = g % kBufs;
                 if (has_res) {
@@ -241,6 +343,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
                     mbar_arrive(&buf_ready[b]);
                 }
             };
+            if (lane == 0) {
             for (int g = 0; g < kBufs && g < total; ++g) prepare(g);
             for (int g = 0; g < total; ++g) {
                 const int b = g % kBufs;
@@ -258,8 +361,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
                 }
             }
             tma_store_wait_all<0>();  // all global writes complete before the CTA may exit
+            }
         }
-    } else if (!p.out_fp32) {
+    } else if (!p.out_fp32 && !WIDE) {
         // ===================== epilogue math (warps 2..9), staged bf16 output =====================
         const int quarter = warp & 3;        // TMEM lane quarter this warp may access
         const int half = (warp - 2) >> 2;    // which 32 of the sub-tile's 64 channels this warp converts
@@ -275,7 +379,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
             mbar_wait(&tmem_full[acc], acc_phase);
             tc_fence_after();
             const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
-                                   static_cast<uint32_t>(acc * BN);
+                                   static_cast<uint32_t>(acc * Cfg::kAccStageCols);
 #pragma unroll 1
             for (int c = 0; c < kChunks; ++c, ++g) {
                 const int b = g % kBufs;
@@ -285,6 +389,13 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
                     uint32_t v[32];
                     tmem_ld_32x32(t_row + static_cast<uint32_t>(c * kChunkCols + half * 32), v);
                     tmem_ld_wait();
+                    for (int a = 1; a < p.nacc; ++a) {  // add the other partial accumulators
+                        uint32_t u[32];
+                        tmem_ld_32x32(t_row + static_cast<uint32_t>(a * BN + c * kChunkCols + half * 32), u);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(u[j]));
+                    }
                     const int col = n_blk * BN + c * kChunkCols + half * 32;
                     const float4* bp = reinterpret_cast<const float4*>(p.bias[0] + col);
                     const float4* bp2 = (p.nseg > 1) ? reinterpret_cast<const float4*>(p.bias[1] + col) : nullptr;
@@ -347,15 +458,30 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
             const uint32_t acc_phase = (it >> 1) & 1u;
             mbar_wait(&tmem_full[acc], acc_phase);
             tc_fence_after();
-            const int row = m_blk * kBlockM + quarter * 32 + lane;
-            const bool row_ok = row < p.M;
+            int row = m_blk * kBlockM + quarter * 32 + lane;
+            bool row_ok = row < p.M;
+            if constexpr (WIDE) {
+                // widened row -> real output pixel; the two columns q' >= Wo of each image row are padding outputs
+                const int line = row / p.Wwide;
+                const int qq = row - line * p.Wwide;
+                row_ok = row_ok && qq < p.Wo;
+                row = line * p.Wo + qq;
+            }
             const size_t row_off = static_cast<size_t>(row) * p.N + static_cast<size_t>(n_blk) * BN;
             const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
-                                   static_cast<uint32_t>(acc * BN);
+                                   static_cast<uint32_t>(acc * Cfg::kAccStageCols);
 #pragma unroll 1
             for (int c = (warp - 2) >> 2; c < BN / 32; c += 2) {
                 uint32_t v[32];
                 tmem_ld_32x32(t_row + static_cast<uint32_t>(c * 32), v);
+                for (int a = 1; a < p.nacc; ++a) {
+                    uint32_t u[32];
+                    tmem_ld_wait();
+                    tmem_ld_32x32(t_row + static_cast<uint32_t>(a * BN + c * 32), u);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(u[j]));
+                }
                 // residual loads overlap the TMEM read
                 uint4 res[4];
                 const bool has_res = (p.residual != nullptr) && row_ok;

@@ -33,7 +33,9 @@ constexpr int kStemABytes = 3 * 128 * 128;         // three 128-row blocks of 12
 constexpr int kStemBBytes = 64 * 128;
 constexpr int kStemRawBytes = 2048;                // >= 39*48, per buffer
 constexpr int kStemInBytes = 3200;                 // >= 39*40*2
-constexpr int kStemSmemBytes = 1024 + kStemABytes + kStemBBytes + 2 * kStemRawBytes + kStemInBytes + 64;
+constexpr int kStemTabBytes = kStemRows * 8 * 4;   // per (row, 16-byte chunk): smem source / destination offsets
+constexpr int kStemSmemBytes =
+    1024 + kStemABytes + kStemBBytes + 2 * kStemRawBytes + kStemInBytes + kStemTabBytes + 64;
 constexpr int kStemSmemRequest = 100 * 1024;       // > 227/3 KB so that at most two CTAs share an SM (TMEM 2 x 256)
 
 struct StemParams {
@@ -62,7 +64,8 @@ __global__ void __launch_bounds__(kStemThreads, 2) stem_fused_kernel(const __gri
     uint8_t* smem_b = smem_a + kStemABytes;                  // weights
     uint8_t* raw = smem_b + kStemBBytes;                     // 2 raw input buffers
     __nv_bfloat16* in_s = reinterpret_cast<__nv_bfloat16*>(raw + 2 * kStemRawBytes);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(in_s) + kStemInBytes);
+    uint32_t* tab = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(in_s) + kStemInBytes);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(tab) + kStemTabBytes);
     uint64_t* w_bar = bars;
     uint64_t* mma_bar = bars + 1;
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2);
@@ -122,6 +125,35 @@ __global__ void __launch_bounds__(kStemThreads, 2) stem_fused_kernel(const __gri
 #pragma unroll
     for (int j = 0; j < 32; ++j) bias_r[j] = __ldg(p.bias + half * 32 + j);
 
+    // Tile-independent index tables (the divisions by 17 are done once per CTA, not once per tile):
+    //   tab[i] for im2col item i = (row m, chunk r): low 16 bits = byte offset of the 16 source bytes in in_s
+    //   (0xFFFF = zero chunk), high 16 bits = byte offset of the destination chunk in the A operand.
+    for (int i = tid; i < kStemRows * 8; i += kStemThreads) {
+        const int m = i >> 3, r = i & 7;
+        const int cy = m / kStemConv, cx = m - cy * kStemConv;
+        const uint32_t src = (r < 7) ? static_cast<uint32_t>(((2 * cy + r) * kStemInPitch + 2 * cx) * 2) : 0xFFFFu;
+        const uint32_t dst = static_cast<uint32_t>(m * 128 + ((r ^ (m & 7)) << 4));
+        tab[i] = src | (dst << 16);
+    }
+    // conv-tile coordinates of the three rows this thread converts in the epilogue (packed cy | cx << 8)
+    uint32_t epi_yx[3];
+#pragma unroll
+    for (int blk = 0; blk < 3; ++blk) {
+        const int m = blk * 128 + quarter * 32 + lane;
+        const int cy = m / kStemConv, cx = m - cy * kStemConv;
+        epi_yx[blk] = static_cast<uint32_t>(cy) | (static_cast<uint32_t>(cx) << 8);
+    }
+    // the two pooled (pixel, 8-channel chunk) items of this thread
+    const int pool_c = tid & 7;
+    int pool_py[2], pool_px[2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        const int pp = (tid + j * kStemThreads) >> 3;
+        pool_py[j] = pp / kStemPool;
+        pool_px[j] = pp - pool_py[j] * kStemPool;
+    }
+    static_assert(kStemPool * kStemPool * 8 == 2 * kStemThreads, "two pooled items per thread");
+
     prefetch(blockIdx.x, 0);
     mbar_wait(w_bar, 0);
     int it = 0;
@@ -147,31 +179,34 @@ __global__ void __launch_bounds__(kStemThreads, 2) stem_fused_kernel(const __gri
         __syncthreads();
 
         // ---- 3. im2col rows: A[m][r*8 .. r*8+7] = in_s[2*cy + r][2*cx .. 2*cx+7], chunk 7 = 0 ----
+#pragma unroll 2
         for (int i = tid; i < kStemRows * 8; i += kStemThreads) {
-            const int m = i >> 3, r = i & 7;
-            const int cy = m / kStemConv, cx = m - cy * kStemConv;
+            const uint32_t e = tab[i];
             uint4 v = make_uint4(0u, 0u, 0u, 0u);
-            if (r < 7) {
-                const uint32_t* src = reinterpret_cast<const uint32_t*>(in_s + (2 * cy + r) * kStemInPitch + 2 * cx);
+            if ((e & 0xFFFFu) != 0xFFFFu) {
+                const uint32_t* src =
+                    reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint8_t*>(in_s) + (e & 0xFFFFu));
                 v = make_uint4(src[0], src[1], src[2], src[3]);
             }
-            *reinterpret_cast<uint4*>(smem_a + m * 128 + ((r ^ (m & 7)) << 4)) = v;
+            *reinterpret_cast<uint4*>(smem_a + (e >> 16)) = v;
         }
         fence_proxy_async_smem();
         tc_fence_before();
         __syncthreads();
 
         // ---- 4. MMA: three 128-row blocks, K = 64 ----
-        if (tid == 0) {
+        if (warp == 0 && elect_one()) {  // warp-uniform branch + election keeps the MMA operands in uniform registers
             tc_fence_after();
             const uint64_t bdesc = umma_desc_k_sw128(smem_u32(smem_b));
+            // k outer, block inner: consecutive MMAs go to different accumulators (same-accumulator MMAs serialise)
 #pragma unroll
-            for (int blk = 0; blk < 3; ++blk) {
-                const uint64_t adesc = umma_desc_k_sw128(smem_u32(smem_a + blk * 128 * 128));
+            for (int k = 0; k < 4; ++k) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
+                for (int blk = 0; blk < 3; ++blk) {
+                    const uint64_t adesc = umma_desc_k_sw128(smem_u32(smem_a + blk * 128 * 128));
                     umma_bf16_ss(tmem_base + static_cast<uint32_t>(blk * 64), adesc + static_cast<uint64_t>(2 * k),
                                  bdesc + static_cast<uint64_t>(2 * k), idesc, k != 0 ? 1u : 0u);
+                }
             }
             umma_commit(mma_bar);
         }
@@ -187,7 +222,7 @@ __global__ void __launch_bounds__(kStemThreads, 2) stem_fused_kernel(const __gri
                               static_cast<uint32_t>(blk * 64 + half * 32), v);
             tmem_ld_wait();
             if (m < kStemRows) {
-                const int cy = m / kStemConv, cx = m - cy * kStemConv;
+                const int cy = static_cast<int>(epi_yx[blk] & 0xFFu), cx = static_cast<int>(epi_yx[blk] >> 8);
                 const int yc = 2 * Y0 - 1 + cy, xc = 2 * X0 - 1 + cx;
                 // conv pixels outside the conv image are the max-pool's padding: post-ReLU values are >= 0 and every
                 // window holds a real pixel, so 0 never wins over the reference's -inf padding semantics
@@ -212,9 +247,9 @@ __global__ void __launch_bounds__(kStemThreads, 2) stem_fused_kernel(const __gri
         __syncthreads();
 
         // ---- 6. max-pool 3x3 stride 2 over the conv tile, 16-byte stores ----
-        for (int i = tid; i < kStemPool * kStemPool * 8; i += kStemThreads) {
-            const int c = i & 7, pp = i >> 3;
-            const int py = pp / kStemPool, px = pp - py * kStemPool;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int c = pool_c, py = pool_py[j], px = pool_px[j];
             __nv_bfloat162 mx[4];
 #pragma unroll
             for (int dy = 0; dy < 3; ++dy) {

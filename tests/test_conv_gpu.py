@@ -54,6 +54,8 @@ CASES = [
     ("1x1_bigK",       2, 15, 2048,  128, 1, 1, 0),
     ("1x1_wideN",      2, 15,  512, 2048, 1, 1, 0),
     ("3x3_s1",         2, 24,   64,   64, 3, 1, 1),
+    ("3x3_s1_w120",    3, 120,  64,   64, 3, 1, 1),
+    ("3x3_s1_w15",     5, 15,   64,   64, 3, 1, 1),
     ("3x3_s1_c256",    3, 30,  256,  256, 3, 1, 1),
     ("3x3_s2_tail",    3, 30,  128,  128, 3, 2, 1),
     ("3x3_s2_big",     2, 120, 128,  128, 3, 2, 1),
@@ -129,7 +131,7 @@ def test_residual_relu(env, integer, shape):
         torch.testing.assert_close(out16.float(), ref.to(torch.bfloat16).float(), rtol=1e-2, atol=1e-2)
 
 
-@pytest.mark.parametrize("cfg", [0, 1, 2, 3, 4])
+@pytest.mark.parametrize("cfg", [0, 1, 2, 3, 4])  # 5 (weight-resident, N == 64 only) is what the N=64 cases run
 def test_every_kernel_configuration(env, cfg, monkeypatch):
     """Force each <BN, STAGES, NBUF> instantiation on one shape (N=256 fits all tile widths), with a residual."""
     N, lib, packing = env
@@ -190,3 +192,23 @@ def test_many_tiles_persistent(env):
     ref = _ref(x, w.to(dev), b.to(dev), 1, 0)
     out = _conv_native(lib, N, x, conv, relu=False, out_fp32=True)
     assert torch.equal(out, ref)
+
+
+@pytest.mark.parametrize("cfg", [4, 5, 6], ids=["stream", "weights_resident", "wide_rows"])
+@pytest.mark.parametrize("H", [15, 60])
+def test_narrow_3x3_configurations(env, cfg, H, monkeypatch):
+    """The three N=64 kernels on the layer1 3x3 shape: B tiles streamed, weights resident in smem, and the wide-row
+    mode (one 130-pixel load per filter row, horizontal taps through row-shifted smem descriptors)."""
+    N, lib, packing = env
+    monkeypatch.setenv("BV_FORCE_CFG", str(cfg))
+    gen = torch.Generator().manual_seed(17 + H)
+    dev = torch.device("cuda:0")
+    B, cin, cout = 3, 64, 64
+    x = torch.randint(-2, 3, (B, H, H, cin), generator=gen).float().to(torch.bfloat16).to(dev)
+    w = torch.randint(-1, 2, (cout, cin, 3, 3), generator=gen).float().to(torch.bfloat16)
+    b = torch.randint(-2, 3, (cout,), generator=gen).float()
+    conv = packing.pack_single_conv(w, b, 1, 1, dev)
+    ref = torch.relu(_ref(x, w.to(dev), b.to(dev), 1, 1)).to(torch.bfloat16)
+    out = _conv_native(lib, N, x, conv, relu=True, out_fp32=False)
+    assert not torch.isnan(out.float()).any()
+    assert torch.equal(out, ref), f"max abs diff {(out.float() - ref.float()).abs().max().item()}"
