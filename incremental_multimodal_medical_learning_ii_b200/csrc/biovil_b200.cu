@@ -236,10 +236,10 @@ int build_conv(ConvLaunch* L, int B, const ConvOperand* ops, int nops, const voi
     p.out_fp32 = out_fp32;
     L->bn = bn;
     L->cfg = cfg;
-    // K steps (16 wide) per tile = 4 * total_kblocks; use every accumulator the TMEM stage offers unless the K
-    // loop is too short to need it (each extra accumulator costs one more TMEM read per output in the epilogue).
-    int nacc = 256 / bn;
-    if (total_kblocks < 2) nacc = std::min(nacc, 2);
+    // Partial TMEM accumulators (K steps dealt round-robin, summed in the epilogue).  Measured with
+    // tools/umma_microbench.cu: tcgen05.mma throughput does not depend on accumulator reuse (68 / 78 / 128 cycles for
+    // N = 64 / 128 / 256 either way: the floor is the 64 B/cycle A-operand read), so one accumulator is used.
+    int nacc = 1;
     if (const char* f = getenv("BV_FORCE_NACC")) nacc = std::max(1, std::min(256 / bn, atoi(f)));
     p.nacc = nacc;
     const long long tiles = (long long)p.num_m_blocks * p.num_n_blocks;
@@ -247,7 +247,15 @@ int build_conv(ConvLaunch* L, int B, const ConvOperand* ops, int nops, const voi
     return BV_OK;
 }
 
-int launch_conv(const ConvLaunch& L, cudaStream_t st) {
+long long* g_dbg = nullptr;  // BV_TIMING=1: per-CTA wait-cycle counters of the most recent conv launch
+
+int launch_conv(const ConvLaunch& L0, cudaStream_t st) {
+    ConvLaunch L = L0;
+    if (env_flag("BV_TIMING")) {
+        if (!g_dbg) cudaMalloc(&g_dbg, 4 * 8 * 1024);
+        cudaMemsetAsync(g_dbg, 0, 4 * 8 * 1024, st);
+        L.p.dbg = g_dbg;
+    }
     switch (L.cfg) {
 #define BV_LAUNCH(id, BN, ST, NB, BR, WD)                                                                 \
     case id:                                                                                              \
@@ -260,6 +268,18 @@ int launch_conv(const ConvLaunch& L, cudaStream_t st) {
             return fail(BV_ERR_INVALID, "unknown conv configuration %d", L.cfg);
     }
     BV_CUDA(cudaGetLastError());
+    if (L.p.dbg) {
+        static long long host[4 * 1024];
+        cudaStreamSynchronize(st);
+        cudaMemcpy(host, g_dbg, sizeof(long long) * 4 * L.grid, cudaMemcpyDeviceToHost);
+        double a[4] = {0, 0, 0, 0};
+        for (int i = 0; i < L.grid; ++i)
+            for (int j = 0; j < 4; ++j) a[j] += (double)host[i * 4 + j] / L.grid;
+        fprintf(stderr, "[timing] cfg %d M=%d N=%d kb=%d: mma-warp total %.0f cyc, wait tmem_empty %.1f%%, wait full "
+                        "%.1f%%; producer wait empty %.1f%%\n",
+                L.cfg, L.p.M, L.p.N, L.p.seg[0].kblocks + (L.p.nseg > 1 ? L.p.seg[1].kblocks : 0), a[0],
+                100 * a[1] / a[0], 100 * a[2] / a[0], 100 * a[3] / a[0]);
+    }
     return BV_OK;
 }
 

@@ -74,6 +74,7 @@ struct ConvGemmParams {
     void* out;                      // [M, N] bf16 (or fp32 when out_fp32)
     int relu;
     int out_fp32;
+    long long* dbg;  // optional [gridDim][4] cycle counters: MMA warp {total, wait tmem_empty, wait full}, producer {wait empty}
     int nacc;  // independent TMEM accumulators the K steps are dealt over (1 .. 256/BN); summed in the epilogue
 };
 
@@ -113,8 +114,11 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
     constexpr int kStages = Cfg::kStages;
     constexpr int kBufs = NBUF;
 
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    // 1024-byte alignment (the 128B-swizzle period) is requested from the toolchain rather than obtained by rounding
+    // a generic pointer: an integer round-trip hides the shared address space from the compiler and every staging
+    // access becomes a generic LD.E/ST.E instead of LDS/STS.
+    extern __shared__ __align__(1024) uint8_t smem[];
+    if ((smem_u32(smem) & 1023u) != 0u) __trap();
     uint8_t* smem_a = smem;
     uint8_t* smem_b = smem + kStages * kAStage;  // per-stage B tiles, or the resident weight panel when BRES
     uint8_t* staging = smem + kStages * Cfg::kStageBytes + Cfg::kResidentBytes;  // NBUF x 16 KB, 1024-byte aligned
@@ -173,6 +177,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
         int stage = 0;
         uint32_t phase = 0;
         const int hw = p.Ho * p.Wo;
+        long long t_empty = 0;
         if constexpr (BRES) {
             // every tile of this CTA uses the same weight panel (the host only picks BRES when N == BN)
             if (elect_one()) {
@@ -198,7 +203,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
                 const int cblocks = p.seg[0].cblocks;
                 for (int tr = 0; tr < 3; ++tr) {
                     for (int cb = 0; cb < cblocks; ++cb) {
+                        const long long tw = clock64();
                         mbar_wait(&empty_bar[stage], phase ^ 1u);
+                        t_empty += clock64() - tw;
                         if (elect_one()) {
                             mbar_arrive_expect_tx(&full_bar[stage], kWideRows * 128);
                             tma_load_im2col_4d(&p.tmA[0], &full_bar[stage], smem_a + stage * kAStage, cb * kBlockK,
@@ -221,7 +228,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
                 const ConvSeg sg = p.seg[s];
                 int tap = 0, cb = 0, kofs = 0, tr = 0, ts = 0;
                 for (int kb = 0; kb < sg.kblocks; ++kb) {
+                    const long long tw = clock64();
                     mbar_wait(&empty_bar[stage], phase ^ 1u);
+                    t_empty += clock64() - tw;
                     if (elect_one()) {
                         mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
                         void* dst_a = smem_a + stage * kAStage;
@@ -253,8 +262,11 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
                 }
             }
         }
+        if (p.dbg && lane == 0) p.dbg[blockIdx.x * 4 + 3] = t_empty;
     } else if (warp == 1) {
         // ===================== MMA issuer (warp-convergent loop, one elected lane issues) =====================
+        long long t_acc = 0, t_full = 0;
+        const long long t_begin = clock64();
         constexpr uint32_t idesc = umma_idesc_bf16_f32(kBlockM, BN);
         const uint32_t a_base = smem_u32(smem_a);
         const uint32_t b_base = smem_u32(smem_b);
@@ -267,11 +279,15 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
             const int acc = it & 1;
             const uint32_t acc_phase = (it >> 1) & 1u;
+            long long tw = clock64();
             mbar_wait(&tmem_empty[acc], acc_phase ^ 1u);
+            t_acc += clock64() - tw;
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * Cfg::kAccStageCols);
             for (int kb = 0; kb < total_kb; ++kb) {
+                tw = clock64();
                 mbar_wait(&full_bar[stage], phase);
+                t_full += clock64() - tw;
                 tc_fence_after();
                 if constexpr (WIDE) {
                     if (elect_one()) {
@@ -316,6 +332,11 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
                     phase ^= 1u;
                 }
             }
+        }
+        if (p.dbg && lane == 0) {
+            p.dbg[blockIdx.x * 4 + 0] = clock64() - t_begin;
+            p.dbg[blockIdx.x * 4 + 1] = t_acc;
+            p.dbg[blockIdx.x * 4 + 2] = t_full;
         }
     } else if (warp == kDmaWarp) {
         // ===================== epilogue DMA (residual prefetch + output stores) =====================

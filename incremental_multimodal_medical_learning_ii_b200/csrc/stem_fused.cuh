@@ -58,8 +58,8 @@ __device__ __forceinline__ void cp_async_wait() {
 }
 
 __global__ void __launch_bounds__(kStemThreads, 2) stem_fused_kernel(const __grid_constant__ StemParams p) {
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    extern __shared__ __align__(1024) uint8_t smem[];   // keep the shared address space visible (LDS/STS, not LD.E)
+    if ((smem_u32(smem) & 1023u) != 0u) __trap();
     uint8_t* smem_a = smem;                                  // A operand, later the conv tile
     uint8_t* smem_b = smem_a + kStemABytes;                  // weights
     uint8_t* raw = smem_b + kStemBBytes;                     // 2 raw input buffers
