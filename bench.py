@@ -241,14 +241,15 @@ def run_ours(args):
         prof_runs.append(eng.get_profile())
     eng.set_profile(False)
     prof = prof_runs[-1]
-    conv_ms = sum(ms for (name, fl, by, ms) in prof if name.startswith("conv_gemm"))
-    conv_flops_issued = sum(fl for (name, fl, by, ms) in prof if name.startswith("conv_gemm"))
-    conv_bytes = sum(by for (name, fl, by, ms) in prof if name.startswith("conv_gemm"))
-    n_conv = sum(1 for (name, *_r) in prof if name.startswith("conv_gemm"))
+    is_conv = lambda name: name.startswith("conv_gemm") or name.startswith("chain_gemm")  # noqa: E731
+    conv_ms = sum(ms for (name, fl, by, ms) in prof if is_conv(name))
+    conv_flops_issued = sum(fl for (name, fl, by, ms) in prof if is_conv(name))
+    conv_bytes = sum(by for (name, fl, by, ms) in prof if is_conv(name))
+    n_conv = sum(1 for (name, *_r) in prof if is_conv(name))
     all_ms = sum(ms for (*_n, ms) in prof)
     peaks = measured_peaks()
     achieved = FLOP_PER_IMAGE * B / (conv_ms / 1000.0) / 1e12
-    roofline = {"bound": "tensor", "kernel": "conv_gemm_kernel (tcgen05 implicit GEMM, all conv launches of a step)",
+    roofline = {"bound": "tensor", "kernel": "conv_gemm_kernel + chain_gemm_kernel (tcgen05 implicit GEMM, all conv launches of a step)",
                 "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["tflops"],
                 "peak_source": peaks["src"], "launches_per_step": n_conv, "kernel_ms_per_step": conv_ms,
                 "kernel_share_of_step": conv_ms / all_ms if all_ms else None,

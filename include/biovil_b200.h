@@ -16,6 +16,9 @@
  *   bv_score          Trainer.myCosineSimilarity + label loop    Trainer.py:1682-1704, 805-837, 1019-1047
  *   bv_set_profile / bv_get_profile   (measurement only; no reference counterpart)
  *   bv_conv2d_nhwc    one Conv2d+BatchNorm2d(+ReLU)(+residual)   (unit-test entry for the tcgen05 kernel)
+ *   bv_conv_chain_nhwc  Bottleneck tail (conv3+bn3+identity/downsample+ReLU) chained with the next Bottleneck's
+ *                     conv1+bn1+ReLU in one kernel               (unit-test entry; torchvision Bottleneck.forward under
+ *                                                                 health_multimodal/image/model/resnet.py:38-42)
  *
  * Conventions: plain pointers and sizes only; every pointer is a DEVICE pointer unless named host_*;
  * the caller owns all buffers and the stream; calls are asynchronous on `stream`; functions return 0 on
@@ -130,6 +133,15 @@ int32_t bv_get_profile(bv_handle* h, bv_launch_info* host_out, int32_t capacity)
 int32_t bv_conv2d_nhwc(const void* x, int32_t batch, int32_t height, int32_t width, const bv_conv* host_c,
                        const void* x2, int32_t height2, int32_t width2, const bv_conv* host_c2, const void* residual,
                        int32_t relu, void* out, int32_t out_fp32, bv_stream stream);
+
+/* Two chained convolutions through one kernel (chain_gemm.cuh):
+ *   out1[B,Ho,Wo,N1] = relu(conv(x, c) + c.bias (+ conv(x2, c2) + c2.bias | + residual))      bf16
+ *   out2[B,Ho,Wo,N2] = relu(conv1x1(out1, next) + next.bias)                                   bf16
+ * `next` must be a 1x1 stride-1 convolution with cin == c.cout; c.cout a multiple of 128 (<= 512); next.cout in
+ * {64, 128, 256}.  x2/c2 and residual are mutually exclusive; either may be NULL. */
+int32_t bv_conv_chain_nhwc(const void* x, int32_t batch, int32_t height, int32_t width, const bv_conv* host_c,
+                           const void* x2, int32_t height2, int32_t width2, const bv_conv* host_c2,
+                           const void* residual, void* out1, const bv_conv* host_next, void* out2, bv_stream stream);
 
 #ifdef __cplusplus
 }

@@ -14,6 +14,7 @@
 
 #include "../../include/biovil_b200.h"
 #include "aux_kernels.cuh"
+#include "chain_gemm.cuh"
 #include "conv_gemm.cuh"
 #include "stem_fused.cuh"
 
@@ -118,6 +119,23 @@ struct ConvLaunch {
     int grid;
 };
 
+// Chained conv3 -> next conv1 kernel: <N2, STAGES, NB1> per width of the second GEMM (see ChainCfg).
+#define BV_FOR_EACH_CHAIN(X) X(64, 3, 7) X(128, 3, 6) X(256, 3, 4)
+
+struct ChainLaunch {
+    bv::ChainParams p;
+    int n2;
+    int grid;
+    int k1;  // total K of the first GEMM (for cost accounting)
+};
+
+// One step of the forward plan: a single fused convolution or a chained pair.
+struct PlanStep {
+    bool chain = false;
+    ConvLaunch conv;
+    ChainLaunch ch;
+};
+
 int g_num_sms = 0;
 bool g_attr_set = false;
 
@@ -142,6 +160,12 @@ int device_setup() {
                                  bv::ConvGemmCfg<BN, ST, NB, BR, WD>::kSmemBytes));
         BV_FOR_EACH_CFG(BV_SET_ATTR)
 #undef BV_SET_ATTR
+#define BV_SET_CHAIN_ATTR(N2, ST, NB)                                                               \
+    BV_CUDA(cudaFuncSetAttribute(bv::chain_gemm_kernel<N2, ST, NB>,                                 \
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize,                       \
+                                 bv::ChainCfg<N2, ST, NB>::kSmemBytes));
+        BV_FOR_EACH_CHAIN(BV_SET_CHAIN_ATTR)
+#undef BV_SET_CHAIN_ATTR
         BV_CUDA(cudaFuncSetAttribute(bv::head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
         BV_CUDA(cudaFuncSetAttribute(bv::stem_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      bv::kStemSmemRequest));
@@ -283,6 +307,94 @@ int launch_conv(const ConvLaunch& L0, cudaStream_t st) {
     return BV_OK;
 }
 
+// conv3 (+ downsample | + residual) + ReLU chained with the next block's 1x1 conv1 + ReLU (chain_gemm.cuh).
+// ops[0] = conv3 operand, ops[1] = optional downsample operand; `next` = the following conv1 (1x1, stride 1).
+bool chain_supported(const ConvOperand* ops, int nops, const bv_conv& next) {
+    const int n1 = ops[0].c.cout;
+    if (n1 % bv::kChainBN1 != 0 || n1 > 512) return false;
+    if (next.r != 1 || next.s != 1 || next.stride != 1 || next.pad != 0 || next.cin != n1) return false;
+    if (next.cout != 64 && next.cout != 128 && next.cout != 256) return false;
+    for (int i = 0; i < nops; ++i)
+        if (ops[i].c.cin % 64 != 0 || ops[i].c.cout != n1) return false;
+    return true;
+}
+
+int build_chain(ChainLaunch* L, int B, const ConvOperand* ops, int nops, const void* residual, void* out1,
+                const bv_conv& next, void* out2) {
+    if (nops < 1 || nops > 2) return fail(BV_ERR_INVALID, "chain needs 1 or 2 operand pairs");
+    if (nops == 2 && residual) return fail(BV_ERR_INVALID, "chain takes a downsample operand or a residual, not both");
+    if (!chain_supported(ops, nops, next)) return fail(BV_ERR_INVALID, "unsupported shapes for the chained kernel");
+    memset(&L->p, 0, sizeof(L->p));
+    bv::ChainParams& p = L->p;
+    const bv_conv& c0 = ops[0].c;
+    const int Ho = conv_out_dim(ops[0].H, c0.r, c0.stride, c0.pad);
+    const int Wo = conv_out_dim(ops[0].W, c0.s, c0.stride, c0.pad);
+    const int N1 = c0.cout, N2 = next.cout;
+    const long long M = (long long)B * Ho * Wo;
+    if (M <= 0 || M > 0x7fffffffLL - 256) return fail(BV_ERR_INVALID, "M=%lld out of range", M);
+    int k1 = 0;
+    for (int i = 0; i < nops; ++i) {
+        const bv_conv& c = ops[i].c;
+        if (conv_out_dim(ops[i].H, c.r, c.stride, c.pad) != Ho || conv_out_dim(ops[i].W, c.s, c.stride, c.pad) != Wo)
+            return fail(BV_ERR_INVALID, "operand %d output size mismatch", i);
+        bv::ConvSeg& sg = p.seg[i];
+        sg.cblocks = c.cin / 64;
+        sg.kblocks = c.r * c.s * sg.cblocks;
+        sg.S = c.s;
+        sg.stride = c.stride;
+        sg.lower = -c.pad;
+        const bool plain = (c.r == 1 && c.s == 1 && c.stride == 1 && c.pad == 0);
+        sg.mode = plain ? bv::kSegTiled : bv::kSegIm2col;
+        int rc;
+        if (plain)
+            rc = make_tmap_2d(&p.tmA[i], ops[i].x, (uint64_t)c.cin, (uint64_t)M, bv::kBlockK, bv::kBlockM);
+        else
+            rc = make_tmap_im2col(&p.tmA[i], ops[i].x, B, ops[i].H, ops[i].W, c.cin, c.r, c.s, c.stride, c.pad);
+        if (rc) return rc;
+        rc = make_tmap_2d(&p.tmB1[i], c.w, (uint64_t)c.r * c.s * c.cin, (uint64_t)N1, bv::kBlockK, bv::kChainBN1);
+        if (rc) return rc;
+        p.bias1[i] = c.bias;
+        k1 += sg.kblocks * 64;
+    }
+    int rc = make_tmap_2d(&p.tmB2, next.w, (uint64_t)N1, (uint64_t)N2, bv::kBlockK, (uint32_t)N2);
+    if (rc) return rc;
+    if ((rc = make_tmap_2d(&p.tmOut1, out1, (uint64_t)N1, (uint64_t)M, bv::kChunkCols, bv::kBlockM))) return rc;
+    if ((rc = make_tmap_2d(&p.tmOut2, out2, (uint64_t)N2, (uint64_t)M, bv::kChunkCols, bv::kBlockM))) return rc;
+    if (residual && (rc = make_tmap_2d(&p.tmRes, residual, (uint64_t)N1, (uint64_t)M, bv::kChunkCols, bv::kBlockM)))
+        return rc;
+    p.bias2 = next.bias;
+    p.nseg = nops;
+    p.Ho = Ho;
+    p.Wo = Wo;
+    p.M = (int)M;
+    p.N1 = N1;
+    p.num_m_blocks = (int)((M + bv::kBlockM - 1) / bv::kBlockM);
+    p.has_res = residual ? 1 : 0;
+    // Measured (ncu dram__bytes_read, profiles/r1n): pulling the next tile into L2 one tile ahead makes the DRAM read
+    // traffic 14-40 % LARGER (lines are evicted again before the smem pipeline reaches them) and the kernel slower.
+    p.l2_prefetch = env_flag("BV_L2_PREFETCH") ? 1 : 0;
+    L->n2 = N2;
+    L->k1 = k1;
+    L->grid = std::min(p.num_m_blocks, g_num_sms);
+    return BV_OK;
+}
+
+int launch_chain(const ChainLaunch& L, cudaStream_t st) {
+    switch (L.n2) {
+#define BV_LAUNCH_CHAIN(N2, ST, NB)                                                                        \
+    case N2:                                                                                               \
+        bv::chain_gemm_kernel<N2, ST, NB>                                                                  \
+            <<<L.grid, bv::kChainThreads, bv::ChainCfg<N2, ST, NB>::kSmemBytes, st>>>(L.p);                \
+        break;
+        BV_FOR_EACH_CHAIN(BV_LAUNCH_CHAIN)
+#undef BV_LAUNCH_CHAIN
+        default:
+            return fail(BV_ERR_INVALID, "unknown chain width %d", L.n2);
+    }
+    BV_CUDA(cudaGetLastError());
+    return BV_OK;
+}
+
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 // Activation buffers inside the caller's workspace.
@@ -335,7 +447,7 @@ struct bv_handle {
         }
     } key{};
     bool plan_valid = false;
-    std::vector<ConvLaunch> convs;  // in execution order (stem GEMM first)
+    std::vector<PlanStep> steps;    // in execution order (stem GEMM first)
     bv::StemParams stem{};          // fused 8-bit stem (valid when use_fused_stem)
     bool use_fused_stem = false;
     const void* trunk = nullptr;    // final [B,h,w,2048] bf16
@@ -381,6 +493,25 @@ void conv_cost(const ConvLaunch& L, double* flops, double* bytes, char* name, si
     snprintf(name, n, "conv_gemm<%d/c%d> M=%d N=%d K=%d%s%s", L.bn, L.cfg, p.M, p.N, (int)k, p.nseg > 1 ? " +ds" : "",
              p.residual ? " +res" : "");
 }
+void chain_cost(const ChainLaunch& L, double* flops, double* bytes, char* name, size_t n) {
+    const bv::ChainParams& p = L.p;
+    double abytes = 0;
+    for (int i = 0; i < p.nseg; ++i) {
+        const double rows = (p.seg[i].mode == bv::kSegTiled) ? (double)p.M : (double)p.M * p.seg[i].stride * p.seg[i].stride;
+        abytes += rows * p.seg[i].cblocks * 64 * 2;
+    }
+    *flops = 2.0 * p.M * p.N1 * L.k1 + 2.0 * p.M * L.n2 * p.N1;
+    *bytes = abytes + (double)p.M * p.N1 * 2 * (p.has_res ? 2 : 1) + (double)p.M * L.n2 * 2 +
+             ((double)L.k1 * p.N1 + (double)p.N1 * L.n2) * 2;
+    snprintf(name, n, "chain_gemm<%d> M=%d N1=%d K1=%d%s", L.n2, p.M, p.N1, L.k1, p.nseg > 1 ? " +ds" : " +res");
+}
+
+void step_cost(const PlanStep& s, double* flops, double* bytes, char* name, size_t n) {
+    if (s.chain) chain_cost(s.ch, flops, bytes, name, n);
+    else conv_cost(s.conv, flops, bytes, name, n);
+}
+
+int launch_step(const PlanStep& s, cudaStream_t st) { return s.chain ? launch_chain(s.ch, st) : launch_conv(s.conv, st); }
 }  // namespace
 
 extern "C" {
@@ -479,14 +610,25 @@ int32_t bv_get_profile(bv_handle* h, bv_launch_info* out, int32_t capacity) {
 
 static int build_plan(bv_handle* h, const void* frames, int dtype, int B, int C, int H, int W, uint8_t* ws) {
     const Layout lay = make_layout(B, C, H, W);
-    h->convs.clear();
+    h->steps.clear();
     const bool fuse_ds = !env_flag("BV_NO_FUSE_DS");
+    const bool use_chain = !env_flag("BV_NO_CHAIN");
     uint8_t* buf_a = ws + lay.buf_a;
     uint8_t* buf_b = ws + lay.buf_b;
     uint8_t* t1 = ws + lay.t1;
     uint8_t* t2 = ws + lay.t2;
     uint8_t* tds = ws + lay.tds;
     const int H2 = H / 2, W2 = W / 2;
+    auto push_conv = [&](const ConvOperand* ops, int nops, const void* residual, int relu, void* out,
+                         int out_fp32) -> int {
+        PlanStep s;
+        s.chain = false;
+        int rc = build_conv(&s.conv, B, ops, nops, residual, relu, out, out_fp32);
+        if (rc) return rc;
+        h->steps.push_back(s);
+        return BV_OK;
+    };
+    int rc;
     // stem GEMM: patches [B*H2*W2, K] (buf_a) x stem weights -> stem_out (buf_b), bias + ReLU
     {
         const bv_conv& sc = (dtype == BV_DTYPE_U8) ? h->w.stem_u8 : (C == 3 ? h->w.stem_f3 : h->w.stem_f1);
@@ -495,16 +637,14 @@ static int build_plan(bv_handle* h, const void* frames, int dtype, int B, int C,
         g.stride = 1;
         g.pad = 0;
         ConvOperand op{buf_a, H2, W2, g};
-        ConvLaunch L;
-        int rc = build_conv(&L, B, &op, 1, nullptr, 1, buf_b, 0);
-        if (rc) return rc;
-        h->convs.push_back(L);
+        if ((rc = push_conv(&op, 1, nullptr, 1, buf_b, 0))) return rc;
     }
     // max-pool writes x0 into buf_a; blocks ping-pong buf_a <-> buf_b
     uint8_t* cur = buf_a;
     uint8_t* nxt = buf_b;
     int ch = H / 4, cw = W / 4;
     int blk = 0;
+    bool t1_ready = false;  // this block's conv1 output was already produced by the previous block's chained kernel
     for (int li = 0; li < 4; ++li) {
         for (int bi = 0; bi < kLayerBlocks[li]; ++bi, ++blk) {
             const bv_conv& c1 = h->w.conv1[blk];
@@ -513,31 +653,39 @@ static int build_plan(bv_handle* h, const void* frames, int dtype, int B, int C,
             const bv_conv& ds = h->w.downsample[blk];
             const int oh = conv_out_dim(ch, c2.r, c2.stride, c2.pad);
             const int ow = conv_out_dim(cw, c2.s, c2.stride, c2.pad);
-            ConvLaunch L;
-            int rc;
-            ConvOperand o1{cur, ch, cw, c1};
-            if ((rc = build_conv(&L, B, &o1, 1, nullptr, 1, t1, 0))) return rc;
-            h->convs.push_back(L);
+            if (!t1_ready) {
+                ConvOperand o1{cur, ch, cw, c1};
+                if ((rc = push_conv(&o1, 1, nullptr, 1, t1, 0))) return rc;
+            }
             ConvOperand o2{t1, ch, cw, c2};
-            if ((rc = build_conv(&L, B, &o2, 1, nullptr, 1, t2, 0))) return rc;
-            h->convs.push_back(L);
+            if ((rc = push_conv(&o2, 1, nullptr, 1, t2, 0))) return rc;
+            // conv3 + (downsample | identity) + ReLU, chained with the next block's conv1 where the shapes allow
+            ConvOperand o3[2] = {{t2, oh, ow, c3}, {cur, ch, cw, ds}};
+            int n3 = 1;
+            const void* res = cur;
             if (ds.w != nullptr) {
                 if (fuse_ds) {
-                    ConvOperand o3[2] = {{t2, oh, ow, c3}, {cur, ch, cw, ds}};
-                    if ((rc = build_conv(&L, B, o3, 2, nullptr, 1, nxt, 0))) return rc;
-                    h->convs.push_back(L);
+                    n3 = 2;
+                    res = nullptr;
                 } else {
                     ConvOperand od{cur, ch, cw, ds};
-                    if ((rc = build_conv(&L, B, &od, 1, nullptr, 0, tds, 0))) return rc;
-                    h->convs.push_back(L);
-                    ConvOperand o3{t2, oh, ow, c3};
-                    if ((rc = build_conv(&L, B, &o3, 1, tds, 1, nxt, 0))) return rc;
-                    h->convs.push_back(L);
+                    if ((rc = push_conv(&od, 1, nullptr, 0, tds, 0))) return rc;
+                    res = tds;
                 }
+            }
+            t1_ready = false;
+            // Measured losses stay unchained: the strided-downsample tail of layer2.0 (six A k-blocks re-streamed per
+            // chunk) and the 256-wide second GEMM into layer3 (its staging leaves too little residual prefetch depth).
+            const bool chain_pays = env_flag("BV_CHAIN_ALL") ||
+                                    (!(n3 == 2 && ds.cin * ds.r * ds.s > 64) && h->w.conv1[blk + 1 < BV_NUM_BLOCKS ? blk + 1 : blk].cout <= 128);
+            if (use_chain && chain_pays && blk + 1 < BV_NUM_BLOCKS && chain_supported(o3, n3, h->w.conv1[blk + 1])) {
+                PlanStep s;
+                s.chain = true;
+                if ((rc = build_chain(&s.ch, B, o3, n3, res, nxt, h->w.conv1[blk + 1], t1))) return rc;
+                h->steps.push_back(s);
+                t1_ready = true;
             } else {
-                ConvOperand o3{t2, oh, ow, c3};
-                if ((rc = build_conv(&L, B, &o3, 1, cur, 1, nxt, 0))) return rc;
-                h->convs.push_back(L);
+                if ((rc = push_conv(o3, n3, res, 1, nxt, 0))) return rc;
             }
             std::swap(cur, nxt);
             ch = oh;
@@ -548,17 +696,13 @@ static int build_plan(bv_handle* h, const void* frames, int dtype, int B, int C,
     // projector conv 2048 -> 128 (+BN, ReLU), fp32 output for the fp32 tail
     {
         ConvOperand op{cur, ch, cw, h->w.proj0};
-        ConvLaunch L;
-        int rc = build_conv(&L, B, &op, 1, nullptr, 1, ws + lay.hid, 1);
-        if (rc) return rc;
-        h->convs.push_back(L);
+        if ((rc = push_conv(&op, 1, nullptr, 1, ws + lay.hid, 1))) return rc;
     }
     h->use_fused_stem = (dtype == BV_DTYPE_U8) && h->w.stem_u8_k8.w != nullptr && !env_flag("BV_NO_FUSED_STEM");
     if (h->use_fused_stem) {
         static_assert(bv::kStemSmemBytes <= bv::kStemSmemRequest, "stem smem request too small");
         memset(&h->stem, 0, sizeof(h->stem));
-        int rc = make_tmap_2d(&h->stem.tmW, h->w.stem_u8_k8.w, 64, 64, 64, 64);
-        if (rc) return rc;
+        if ((rc = make_tmap_2d(&h->stem.tmW, h->w.stem_u8_k8.w, 64, 64, 64, 64))) return rc;
         h->stem.bias = h->w.stem_u8_k8.bias;
         h->stem.out = reinterpret_cast<__nv_bfloat16*>(buf_a);
         h->stem.B = B;
@@ -635,9 +779,9 @@ int32_t bv_forward(bv_handle* h, const void* frames, int32_t dtype, int32_t B, i
             prof_mark(h, st, "stem_patch_gather", 0, (double)B * C * H * W * (dtype == BV_DTYPE_U8 ? 1 : 4) + px * ((C == 3) ? 192 : 64) * 2);
         }
         // 2. stem GEMM (+bias, ReLU)
-        if ((rc = launch_conv(h->convs[0], st))) return rc;
+        if ((rc = launch_step(h->steps[0], st))) return rc;
         ++launches;
-        conv_cost(h->convs[0], &pflops, &pbytes, pname, sizeof(pname));
+        step_cost(h->steps[0], &pflops, &pbytes, pname, sizeof(pname));
         prof_mark(h, st, pname, pflops, pbytes);
         // 3. max-pool into buf_a
         {
@@ -652,11 +796,11 @@ int32_t bv_forward(bv_handle* h, const void* frames, int32_t dtype, int32_t B, i
         }
     }
     // 4. bottleneck convs + projector conv
-    for (size_t i = 1; i < h->convs.size(); ++i) {
-        if ((rc = launch_conv(h->convs[i], st))) return rc;
+    for (size_t i = 1; i < h->steps.size(); ++i) {
+        if ((rc = launch_step(h->steps[i], st))) return rc;
         ++launches;
         if (h->profile) {
-            conv_cost(h->convs[i], &pflops, &pbytes, pname, sizeof(pname));
+            step_cost(h->steps[i], &pflops, &pbytes, pname, sizeof(pname));
             prof_mark(h, st, pname, pflops, pbytes);
         }
     }
@@ -721,6 +865,25 @@ int32_t bv_conv2d_nhwc(const void* x, int32_t B, int32_t H, int32_t W, const bv_
     rc = build_conv(&L, B, ops, nops, residual, relu, out, out_fp32);
     if (rc) return rc;
     return launch_conv(L, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int32_t bv_conv_chain_nhwc(const void* x, int32_t B, int32_t H, int32_t W, const bv_conv* c, const void* x2, int32_t H2,
+                           int32_t W2, const bv_conv* c2, const void* residual, void* out1, const bv_conv* next,
+                           void* out2, bv_stream stream) {
+    if (!x || !c || !out1 || !next || !out2) return fail(BV_ERR_INVALID, "null argument");
+    int rc = device_setup();
+    if (rc) return rc;
+    ConvOperand ops[2];
+    ops[0] = ConvOperand{x, H, W, *c};
+    int nops = 1;
+    if (x2 && c2) {
+        ops[1] = ConvOperand{x2, H2, W2, *c2};
+        nops = 2;
+    }
+    ChainLaunch L;
+    rc = build_chain(&L, B, ops, nops, residual, out1, *next, out2);
+    if (rc) return rc;
+    return launch_chain(L, reinterpret_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"
