@@ -120,11 +120,13 @@ struct ConvLaunch {
 };
 
 // Chained conv3 -> next conv1 kernel: <N2, STAGES, NB1> per width of the second GEMM (see ChainCfg).
-#define BV_FOR_EACH_CHAIN(X) X(64, 3, 7) X(128, 3, 6) X(256, 3, 4)
+// cfg 3: the downsample tail streams two A k-blocks per chunk and carries no residual -> deeper ring, fewer staging tiles
+#define BV_FOR_EACH_CHAIN(X) X(0, 64, 3, 7) X(1, 128, 3, 6) X(2, 256, 3, 4) X(3, 64, 4, 5)
 
 struct ChainLaunch {
     bv::ChainParams p;
     int n2;
+    int cfg;
     int grid;
     int k1;  // total K of the first GEMM (for cost accounting)
 };
@@ -160,7 +162,7 @@ int device_setup() {
                                  bv::ConvGemmCfg<BN, ST, NB, BR, WD>::kSmemBytes));
         BV_FOR_EACH_CFG(BV_SET_ATTR)
 #undef BV_SET_ATTR
-#define BV_SET_CHAIN_ATTR(N2, ST, NB)                                                               \
+#define BV_SET_CHAIN_ATTR(id, N2, ST, NB)                                                              \
     BV_CUDA(cudaFuncSetAttribute(bv::chain_gemm_kernel<N2, ST, NB>,                                 \
                                  cudaFuncAttributeMaxDynamicSharedMemorySize,                       \
                                  bv::ChainCfg<N2, ST, NB>::kSmemBytes));
@@ -374,22 +376,23 @@ int build_chain(ChainLaunch* L, int B, const ConvOperand* ops, int nops, const v
     // traffic 14-40 % LARGER (lines are evicted again before the smem pipeline reaches them) and the kernel slower.
     p.l2_prefetch = env_flag("BV_L2_PREFETCH") ? 1 : 0;
     L->n2 = N2;
+    L->cfg = (N2 == 64) ? ((nops == 2 && !env_flag("BV_CHAIN_NO_DEEP")) ? 3 : 0) : (N2 == 128 ? 1 : 2);
     L->k1 = k1;
     L->grid = std::min(p.num_m_blocks, g_num_sms);
     return BV_OK;
 }
 
 int launch_chain(const ChainLaunch& L, cudaStream_t st) {
-    switch (L.n2) {
-#define BV_LAUNCH_CHAIN(N2, ST, NB)                                                                        \
-    case N2:                                                                                               \
+    switch (L.cfg) {
+#define BV_LAUNCH_CHAIN(id, N2, ST, NB)                                                                    \
+    case id:                                                                                               \
         bv::chain_gemm_kernel<N2, ST, NB>                                                                  \
             <<<L.grid, bv::kChainThreads, bv::ChainCfg<N2, ST, NB>::kSmemBytes, st>>>(L.p);                \
         break;
         BV_FOR_EACH_CHAIN(BV_LAUNCH_CHAIN)
 #undef BV_LAUNCH_CHAIN
         default:
-            return fail(BV_ERR_INVALID, "unknown chain width %d", L.n2);
+            return fail(BV_ERR_INVALID, "unknown chain configuration %d", L.cfg);
     }
     BV_CUDA(cudaGetLastError());
     return BV_OK;

@@ -238,13 +238,17 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_gemm_kernel(const __gr
             }
         };
         auto load_g2 = [&](int q) {
+            // both 64-wide k-blocks of the chunk's second-GEMM weights travel in ONE ring stage when they fit
+            // (N2 <= 128: 2 x N2 x 128 B <= 32 KB); N2 = 256 takes one stage per k-block
             const int c = q % C;
-            for (int j = 0; j < 2; ++j) {
+            constexpr int kPerStage = (N2 <= 128) ? 2 : 1;
+            for (int j = 0; j < 2; j += kPerStage) {
                 mbar_wait(&empty_bar[stage], phase ^ 1u);
                 if (elect_one()) {
-                    mbar_arrive_expect_tx(&full_bar[stage], N2 * 128);
-                    tma_load_2d(&p.tmB2, &full_bar[stage], ring + stage * kChainStageBytes, (2 * c + j) * kBlockK, 0,
-                                kEvictLast);
+                    mbar_arrive_expect_tx(&full_bar[stage], kPerStage * N2 * 128);
+                    for (int u = 0; u < kPerStage; ++u)
+                        tma_load_2d(&p.tmB2, &full_bar[stage], ring + stage * kChainStageBytes + u * N2 * 128,
+                                    (2 * c + j + u) * kBlockK, 0, kEvictLast);
                 }
                 __syncwarp();
                 advance();
@@ -301,25 +305,29 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_gemm_kernel(const __gr
                 tc_fence_after();
             }
             const uint32_t d_tmem = tmem_base + 256u + static_cast<uint32_t>(acc2 * 128);
+            constexpr int kPerStage = (N2 <= 128) ? 2 : 1;
             for (int j = 0; j < 2; ++j) {
                 const int g = 2 * q + j;
                 const int b = g % NB1;
+                const bool new_stage = (j % kPerStage) == 0;
+                const bool last_of_stage = (j % kPerStage) == kPerStage - 1;
                 mbar_wait(&buf_written[b], (g / NB1) & 1u);
-                mbar_wait(&full_bar[stage], phase);
+                if (new_stage) mbar_wait(&full_bar[stage], phase);
                 tc_fence_after();
                 if (elect_one()) {
                     const uint64_t adesc = umma_desc_k_sw128(stg_base + static_cast<uint32_t>(b * kStagingBytes));
-                    const uint64_t bdesc = umma_desc_k_sw128(ring_base + static_cast<uint32_t>(stage * kChainStageBytes));
+                    const uint64_t bdesc = umma_desc_k_sw128(
+                        ring_base + static_cast<uint32_t>(stage * kChainStageBytes + (j % kPerStage) * N2 * 128));
 #pragma unroll
                     for (int k = 0; k < kBlockK / 16; ++k)
                         umma_bf16_ss(d_tmem, adesc + static_cast<uint64_t>(2 * k), bdesc + static_cast<uint64_t>(2 * k),
                                      idesc2, (c != 0 || j != 0 || k != 0) ? 1u : 0u);
-                    umma_commit(&empty_bar[stage]);
+                    if (last_of_stage) umma_commit(&empty_bar[stage]);
                     umma_commit(&buf_consumed[b]);
                     if (c == C - 1 && j == 1) umma_commit(&d2_full[acc2]);
                 }
                 __syncwarp();
-                advance();
+                if (last_of_stage) advance();
             }
         };
         for (int q = 0; q < Q; ++q) {
