@@ -256,6 +256,16 @@ def run_ours(args):
                 "issued_tflops": conv_flops_issued / (conv_ms / 1000.0) / 1e12,
                 "hbm_gbs_algorithmic": conv_bytes / (conv_ms / 1000.0) / 1e9, "hbm_peak_gbs": peaks["hbm"],
                 "traffic": None}
+    # DRAM traffic of the same launches from the committed ncu launch list (tools/summarise_ncu_launches.py)
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            tj = json.load(f)
+        if tj.get("batch") == B:
+            roofline["traffic"] = tj["conv_dram_bytes_per_step"]
+            roofline["traffic_unit"] = "bytes per step over all conv launches (ncu dram__bytes_read+write)"
+            roofline["traffic_source"] = tj.get("source")
+            roofline["hbm_gbs_traffic"] = tj["conv_dram_bytes_per_step"] / (conv_ms / 1000.0) / 1e9
     if args.profile_out and rank == 0:
         with open(args.profile_out, "w") as f:
             f.write("name,ms,tflops,algorithmic_gbs\n")

@@ -14,6 +14,7 @@
  *                     patch x prompt similarity map              health_multimodal/vlp/inference_engine.py:93-108
  *   bv_set_prompts    Trainer.bert_forward_mean (prompt side)    Trainer.py:1657-1680
  *   bv_score          Trainer.myCosineSimilarity + label loop    Trainer.py:1682-1704, 805-837, 1019-1047
+ *   bv_smooth_heatmaps  gaussian_filter(sigma) of the similarity maps health_multimodal/vlp/inference_engine.py:107-109
  *   bv_set_profile / bv_get_profile   (measurement only; no reference counterpart)
  *   bv_conv2d_nhwc    one Conv2d+BatchNorm2d(+ReLU)(+residual)   (unit-test entry for the tcgen05 kernel)
  *   bv_conv_chain_nhwc  Bottleneck tail (conv3+bn3+identity/downsample+ReLU) chained with the next Bottleneck's
@@ -110,6 +111,11 @@ int32_t bv_forward(bv_handle* h, const void* frames, int32_t dtype, int32_t batc
 /* Score cached embeddings emb [B,128] (un-normalised) against the installed prompts. */
 int32_t bv_score(bv_handle* h, const float* emb, int32_t batch, float* sim, float* prob, uint8_t* pred, float* score,
                  bv_stream stream);
+
+/* Smooth patch-similarity maps heat [B,gh,gw,L] -> out [B,gh,gw,L] with scipy.ndimage.gaussian_filter semantics
+ * (order 0, mode 'reflect', truncate 4.0, separable, same sigma on both axes); gh*gw <= 1024, radius <= 16. */
+int32_t bv_smooth_heatmaps(const float* heat, int32_t batch, int32_t grid_h, int32_t grid_w, int32_t num_labels,
+                           float sigma, float* out, bv_stream stream);
 
 /* Number of kernels the last bv_forward launched (for launch accounting in the benchmark). */
 int32_t bv_last_forward_launches(const bv_handle* h);

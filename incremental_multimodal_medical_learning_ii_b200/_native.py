@@ -65,7 +65,7 @@ class BvLaunchInfo(Structure):
 EXPORTED_SYMBOLS = (
     "bv_last_error", "bv_version", "bv_workspace_bytes", "bv_patch_grid", "bv_create", "bv_destroy",
     "bv_set_prompts", "bv_forward", "bv_score", "bv_last_forward_launches", "bv_set_profile", "bv_get_profile",
-    "bv_conv2d_nhwc", "bv_conv_chain_nhwc",
+    "bv_conv2d_nhwc", "bv_conv_chain_nhwc", "bv_smooth_heatmaps",
 )
 
 _lib = None
@@ -131,6 +131,8 @@ def lib() -> ctypes.CDLL:
     l.bv_conv2d_nhwc.restype = c_int32
     l.bv_conv2d_nhwc.argtypes = [c_void_p, c_int32, c_int32, c_int32, POINTER(BvConv), c_void_p, c_int32, c_int32,
                                  POINTER(BvConv), c_void_p, c_int32, c_void_p, c_int32, c_void_p]
+    l.bv_smooth_heatmaps.restype = c_int32
+    l.bv_smooth_heatmaps.argtypes = [c_void_p, c_int32, c_int32, c_int32, c_int32, c_float, c_void_p, c_void_p]
     l.bv_conv_chain_nhwc.restype = c_int32
     l.bv_conv_chain_nhwc.argtypes = [c_void_p, c_int32, c_int32, c_int32, POINTER(BvConv), c_void_p, c_int32, c_int32,
                                      POINTER(BvConv), c_void_p, c_void_p, POINTER(BvConv), c_void_p, c_void_p]

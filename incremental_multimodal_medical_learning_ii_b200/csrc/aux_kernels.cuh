@@ -352,4 +352,50 @@ __global__ void __launch_bounds__(256) head_kernel(const HeadParams hp) {
     }
 }
 
+// ----------------------------------------------------------------------------------------------
+// Heat-map smoothing: scipy.ndimage.gaussian_filter(sigma=(s,s), order=0, mode='reflect', truncate=4.0) applied to
+// every [gh, gw] patch-similarity map (vlp/inference_engine.py:107-109), separable, rows axis first like scipy.
+// heat / out are [B, gh, gw, L]; one CTA per (image, label) map; weights are computed on the host in double
+// exactly as scipy's _gaussian_kernel1d does and passed by value.
+// ----------------------------------------------------------------------------------------------
+constexpr int kSmoothMaxRadius = 16;
+constexpr int kSmoothMaxCells = 32 * 32;
+struct SmoothParams {
+    const float* heat;
+    float* out;
+    int B, gh, gw, L;
+    int radius;
+    float w[2 * kSmoothMaxRadius + 1];
+};
+
+// 'reflect' = half-sample symmetric: (d c b a | a b c d | d c b a)
+__device__ __forceinline__ int reflect_index(int i, int n) {
+    while (i < 0 || i >= n) i = (i < 0) ? (-i - 1) : (2 * n - 1 - i);
+    return i;
+}
+
+__global__ void __launch_bounds__(256) heat_smooth_kernel(const SmoothParams p) {
+    __shared__ float a[kSmoothMaxCells];
+    __shared__ float t[kSmoothMaxCells];
+    const int b = blockIdx.x / p.L, l = blockIdx.x - b * p.L;
+    const int cells = p.gh * p.gw;
+    const float* src = p.heat + static_cast<size_t>(b) * cells * p.L + l;
+    for (int i = threadIdx.x; i < cells; i += blockDim.x) a[i] = src[static_cast<size_t>(i) * p.L];
+    __syncthreads();
+    for (int i = threadIdx.x; i < cells; i += blockDim.x) {  // axis 0 (rows)
+        const int y = i / p.gw, x = i - y * p.gw;
+        float acc = 0.0f;
+        for (int k = -p.radius; k <= p.radius; ++k) acc = fmaf(p.w[k + p.radius], a[reflect_index(y + k, p.gh) * p.gw + x], acc);
+        t[i] = acc;
+    }
+    __syncthreads();
+    float* dst = p.out + static_cast<size_t>(b) * cells * p.L + l;
+    for (int i = threadIdx.x; i < cells; i += blockDim.x) {  // axis 1 (columns)
+        const int y = i / p.gw, x = i - y * p.gw;
+        float acc = 0.0f;
+        for (int k = -p.radius; k <= p.radius; ++k) acc = fmaf(p.w[k + p.radius], t[y * p.gw + reflect_index(x + k, p.gw)], acc);
+        dst[static_cast<size_t>(i) * p.L] = acc;
+    }
+}
+
 }  // namespace bv

@@ -5,6 +5,7 @@
 #include <cudaTypedefs.h>
 
 #include <algorithm>
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -868,6 +869,30 @@ int32_t bv_conv2d_nhwc(const void* x, int32_t B, int32_t H, int32_t W, const bv_
     rc = build_conv(&L, B, ops, nops, residual, relu, out, out_fp32);
     if (rc) return rc;
     return launch_conv(L, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int32_t bv_smooth_heatmaps(const float* heat, int32_t B, int32_t gh, int32_t gw, int32_t L, float sigma, float* out,
+                           bv_stream stream) {
+    if (!heat || !out || B <= 0 || L <= 0 || gh <= 0 || gw <= 0) return fail(BV_ERR_INVALID, "bad heat-map arguments");
+    if (gh * gw > bv::kSmoothMaxCells) return fail(BV_ERR_INVALID, "patch grid %dx%d too large (max %d cells)", gh, gw, bv::kSmoothMaxCells);
+    if (!(sigma > 0.f)) return fail(BV_ERR_INVALID, "sigma must be positive");
+    int rc = device_setup();
+    if (rc) return rc;
+    bv::SmoothParams p{};
+    // scipy.ndimage._filters: lw = int(truncate * sd + 0.5); phi = exp(-0.5 / sd^2 * x^2); phi /= phi.sum()
+    const double sd = (double)sigma;
+    const int radius = (int)(4.0 * sd + 0.5);
+    if (radius > bv::kSmoothMaxRadius) return fail(BV_ERR_INVALID, "sigma %.3f needs radius %d > %d", sigma, radius, bv::kSmoothMaxRadius);
+    double w[2 * bv::kSmoothMaxRadius + 1], sum = 0;
+    for (int k = -radius; k <= radius; ++k) sum += (w[k + radius] = exp(-0.5 / (sd * sd) * (double)k * k));
+    for (int k = 0; k <= 2 * radius; ++k) p.w[k] = (float)(w[k] / sum);
+    p.heat = heat;
+    p.out = out;
+    p.B = B; p.gh = gh; p.gw = gw; p.L = L;
+    p.radius = radius;
+    bv::heat_smooth_kernel<<<B * L, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+    BV_CUDA(cudaGetLastError());
+    return BV_OK;
 }
 
 int32_t bv_conv_chain_nhwc(const void* x, int32_t B, int32_t H, int32_t W, const bv_conv* c, const void* x2, int32_t H2,

@@ -300,6 +300,20 @@ class ImageModel(nn.Module):
         return self._run(frames, score=True, heat=heat, patch=patch, normalize_patch=True)
 
     @torch.no_grad()
+    def smooth_heatmaps(self, heat: torch.Tensor, sigma: float = 1.5) -> torch.Tensor:
+        """Gaussian smoothing of ``[B,H',W',L]`` similarity maps on the GPU with the semantics of
+        ``ndimage.gaussian_filter(map, sigma=(sigma, sigma), order=0)`` (vlp/inference_engine.py:107-109)."""
+        if heat.dim() != 4 or not heat.is_cuda:
+            raise ValueError("expected CUDA similarity maps [B, H', W', L]")
+        heat = heat.float().contiguous()
+        out = torch.empty_like(heat)
+        B, gh, gw, L = heat.shape
+        with torch.cuda.device(heat.device):
+            N.check(N.lib().bv_smooth_heatmaps(N.ptr(heat), B, gh, gw, L, float(sigma), N.ptr(out),
+                                               N.current_stream_handle(heat.device)))
+        return out
+
+    @torch.no_grad()
     def score_embeddings(self, emb: torch.Tensor) -> Dict[str, torch.Tensor]:
         """Score cached ``[B,128]`` embeddings (the ``Trainer.val/test`` path) against the installed prompts."""
         if self._prompts is None:

@@ -97,3 +97,37 @@ def my_cosine_similarity(x: torch.Tensor, y: torch.Tensor, use_grad: bool = Fals
     prompts = torch.stack([y, y], dim=0).unsqueeze(0)            # [1, 2, P, 128]: same vectors as pos and neg
     _default_scorer.set_prompts(prompts, reduce="max")
     return _default_scorer.score(x)["sim"][:, 0, :1].contiguous()
+
+
+class TrainerEvalScorer:
+    """The whole label loop of ``Trainer.val`` / ``Trainer.test`` (Trainer.py:797-837, 1019-1047) as ONE kernel launch.
+
+    The reference re-runs CXR-BERT on every label's prompts for every batch (``bert_forward_mean`` inside the batch
+    loop, Trainer.py:816 / 1030) although the prompt embeddings are constant during evaluation, then launches
+    2 x L ``pairwise_cosine_similarity`` calls.  Here the ``[L,2,P,128]`` prompt embeddings are installed once and a
+    batch of cached image embeddings gives ``predicted_labels``, ``tmp_score`` and ``logits`` exactly as the loop
+    fills them:
+
+    * ``train_logit_diff`` (Trainer.py:52, 809-814): False compares against the positive prompts only (the reference
+      passes the positive prompts as "negative" too, so ``logits = pos`` and ``predicted_labels = argmax([pos, pos]) = 0``);
+    * ``pred_logit_diff`` (Trainer.py:53, 824-827): ``tmp_score = (pos+1)/2`` or ``(pos-neg+2)/4``;
+    * ``max_emb`` (Trainer.py:49, 1691-1694): max over per-prompt cosines instead of the cosine to the mean prompt.
+    """
+
+    def __init__(self, prompts: torch.Tensor, device="cuda:0", train_logit_diff: bool = True,
+                 pred_logit_diff: bool = False, max_emb: bool = False):
+        if prompts.dim() == 3:
+            prompts = prompts.unsqueeze(2)
+        if not train_logit_diff:
+            prompts = torch.stack([prompts[:, 0], prompts[:, 0]], dim=1)   # the "trick" of Trainer.py:814
+        self.train_logit_diff, self.pred_logit_diff = train_logit_diff, pred_logit_diff
+        self._scorer = ZeroShotScorer(device)
+        self._scorer.set_prompts(prompts, reduce="max" if max_emb else "mean")
+
+    @torch.no_grad()
+    def __call__(self, embs: torch.Tensor) -> Dict[str, torch.Tensor]:
+        r = self._scorer.score(embs)
+        pos, neg = r["sim"][..., 0], r["sim"][..., 1]
+        tmp_score = (pos - neg + 2) / 4 if self.pred_logit_diff else r["score"]
+        logits = r["logit"] if self.train_logit_diff else pos
+        return {"predicted_labels": r["pred"].float(), "tmp_score": tmp_score, "logits": logits, "sim": r["sim"]}

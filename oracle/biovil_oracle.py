@@ -167,6 +167,36 @@ def zero_shot_score(emb: torch.Tensor, prompts: torch.Tensor, reduce: str = "mea
             "score_diff": (pos - neg + 2) / 4, "pred": pred}
 
 
+def trainer_val_batch(embs: torch.Tensor, prompts: torch.Tensor, train_logit_diff: bool = True,
+                      pred_logit_diff: bool = False, max_emb: bool = False) -> Dict[str, torch.Tensor]:
+    """One batch of ``Trainer.val`` / ``Trainer.test`` restated line by line (Trainer.py:797-837, 1019-1047), with the
+    module-level switches TRAIN_LOGIT_DIFF (:52), PRED_LOGIT_DIFF (:53) and MAX_EMB (:49) as arguments.
+    ``prompts`` [L,2,P,D] stands for what ``get_embeddings_from_prompt(normalize=False)`` returns per label."""
+    B, L = embs.shape[0], prompts.shape[0]
+    predicted_labels = torch.zeros(B, L)
+    tmp_score = torch.zeros(B, L)
+    logits = torch.empty(B, L)
+
+    def cos(x, y):                                           # Trainer.myCosineSimilarity, no-grad branch (:1682-1704)
+        if not max_emb:
+            return pairwise_cosine_similarity(x, y.reshape(1, -1))
+        return torch.max(pairwise_cosine_similarity(x, y), dim=1).values
+
+    for i in range(L):
+        pos_prompt = prompts[i, 0]
+        neg_prompt = prompts[i, 1] if train_logit_diff else prompts[i, 0]          # :809-814
+        pos_e = pos_prompt if max_emb else pos_prompt.mean(dim=0)                  # bert_forward_mean :1665-1666
+        neg_e = neg_prompt if max_emb else neg_prompt.mean(dim=0)
+        pos_s, neg_s = cos(embs.float(), pos_e.float()), cos(embs.float(), neg_e.float())
+        if not pred_logit_diff:
+            tmp_score[:, i] = (pos_s.flatten() + 1) / 2
+        else:
+            tmp_score[:, i] = (pos_s.flatten() - neg_s.flatten() + 2) / 4
+        logits[:, i] = pos_s.flatten() - neg_s.flatten() if train_logit_diff else pos_s.flatten()
+        predicted_labels[:, i] = torch.argmax(torch.cat([neg_s.reshape(-1, 1), pos_s.reshape(-1, 1)], dim=1), dim=1)
+    return {"predicted_labels": predicted_labels, "tmp_score": tmp_score, "logits": logits}
+
+
 def patch_similarity_map(patch_emb_normalized: torch.Tensor, prompts_pos: torch.Tensor) -> torch.Tensor:
     """``ImageTextInferenceEngine._get_similarity_map_from_embeddings`` before smoothing
     (vlp/inference_engine.py:93-108) batched over images and labels.
@@ -182,7 +212,7 @@ def gaussian_smooth_map(sim_map: torch.Tensor, sigma: float = 1.5) -> torch.Tens
     of [.., H', W'] (vlp/inference_engine.py:109).  Used by the 'next' row for heat-map post-processing."""
     from scipy import ndimage
     import numpy as np
-    a = sim_map.detach().cpu().numpy()
+    a = np.ascontiguousarray(sim_map.detach().cpu().numpy())     # reshape below must be a view, not a copy
     out = np.empty_like(a)
     flat_in = a.reshape(-1, a.shape[-2], a.shape[-1])
     flat_out = out.reshape(-1, a.shape[-2], a.shape[-1])

@@ -1,0 +1,57 @@
+"""GPU parity for the SURVEY 8(f) "next" rows built so far:
+rank 2 - the whole Trainer.val/test label loop as one scorer launch (Trainer.py:797-837);
+rank 4 - Gaussian smoothing of the patch similarity maps (vlp/inference_engine.py:107-109)."""
+import pytest
+import torch
+
+import biovil_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("train_logit_diff", [True, False])
+@pytest.mark.parametrize("pred_logit_diff", [False, True])
+@pytest.mark.parametrize("max_emb,P", [(False, 1), (False, 5), (True, 5)])
+def test_trainer_eval_loop_is_one_launch(train_logit_diff, pred_logit_diff, max_emb, P):
+    from incremental_multimodal_medical_learning_ii_b200.scorer import TrainerEvalScorer
+    g = torch.Generator().manual_seed(31 + P)
+    embs = torch.randn(1024, 128, generator=g)                 # the reference's val/test batch size (Trainer.py:237)
+    prompts = torch.randn(5, 2, P, 128, generator=g)           # 5 CheXpert competition labels (Trainer.py:797)
+    ref = O.trainer_val_batch(embs, prompts, train_logit_diff, pred_logit_diff, max_emb)
+    sc = TrainerEvalScorer(prompts, "cuda:0", train_logit_diff, pred_logit_diff, max_emb)
+    out = sc(embs.cuda())
+    # fp32 cosines of 128-d vectors: tolerance 1e-5 absolute (north_star asks 1e-3 on probabilities)
+    torch.testing.assert_close(out["tmp_score"].cpu(), ref["tmp_score"], rtol=0, atol=1e-5)
+    torch.testing.assert_close(out["logits"].cpu(), ref["logits"], rtol=0, atol=1e-5)
+    if train_logit_diff:
+        decided = ref["logits"].abs() > 1e-5                   # labels identical wherever fp32 itself decides
+        assert torch.equal(out["predicted_labels"].cpu()[decided], ref["predicted_labels"][decided])
+    else:
+        # argmax([pos, pos]) is 0 in the reference (first maximum); `pos > pos` is false here as well
+        assert torch.equal(out["predicted_labels"].cpu(), ref["predicted_labels"])
+        assert ref["predicted_labels"].sum() == 0
+
+
+@pytest.mark.parametrize("shape", [(3, 15, 15, 14), (2, 16, 16, 5), (1, 4, 7, 1), (2, 15, 15, 140)])
+@pytest.mark.parametrize("sigma", [1.5, 0.8])
+def test_heatmap_gaussian_smoothing_vs_scipy(shape, sigma):
+    from incremental_multimodal_medical_learning_ii_b200.image import get_biovil_resnet
+    g = torch.Generator().manual_seed(sum(shape))
+    heat = torch.rand(shape, generator=g) * 2 - 1               # cosines in [-1, 1]
+    ref = O.gaussian_smooth_map(heat.permute(0, 3, 1, 2), sigma).permute(0, 2, 3, 1)   # scipy on each [H',W'] map
+    model = get_biovil_resnet(None)
+    out = model.smooth_heatmaps(heat.cuda(), sigma).cpu()
+    # scipy accumulates in double and rounds to fp32 after each axis; the kernel accumulates 13 fp32 FMAs per axis
+    torch.testing.assert_close(out, ref, rtol=0, atol=2e-6)
+
+
+def test_heatmap_smoothing_rejects_bad_arguments():
+    from incremental_multimodal_medical_learning_ii_b200.image import get_biovil_resnet
+    from incremental_multimodal_medical_learning_ii_b200._native import NativeError
+    model = get_biovil_resnet(None)
+    with pytest.raises(ValueError):
+        model.smooth_heatmaps(torch.zeros(2, 15, 15, 14))                      # CPU tensor
+    with pytest.raises(NativeError):
+        model.smooth_heatmaps(torch.zeros(1, 15, 15, 2, device="cuda"), sigma=10.0)   # radius 40 > 16
+    with pytest.raises(NativeError):
+        model.smooth_heatmaps(torch.zeros(1, 40, 40, 2, device="cuda"))        # 1600 cells > 1024

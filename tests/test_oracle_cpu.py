@@ -79,3 +79,37 @@ def test_small_frames_and_margin_prompts():
                                              min_margin=5e-3)
     s = O.zero_shot_score(out["projected_global_embedding"], prompts, "mean")
     assert ((s["sim"][..., 0] - s["sim"][..., 1]).abs() > 5e-3).all()
+
+
+def test_trainer_val_batch_restatement_is_consistent_with_zero_shot_score():
+    """The line-by-line restatement of the Trainer.val label loop (Trainer.py:797-837) agrees with the vectorised
+    scorer oracle for the default switches, and shows the documented degenerate behaviour of TRAIN_LOGIT_DIFF=False."""
+    import torch
+    import biovil_oracle as O
+    g = torch.Generator().manual_seed(3)
+    embs, prompts = torch.randn(64, 128, generator=g), torch.randn(5, 2, 4, 128, generator=g)
+    for max_emb in (False, True):
+        loop = O.trainer_val_batch(embs, prompts, True, False, max_emb)
+        vec = O.zero_shot_score(embs, prompts, "max" if max_emb else "mean")
+        assert torch.allclose(loop["logits"], vec["logit"], atol=1e-6)
+        assert torch.allclose(loop["tmp_score"], vec["score"], atol=1e-6)
+        assert torch.equal(loop["predicted_labels"], vec["pred"].float())
+        diff = O.trainer_val_batch(embs, prompts, True, True, max_emb)
+        assert torch.allclose(diff["tmp_score"], vec["score_diff"], atol=1e-6)
+    single = O.trainer_val_batch(embs, prompts, False, False, False)
+    assert single["predicted_labels"].sum() == 0                   # argmax([pos, pos]) -> index 0
+    assert torch.allclose(single["logits"], O.zero_shot_score(embs, prompts, "mean")["sim"][..., 0], atol=1e-6)
+
+
+def test_gaussian_smooth_oracle_handles_views_and_matches_direct_scipy():
+    import numpy as np
+    import torch
+    from scipy import ndimage
+    import biovil_oracle as O
+    heat = torch.rand(2, 15, 15, 3, generator=torch.Generator().manual_seed(1))
+    sm = O.gaussian_smooth_map(heat.permute(0, 3, 1, 2), 1.5)              # non-contiguous view in
+    direct = ndimage.gaussian_filter(heat[1, :, :, 2].numpy(), sigma=(1.5, 1.5), order=0)
+    assert np.array_equal(sm[1, 2].numpy(), direct)
+    # smoothing preserves the mean of a constant map and is bounded by the input range
+    const = O.gaussian_smooth_map(torch.full((1, 15, 15), 0.25), 1.5)
+    assert torch.allclose(const, torch.full((1, 15, 15), 0.25), atol=1e-6)
