@@ -14,6 +14,8 @@
  *                     patch x prompt similarity map              health_multimodal/vlp/inference_engine.py:93-108
  *   bv_set_prompts    Trainer.bert_forward_mean (prompt side)    Trainer.py:1657-1680
  *   bv_score          Trainer.myCosineSimilarity + label loop    Trainer.py:1682-1704, 805-837, 1019-1047
+ *   bv_resize_center_crop_u8  transforms.Resize + CenterCrop on 8-bit frames (Pillow 8bpc bilinear, bit-exact)
+ *                     DataRetrieval.py:175-180; health_multimodal/image/data/transforms.py:30-41
  *   bv_smooth_heatmaps  gaussian_filter(sigma) of the similarity maps health_multimodal/vlp/inference_engine.py:107-109
  *   bv_set_profile / bv_get_profile   (measurement only; no reference counterpart)
  *   bv_conv2d_nhwc    one Conv2d+BatchNorm2d(+ReLU)(+residual)   (unit-test entry for the tcgen05 kernel)
@@ -111,6 +113,13 @@ int32_t bv_forward(bv_handle* h, const void* frames, int32_t dtype, int32_t batc
 /* Score cached embeddings emb [B,128] (un-normalised) against the installed prompts. */
 int32_t bv_score(bv_handle* h, const float* emb, int32_t batch, float* sim, float* prob, uint8_t* pred, float* score,
                  bv_stream stream);
+
+/* Resize(size) -> CenterCrop(crop) of n same-sized 8-bit grayscale frames src [n,h,w] -> out [n,crop,crop] with the
+ * integer arithmetic of Pillow's 8bpc bilinear resampler (short side -> size, long side int(size*long/short), centre
+ * crop offsets int(round((dim-crop)/2))).  workspace: bv_resize_workspace_bytes(...) bytes of device memory. */
+size_t bv_resize_workspace_bytes(int32_t n, int32_t height, int32_t width, int32_t size, int32_t crop);
+int32_t bv_resize_center_crop_u8(const uint8_t* src, int32_t n, int32_t height, int32_t width, int32_t size,
+                                 int32_t crop, uint8_t* out, void* workspace, size_t workspace_bytes, bv_stream stream);
 
 /* Smooth patch-similarity maps heat [B,gh,gw,L] -> out [B,gh,gw,L] with scipy.ndimage.gaussian_filter semantics
  * (order 0, mode 'reflect', truncate 4.0, separable, same sigma on both axes); gh*gw <= 1024, radius <= 16. */

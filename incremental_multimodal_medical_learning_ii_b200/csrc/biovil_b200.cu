@@ -10,6 +10,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -17,6 +19,7 @@
 #include "aux_kernels.cuh"
 #include "chain_gemm.cuh"
 #include "conv_gemm.cuh"
+#include "resize.cuh"
 #include "stem_fused.cuh"
 
 namespace {
@@ -869,6 +872,217 @@ int32_t bv_conv2d_nhwc(const void* x, int32_t B, int32_t H, int32_t W, const bv_
     rc = build_conv(&L, B, ops, nops, residual, relu, out, out_fp32);
     if (rc) return rc;
     return launch_conv(L, reinterpret_cast<cudaStream_t>(stream));
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Resize + CenterCrop (resize.cuh)
+// ---------------------------------------------------------------------------------------------------------------
+}  // extern "C"
+
+namespace {
+
+struct ResampleTable {
+    int ksize = 0;
+    std::vector<int> bounds;  // [out][2]
+    std::vector<int> kk;      // [out][ksize]
+    int* d_bounds = nullptr;
+    int* d_kk = nullptr;
+};
+
+// Pillow Resample.c precompute_coeffs (BILINEAR, support 1.0, box = the whole axis) + normalize_coeffs_8bpc.
+void build_resample_table(int in_size, int out_size, ResampleTable* t) {
+    double scale, filterscale;
+    filterscale = scale = (double)in_size / out_size;
+    if (filterscale < 1.0) filterscale = 1.0;
+    const double support = 1.0 * filterscale;
+    const int ksize = (int)ceil(support) * 2 + 1;
+    t->ksize = ksize;
+    t->bounds.assign((size_t)out_size * 2, 0);
+    t->kk.assign((size_t)out_size * ksize, 0);
+    std::vector<double> k(ksize);
+    const double ss = 1.0 / filterscale;
+    for (int xx = 0; xx < out_size; ++xx) {
+        const double center = 0.0 + (xx + 0.5) * scale;
+        double ww = 0.0;
+        int xmin = (int)(center - support + 0.5);
+        if (xmin < 0) xmin = 0;
+        int xmax = (int)(center + support + 0.5);
+        if (xmax > in_size) xmax = in_size;
+        xmax -= xmin;
+        for (int x = 0; x < ksize; ++x) k[x] = 0.0;
+        for (int x = 0; x < xmax; ++x) {
+            double a = (x + xmin - center + 0.5) * ss;
+            if (a < 0.0) a = -a;
+            const double w = (a < 1.0) ? 1.0 - a : 0.0;
+            k[x] = w;
+            ww += w;
+        }
+        for (int x = 0; x < xmax; ++x)
+            if (ww != 0.0) k[x] /= ww;
+        for (int x = 0; x < ksize; ++x) {
+            const double v = k[x] * (double)(1 << bv::kResamplePrecisionBits);
+            t->kk[(size_t)xx * ksize + x] = (k[x] < 0) ? (int)(-0.5 + v) : (int)(0.5 + v);
+        }
+        t->bounds[2 * xx] = xmin;
+        t->bounds[2 * xx + 1] = xmax;
+    }
+}
+
+std::mutex g_resample_mutex;
+std::map<std::pair<int, int>, ResampleTable> g_resample_tables[16];  // per device
+
+// Device copy of the table for (in_size -> out_size), built once per process and device.
+int get_resample_table(int in_size, int out_size, const ResampleTable** out) {
+    int dev = 0;
+    BV_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 16) return fail(BV_ERR_INVALID, "device index %d out of range", dev);
+    std::lock_guard<std::mutex> lock(g_resample_mutex);
+    auto& cache = g_resample_tables[dev];
+    auto it = cache.find({in_size, out_size});
+    if (it == cache.end()) {
+        ResampleTable t;
+        build_resample_table(in_size, out_size, &t);
+        BV_CUDA(cudaMalloc(&t.d_bounds, t.bounds.size() * sizeof(int)));
+        BV_CUDA(cudaMalloc(&t.d_kk, t.kk.size() * sizeof(int)));
+        BV_CUDA(cudaMemcpy(t.d_bounds, t.bounds.data(), t.bounds.size() * sizeof(int), cudaMemcpyHostToDevice));
+        BV_CUDA(cudaMemcpy(t.d_kk, t.kk.data(), t.kk.size() * sizeof(int), cudaMemcpyHostToDevice));
+        it = cache.emplace(std::make_pair(in_size, out_size), std::move(t)).first;
+    }
+    *out = &it->second;
+    return BV_OK;
+}
+
+// torchvision _compute_resized_output_size (int size) and center_crop offsets
+void resized_size(int h, int w, int size, int* nh, int* nw) {
+    const int short_side = (w <= h) ? w : h, long_side = (w <= h) ? h : w;
+    const int new_long = (int)((double)size * long_side / short_side);
+    if (w <= h) { *nw = size; *nh = new_long; } else { *nh = size; *nw = new_long; }
+}
+int py_round_half(int num) {  // int(round(num / 2.0)) with Python's round-half-to-even
+    if (num % 2 == 0) return num / 2;
+    const int lo = (num - 1) / 2;  // num >= 0 here
+    return (lo % 2 == 0) ? lo : lo + 1;
+}
+
+struct ResizePlan {
+    int nh, nw, top, left;
+    bool need_h, need_v;
+    int row_first, row_count;  // source rows the horizontal pass must produce for the cropped vertical outputs
+    const ResampleTable* th = nullptr;
+    const ResampleTable* tv = nullptr;
+};
+
+int plan_resize(int h, int w, int size, int crop, bool tables, ResizePlan* pl) {
+    if (h <= 0 || w <= 0 || size <= 0 || crop <= 0) return fail(BV_ERR_INVALID, "bad resize arguments");
+    resized_size(h, w, size, &pl->nh, &pl->nw);
+    if (pl->nh < crop || pl->nw < crop)
+        return fail(BV_ERR_INVALID, "crop %d exceeds the resized frame %dx%d (the reference never pads)", crop, pl->nh, pl->nw);
+    pl->top = py_round_half(pl->nh - crop);
+    pl->left = py_round_half(pl->nw - crop);
+    pl->need_h = pl->nw != w;
+    pl->need_v = pl->nh != h;
+    pl->row_first = pl->need_v ? 0 : pl->top;
+    pl->row_count = pl->need_v ? h : crop;
+    if (pl->need_v) {
+        // rows touched by the cropped vertical outputs: [bounds[top].first, bounds[top+crop-1].first + count)
+        ResampleTable tmp;
+        const ResampleTable* tv = &tmp;
+        if (tables) {
+            int rc = get_resample_table(h, pl->nh, &pl->tv);
+            if (rc) return rc;
+            tv = pl->tv;
+        } else {
+            build_resample_table(h, pl->nh, &tmp);
+        }
+        pl->row_first = tv->bounds[2 * pl->top];
+        const int last = pl->top + crop - 1;
+        pl->row_count = tv->bounds[2 * last] + tv->bounds[2 * last + 1] - pl->row_first;
+    }
+    if (pl->need_h && tables) {
+        int rc = get_resample_table(w, pl->nw, &pl->th);
+        if (rc) return rc;
+    }
+    return BV_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+size_t bv_resize_workspace_bytes(int32_t n, int32_t h, int32_t w, int32_t size, int32_t crop) {
+    ResizePlan pl;
+    if (n <= 0 || plan_resize(h, w, size, crop, false, &pl) != BV_OK) return 0;
+    if (!(pl.need_h && pl.need_v)) return 256;  // a single pass writes straight to the output
+    return align_up((size_t)n * pl.row_count * crop, 256) + 256;
+}
+
+int32_t bv_resize_center_crop_u8(const uint8_t* src, int32_t n, int32_t h, int32_t w, int32_t size, int32_t crop,
+                                 uint8_t* out, void* workspace, size_t workspace_bytes, bv_stream stream) {
+    if (!src || !out || n <= 0) return fail(BV_ERR_INVALID, "bad resize arguments");
+    int rc = device_setup();
+    if (rc) return rc;
+    ResizePlan pl;
+    if ((rc = plan_resize(h, w, size, crop, true, &pl))) return rc;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    auto blocks_for = [](long long total) { return (int)std::min<long long>((total + 255) / 256, (long long)g_num_sms * 32); };
+    if (!pl.need_h && !pl.need_v) {
+        bv::crop_copy_kernel<<<blocks_for((long long)n * crop * crop), 256, 0, st>>>(src, out, n, h, w, pl.top, pl.left, crop);
+        BV_CUDA(cudaGetLastError());
+        return BV_OK;
+    }
+    const uint8_t* vsrc = src;     // what the vertical pass reads
+    int v_rows = h, v_pitch = w, v_col0 = pl.left, v_origin = 0;
+    if (pl.need_h) {
+        bv::ResamplePass ph{};
+        ph.src = src;
+        ph.bounds = pl.th->d_bounds;
+        ph.kk = pl.th->d_kk;
+        ph.ksize = pl.th->ksize;
+        ph.n = n;
+        ph.src_rows = h;
+        ph.src_pitch = w;
+        ph.dst_rows = pl.row_count;
+        ph.dst_cols = crop;
+        ph.dst_pitch = crop;
+        ph.out0 = pl.left;
+        ph.other0 = pl.row_first;
+        ph.tap_origin = 0;
+        if (pl.need_v) {
+            const size_t need = (size_t)n * pl.row_count * crop;
+            if (!workspace || workspace_bytes < need)
+                return fail(BV_ERR_WORKSPACE, "resize workspace too small: %zu < %zu", workspace_bytes, need);
+            ph.dst = reinterpret_cast<uint8_t*>(workspace);
+        } else {
+            ph.dst = out;          // rows [top, top + crop) of the source, columns resampled
+        }
+        bv::resample_horizontal_kernel<<<blocks_for((long long)n * pl.row_count * crop), 256, 0, st>>>(ph);
+        BV_CUDA(cudaGetLastError());
+        vsrc = ph.dst;
+        v_rows = pl.row_count;
+        v_pitch = crop;
+        v_col0 = 0;
+        v_origin = pl.row_first;
+    }
+    if (pl.need_v) {
+        bv::ResamplePass pv{};
+        pv.src = vsrc;
+        pv.dst = out;
+        pv.bounds = pl.tv->d_bounds;
+        pv.kk = pl.tv->d_kk;
+        pv.ksize = pl.tv->ksize;
+        pv.n = n;
+        pv.src_rows = v_rows;
+        pv.src_pitch = v_pitch;
+        pv.dst_rows = crop;
+        pv.dst_cols = crop;
+        pv.dst_pitch = crop;
+        pv.out0 = pl.top;
+        pv.other0 = v_col0;
+        pv.tap_origin = v_origin;
+        bv::resample_vertical_kernel<<<blocks_for((long long)n * crop * crop), 256, 0, st>>>(pv);
+        BV_CUDA(cudaGetLastError());
+    }
+    return BV_OK;
 }
 
 int32_t bv_smooth_heatmaps(const float* heat, int32_t B, int32_t gh, int32_t gw, int32_t L, float sigma, float* out,

@@ -115,7 +115,8 @@ class AsyncChunkWriter:
                 ev = torch.cuda.Event()
                 ev.record(self._stream)
             embeddings.record_stream(self._stream)
-            labels.record_stream(self._stream)
+            if labels.is_cuda:
+                labels.record_stream(self._stream)
             self._q.put(("block", e, l, ev))
         else:
             self._q.put(("block", embeddings.detach().float().clone(), labels.detach().float().clone(), None))

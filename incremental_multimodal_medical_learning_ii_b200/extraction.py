@@ -119,3 +119,30 @@ def extract_embeddings(model, frame_source: FrameSource, n_frames: int, batch_si
         keys = ("global",)
     local = extract_shard(embed_fn, frame_source, n_frames, batch_size, rank, world_size, keys)
     return gather_shards(local, n_frames, rank, world_size, keys)
+
+
+def extract_to_store(model, raw_frame_source: Callable[[int, int], torch.Tensor],
+                     label_source: Callable[[int, int], torch.Tensor], n_frames: int, out_dir: str,
+                     resize: int = 512, crop: int = 480, batch_size: int = 512, chunk: int = 5000,
+                     rank: int = 0, world_size: int = 1) -> list:
+    """The whole ``chexpert-get-embedding.py`` job for this rank's shard, on the device end to end:
+    raw 8-bit frames -> GPU Resize/CenterCrop (PIL-exact) -> ``ImageModel`` -> un-normalised ``[n,128]`` embeddings ->
+    reference-format chunk files written by a background thread (``embedding_store.AsyncChunkWriter``).
+
+    ``raw_frame_source(first, count)`` returns decoded frames ``[count,h,w]`` uint8 (same size within a call) on the
+    model's device or on the host; ``label_source(first, count)`` the ``[count,5]`` labels.  Each rank writes its
+    shard under ``out_dir/rank{r}`` (one directory when ``world_size == 1``), so ranks never contend for a file and
+    gluing the rank directories in rank order reproduces the reference's sequential order."""
+    from .embedding_store import AsyncChunkWriter
+    from .image.data.gpu_transforms import GpuResizeCenterCrop
+    device = next(model.parameters()).device
+    transform = GpuResizeCenterCrop(resize, crop)
+    start, end = shard_range(n_frames, rank, world_size)
+    directory = out_dir if world_size == 1 else os.path.join(out_dir, f"rank{rank}")
+    with AsyncChunkWriter(directory, chunk=chunk) as writer:
+        for first in range(start, end, batch_size):
+            count = min(batch_size, end - first)
+            raw = raw_frame_source(first, count).to(device, non_blocking=True)
+            emb = model(transform(raw)).projected_global_embedding
+            writer.add(emb, label_source(first, count))
+    return writer.paths

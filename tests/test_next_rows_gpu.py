@@ -55,3 +55,30 @@ def test_heatmap_smoothing_rejects_bad_arguments():
         model.smooth_heatmaps(torch.zeros(1, 15, 15, 2, device="cuda"), sigma=10.0)   # radius 40 > 16
     with pytest.raises(NativeError):
         model.smooth_heatmaps(torch.zeros(1, 40, 40, 2, device="cuda"))        # 1600 cells > 1024
+
+
+def test_extract_to_store_end_to_end(tmp_path):
+    """Raw frames -> GPU resize -> model -> async chunk files: embeddings equal a direct forward of the PIL-resized
+    frames, files follow the reference naming, labels are carried through."""
+    import numpy as np
+    import pil_resize_oracle as R
+    import weights as Wt
+    from incremental_multimodal_medical_learning_ii_b200 import embedding_store as ES
+    from incremental_multimodal_medical_learning_ii_b200.extraction import extract_to_store
+    from incremental_multimodal_medical_learning_ii_b200.image import get_biovil_resnet
+    model = get_biovil_resnet(None)
+    model.load_state_dict(Wt.make_state_dict(27, randomize_bn=True))
+    model.eval().to("cuda:0")
+    n, h, w = 11, 80, 100
+    g = np.random.default_rng(0)
+    raw = torch.from_numpy(g.integers(0, 256, size=(n, h, w)).astype(np.uint8))
+    labels = torch.from_numpy((g.random((n, 5)) > 0.5).astype(np.float32))
+    paths = extract_to_store(model, lambda f, c: raw[f:f + c], lambda f, c: labels[f:f + c], n, str(tmp_path),
+                             resize=128, crop=96, batch_size=4, chunk=5)
+    assert [p.split("/")[-1] for p in paths] == ["embeddings_dataset_5.pt", "embeddings_dataset_10.pt",
+                                                 "embeddings_dataset_final.pt"]
+    flat = ES.concat_to_tensors(ES.load_embedding_chunks(str(tmp_path)))
+    assert flat.tensors[0].shape == (n, 128) and torch.equal(flat.tensors[1], labels)
+    resized = torch.from_numpy(np.stack([R.resize_center_crop(f.numpy(), 128, 96) for f in raw])).unsqueeze(1)
+    direct = model(resized.cuda()).projected_global_embedding.cpu()
+    assert torch.equal(flat.tensors[0], direct)            # same kernels on the same bytes: identical embeddings
