@@ -18,6 +18,7 @@
 #include "../../include/biovil_b200.h"
 #include "aux_kernels.cuh"
 #include "chain_gemm.cuh"
+#include "conv3x3_tap3.cuh"
 #include "conv_gemm.cuh"
 #include "resize.cuh"
 #include "stem_fused.cuh"
@@ -79,7 +80,7 @@ int make_tmap_2d(CUtensorMap* tm, const void* base, uint64_t inner, uint64_t out
 
 // NHWC activation tensor [N][H][W][C] seen by TMA as (C, W, H, N); 128 output pixels x 64 channels per load.
 int make_tmap_im2col(CUtensorMap* tm, const void* base, int N, int H, int W, int C, int R, int S, int stride,
-                     int pad, bool wide = false) {
+                     int pad, bool wide = false, int pixels = 0) {
     cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
     cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
     int lower[2] = {-pad, -pad};
@@ -87,7 +88,7 @@ int make_tmap_im2col(CUtensorMap* tm, const void* base, int N, int H, int W, int
     if (wide) upper[0] = pad;  // window origins -pad .. W-1+pad: the zero-padded image row, linear in memory order
     cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
     CUresult r = g_encode_im2col(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides,
-                                 lower, upper, bv::kBlockK, wide ? bv::kWideRows : bv::kBlockM, estr,
+                                 lower, upper, bv::kBlockK, pixels > 0 ? pixels : (wide ? bv::kWideRows : bv::kBlockM), estr,
                                  CU_TENSOR_MAP_INTERLEAVE_NONE,
                                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -109,12 +110,13 @@ struct ConvOperand {
 };
 
 // Kernel configurations <BN, STAGES, NBUF> (see ConvGemmCfg): picked per layer by arithmetic intensity.
-enum ConvCfg { kCfg256Deep = 0, kCfg256Res, kCfg128Res, kCfg128Deep, kCfg64, kCfg64BRes, kCfg64Wide, kNumCfg };
+enum ConvCfg { kCfg256Deep = 0, kCfg256Res, kCfg128Res, kCfg128Deep, kCfg64, kCfg64BRes, kCfg64Wide, kCfg64Tap3, kNumCfg };
+// kCfg64Tap3 is a different kernel (conv3x3_tap3.cuh): the three horizontal taps of a filter row in one N = 192 MMA
 #define BV_FOR_EACH_CFG(X)                                                                                        \
     X(kCfg256Deep, 256, 4, 2, false, false) X(kCfg256Res, 256, 3, 4, false, false)                                \
     X(kCfg128Res, 128, 3, 7, false, false) X(kCfg128Deep, 128, 6, 2, false, false) X(kCfg64, 64, 8, 2, false, false) \
     X(kCfg64BRes, 64, 6, 2, true, false) X(kCfg64Wide, 64, 6, 2, true, true)
-const int kCfgBN[kNumCfg] = {256, 256, 128, 128, 64, 64, 64};
+const int kCfgBN[kNumCfg] = {256, 256, 128, 128, 64, 64, 64, 64};
 
 struct ConvLaunch {
     bv::ConvGemmParams p;
@@ -172,6 +174,8 @@ int device_setup() {
                                  bv::ChainCfg<N2, ST, NB>::kSmemBytes));
         BV_FOR_EACH_CHAIN(BV_SET_CHAIN_ATTR)
 #undef BV_SET_CHAIN_ATTR
+        BV_CUDA(cudaFuncSetAttribute(bv::conv3x3_tap3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     bv::kTap3SmemBytes));
         BV_CUDA(cudaFuncSetAttribute(bv::head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
         BV_CUDA(cudaFuncSetAttribute(bv::stem_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      bv::kStemSmemRequest));
@@ -207,6 +211,8 @@ int build_conv(ConvLaunch* L, int B, const ConvOperand* ops, int nops, const voi
     const bool wide_ok = nops == 1 && c0.r == 3 && c0.s == 3 && c0.stride == 1 && c0.pad == 1 && !residual &&
                          !out_fp32 && N == 64 && total_kblocks <= bv::kMaxResidentKB;
     if (cfg == kCfg64BRes && wide_ok && !env_flag("BV_NO_WIDE")) cfg = kCfg64Wide;
+    const bool tap3_ok = wide_ok && c0.cin == 64;
+    if (cfg == kCfg64Wide && tap3_ok && !env_flag("BV_NO_TAP3")) cfg = kCfg64Tap3;
     if (const char* force = getenv("BV_FORCE_CFG")) {
         const int f = atoi(force);
         if (f >= 0 && f < kNumCfg && N % kCfgBN[f] == 0 &&
@@ -214,7 +220,9 @@ int build_conv(ConvLaunch* L, int B, const ConvOperand* ops, int nops, const voi
             cfg = f;
     }
     if (cfg == kCfg64Wide && !wide_ok) cfg = kCfg64;
-    const bool wide = cfg == kCfg64Wide;
+    if (cfg == kCfg64Tap3 && !tap3_ok) cfg = kCfg64;
+    const bool tap3 = cfg == kCfg64Tap3;
+    const bool wide = cfg == kCfg64Wide || tap3;
     const int bn = kCfgBN[cfg];
     const long long M = wide ? (long long)B * Ho * (Wo + 2) : (long long)B * Ho * Wo;
     if (M <= 0 || M > 0x7fffffffLL - 256) return fail(BV_ERR_INVALID, "M=%lld out of range", M);
@@ -237,7 +245,8 @@ int build_conv(ConvLaunch* L, int B, const ConvOperand* ops, int nops, const voi
         if (sg.mode == bv::kSegTiled) {
             rc = make_tmap_2d(&p.tmA[i], ops[i].x, (uint64_t)c.cin, (uint64_t)M, bv::kBlockK, bv::kBlockM);
         } else {
-            rc = make_tmap_im2col(&p.tmA[i], ops[i].x, B, ops[i].H, ops[i].W, c.cin, c.r, c.s, c.stride, c.pad, wide);
+            rc = make_tmap_im2col(&p.tmA[i], ops[i].x, B, ops[i].H, ops[i].W, c.cin, c.r, c.s, c.stride, c.pad, wide,
+                                  tap3 ? 32 : 0);
         }
         if (rc) return rc;
         rc = make_tmap_2d(&p.tmB[i], c.w, (uint64_t)c.r * c.s * c.cin, (uint64_t)N, bv::kBlockK, (uint32_t)bn);
@@ -258,7 +267,7 @@ int build_conv(ConvLaunch* L, int B, const ConvOperand* ops, int nops, const voi
     p.Wo = Wo;
     p.M = (int)M;
     p.N = N;
-    p.num_m_blocks = (int)((M + bv::kBlockM - 1) / bv::kBlockM);
+    p.num_m_blocks = tap3 ? (int)((M + bv::kTap3Rows - 1) / bv::kTap3Rows) : (int)((M + bv::kBlockM - 1) / bv::kBlockM);
     p.num_n_blocks = N / bn;
     p.residual = reinterpret_cast<const __nv_bfloat16*>(residual);
     p.out = out;
@@ -294,6 +303,9 @@ int launch_conv(const ConvLaunch& L0, cudaStream_t st) {
         break;
         BV_FOR_EACH_CFG(BV_LAUNCH)
 #undef BV_LAUNCH
+        case kCfg64Tap3:
+            bv::conv3x3_tap3_kernel<<<L.grid, bv::kTap3Threads, bv::kTap3SmemBytes, st>>>(L.p);
+            break;
         default:
             return fail(BV_ERR_INVALID, "unknown conv configuration %d", L.cfg);
     }

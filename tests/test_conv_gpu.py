@@ -194,11 +194,12 @@ def test_many_tiles_persistent(env):
     assert torch.equal(out, ref)
 
 
-@pytest.mark.parametrize("cfg", [4, 5, 6], ids=["stream", "weights_resident", "wide_rows"])
-@pytest.mark.parametrize("H", [15, 60])
+@pytest.mark.parametrize("cfg", [4, 5, 6, 7], ids=["stream", "weights_resident", "wide_rows", "tap3_n192"])
+@pytest.mark.parametrize("H", [15, 60, 37])
 def test_narrow_3x3_configurations(env, cfg, H, monkeypatch):
-    """The three N=64 kernels on the layer1 3x3 shape: B tiles streamed, weights resident in smem, and the wide-row
-    mode (one 130-pixel load per filter row, horizontal taps through row-shifted smem descriptors)."""
+    """The four N=64 kernels on the layer1 3x3 shape: B tiles streamed, weights resident in smem, the wide-row mode
+    (one 130-pixel load per filter row, horizontal taps through row-shifted smem descriptors) and the tap-fused kernel
+    (conv3x3_tap3.cuh: one N=192 MMA per filter row, taps recombined across rows in the epilogue)."""
     N, lib, packing = env
     monkeypatch.setenv("BV_FORCE_CFG", str(cfg))
     gen = torch.Generator().manual_seed(17 + H)

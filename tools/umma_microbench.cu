@@ -61,6 +61,7 @@ int main() {
     for (int grid : {1, 148}) {
         run<64>(1, 1, grid); run<64>(4, 1, grid); run<64>(4, 8, grid);
         run<128>(1, 1, grid); run<128>(2, 1, grid); run<128>(2, 8, grid);
+        run<192>(1, 1, grid); run<192>(2, 8, grid);
         run<256>(1, 1, grid); run<256>(2, 8, grid);
     }
     return 0;
