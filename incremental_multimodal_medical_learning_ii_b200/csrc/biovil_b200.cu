@@ -207,7 +207,10 @@ int build_conv(ConvLaunch* L, int B, const ConvOperand* ops, int nops, const voi
     if (N % 128 != 0) cfg = (N == 64 && total_kblocks <= bv::kMaxResidentKB && !env_flag("BV_NO_BRES")) ? kCfg64BRes : kCfg64;
     else if (N % 256 != 0) cfg = kCfg128Deep;
     else if (total_kblocks >= 8) cfg = res_stream ? kCfg256Res : kCfg256Deep;
-    else cfg = res_stream ? kCfg128Res : kCfg256Res;  // short K: HBM-bound, wants staging depth
+    // short K: HBM-bound, wants staging depth.  From four k-blocks on, the A/B re-reads of 128-wide tiles saturate the
+    // L2 -> SM path before HBM does (layer3 conv3: 160 KB of operand + residual loads per 32 KB of output), and the
+    // 256-wide tile, which moves 20 % less, is faster (0.478 vs 0.525 ms, profiles/r1w notes).
+    else cfg = res_stream ? (total_kblocks >= 4 ? kCfg256Res : kCfg128Res) : kCfg256Res;
     const bool wide_ok = nops == 1 && c0.r == 3 && c0.s == 3 && c0.stride == 1 && c0.pad == 1 && !residual &&
                          !out_fp32 && N == 64 && total_kblocks <= bv::kMaxResidentKB;
     if (cfg == kCfg64BRes && wide_ok && !env_flag("BV_NO_WIDE")) cfg = kCfg64Wide;
