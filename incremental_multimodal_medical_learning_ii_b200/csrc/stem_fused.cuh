@@ -12,10 +12,15 @@
 //   1. cp.async the NEXT tile's raw bytes (zero-filled outside the frame) while working on this one
 //   2. u8 -> bf16 into a small smem image
 //   3. build the im2col A operand in the 128B-swizzled K-major layout tcgen05 reads: row = conv pixel,
-//      k = r*8 + s (7 rows x 8 columns of the window; column 7 and k >= 56 have zero weights)
+//      k = r*8 + s (7 rows x 8 columns of the window; column 7 has zero weights); k = 56..58 hold 1.0 against the
+//      BatchNorm bias split into three bf16 terms, so the bias is added by the MMA itself
 //   4. one thread issues 3 x 4 tcgen05.mma (128x64x16) into three TMEM accumulators
-//   5. all warps: TMEM -> bias + ReLU -> bf16 conv tile in smem (aliasing the dead A operand)
-//   6. 3x3/2 max-pool from smem, 16-byte coalesced stores of the pooled pixels
+//   5. all warps: TMEM -> bf16 conv tile in smem (aliasing the dead A operand); no arithmetic
+//   6. 3x3/2 max-pool from smem, THEN ReLU (max, ReLU and the bf16 rounding are monotonic, so
+//      relu(max(round(x))) == max(round(relu(x))) exactly, on 64 pooled instead of 289 conv pixels),
+//      16-byte coalesced stores of the pooled pixels
+// (Converting the next tile's pixels while this tile's MMAs run was measured slower: the two extra CTA barriers
+// inside the MMA window cost more than the conversion they hide.)
 // Persistent CTAs, two per SM (TMEM: 256 columns each) so one CTA's load/convert phases overlap the other's math.
 #pragma once
 #include "ptx.cuh"
@@ -121,9 +126,6 @@ __global__ void __launch_bounds__(kStemThreads, 2) stem_fused_kernel(const __gri
     constexpr uint32_t idesc = umma_idesc_bf16_f32(128, 64);
     const int quarter = warp & 3;   // TMEM lane quarter of this warp
     const int half = warp >> 2;     // which 32 of the 64 output channels this warp converts
-    float bias_r[32];
-#pragma unroll
-    for (int j = 0; j < 32; ++j) bias_r[j] = __ldg(p.bias + half * 32 + j);
 
     // Tile-independent index tables (the divisions by 17 are done once per CTA, not once per tile):
     //   tab[i] for im2col item i = (row m, chunk r): low 16 bits = byte offset of the 16 source bytes in in_s
@@ -182,7 +184,7 @@ __global__ void __launch_bounds__(kStemThreads, 2) stem_fused_kernel(const __gri
 #pragma unroll 2
         for (int i = tid; i < kStemRows * 8; i += kStemThreads) {
             const uint32_t e = tab[i];
-            uint4 v = make_uint4(0u, 0u, 0u, 0u);
+            uint4 v = make_uint4(0x3F803F80u, 0x00003F80u, 0u, 0u);   // chunk 7: k = 56..58 = 1.0 (bias columns)
             if ((e & 0xFFFFu) != 0xFFFFu) {
                 const uint32_t* src =
                     reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint8_t*>(in_s) + (e & 0xFFFFu));
@@ -213,7 +215,7 @@ __global__ void __launch_bounds__(kStemThreads, 2) stem_fused_kernel(const __gri
         mbar_wait(mma_bar, it & 1u);
         tc_fence_after();
 
-        // ---- 5. TMEM -> bias + ReLU -> bf16 conv tile (overwrites A: the MMAs have finished reading it) ----
+        // ---- 5. TMEM (conv + bias) -> bf16 conv tile (overwrites A: the MMAs have finished reading it) ----
 #pragma unroll
         for (int blk = 0; blk < 3; ++blk) {
             const int m = blk * 128 + quarter * 32 + lane;
@@ -224,19 +226,17 @@ __global__ void __launch_bounds__(kStemThreads, 2) stem_fused_kernel(const __gri
             if (m < kStemRows) {
                 const int cy = static_cast<int>(epi_yx[blk] & 0xFFu), cx = static_cast<int>(epi_yx[blk] >> 8);
                 const int yc = 2 * Y0 - 1 + cy, xc = 2 * X0 - 1 + cx;
-                // conv pixels outside the conv image are the max-pool's padding: post-ReLU values are >= 0 and every
-                // window holds a real pixel, so 0 never wins over the reference's -inf padding semantics
+                // conv pixels outside the conv image are the max-pool's padding: -inf never wins (every window holds
+                // a real pixel), which is the reference's padding semantics
                 const bool inside = yc >= 0 && yc < Hc && xc >= 0 && xc < Wc;
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     uint32_t w[4];
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
-                        float a = fmaxf(__uint_as_float(v[8 * j + 2 * e]) + bias_r[8 * j + 2 * e], 0.0f);
-                        float c = fmaxf(__uint_as_float(v[8 * j + 2 * e + 1]) + bias_r[8 * j + 2 * e + 1], 0.0f);
-                        if (!inside) a = c = 0.0f;
-                        const __nv_bfloat162 h2 = __floats2bfloat162_rn(a, c);
-                        w[e] = *reinterpret_cast<const uint32_t*>(&h2);
+                        const __nv_bfloat162 h2 =
+                            __floats2bfloat162_rn(__uint_as_float(v[8 * j + 2 * e]), __uint_as_float(v[8 * j + 2 * e + 1]));
+                        w[e] = inside ? *reinterpret_cast<const uint32_t*>(&h2) : 0xFF80FF80u;
                     }
                     *reinterpret_cast<uint4*>(smem_a + m * 128 + (((half * 4 + j) ^ (m & 7)) << 4)) =
                         make_uint4(w[0], w[1], w[2], w[3]);
@@ -267,6 +267,9 @@ __global__ void __launch_bounds__(kStemThreads, 2) stem_fused_kernel(const __gri
                     }
                 }
             }
+            const __nv_bfloat162 zero2 = __floats2bfloat162_rn(0.0f, 0.0f);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) mx[e] = __hmax2(mx[e], zero2);   // ReLU after the pool
             uint4 o;
             o.x = *reinterpret_cast<uint32_t*>(&mx[0]);
             o.y = *reinterpret_cast<uint32_t*>(&mx[1]);

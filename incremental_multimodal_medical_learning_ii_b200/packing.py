@@ -57,9 +57,16 @@ class PackedWeights:
         self.struct.stem_f3 = self._matrix(torch.nn.functional.pad(w3, (0, 192 - 147)), b, cin=192)
         self.struct.stem_f1 = self._matrix(torch.nn.functional.pad(w1, (0, 64 - 49)), b, cin=64)
         self.struct.stem_u8 = self._matrix(torch.nn.functional.pad(w1 / 255.0, (0, 64 - 49)), b, cin=64)
-        # fused stem kernel: k = r*8 + s, window column s = 7 and row r = 7 carry zero weights
+        # fused stem kernel: k = r*8 + s, window column s = 7 carries zero weights; row r = 7 (k = 56..58) carries the
+        # BatchNorm bias split into three bf16 terms (hi + mid + lo reproduces the fp32 bias to 24 bits): the kernel
+        # feeds 1.0 in those three A columns, so the accumulator already holds conv + bias
         w8 = torch.zeros(64, 8, 8, dtype=w.dtype)
         w8[:, :7, :7] = w.sum(dim=1) / 255.0
+        b64 = b.double()
+        b_hi = b64.float().to(torch.bfloat16)
+        b_mid = (b64 - b_hi.double()).float().to(torch.bfloat16)
+        b_lo = (b64 - b_hi.double() - b_mid.double()).float().to(torch.bfloat16)
+        w8[:, 7, 0], w8[:, 7, 1], w8[:, 7, 2] = b_hi.to(w.dtype), b_mid.to(w.dtype), b_lo.to(w.dtype)
         self.struct.stem_u8_k8 = self._matrix(w8.reshape(64, 64), b, cin=64)
 
         # ---- bottlenecks ------------------------------------------------------------------------------------
