@@ -347,10 +347,34 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-out", default=None, help="write the per-launch CUDA-event table (CSV) here")
     args = ap.parse_args()
-    if args.impl == "reference":
-        run_reference(args)
-    else:
-        run_ours(args)
+    # Libraries (NCCL's version banner, torch.distributed warnings) write to fd 1; the contract is ONE JSON line on
+    # stdout, so everything but that line goes to stderr.
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    out_lines = []
+    builtin_print = print
+
+    def capture_print(*a, **k):
+        if k.get("file") in (None, sys.stdout):
+            out_lines.append(" ".join(str(x) for x in a))
+        else:
+            builtin_print(*a, **k)
+
+    import builtins
+    builtins.print = capture_print
+    try:
+        if args.impl == "reference":
+            run_reference(args)
+        else:
+            run_ours(args)
+    finally:
+        builtins.print = builtin_print
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        os.close(real_stdout)
+    for line in out_lines:
+        print(line, flush=True)
 
 
 if __name__ == "__main__":

@@ -332,7 +332,7 @@ int launch_conv(const ConvLaunch& L0, cudaStream_t st) {
 // ops[0] = conv3 operand, ops[1] = optional downsample operand; `next` = the following conv1 (1x1, stride 1).
 bool chain_supported(const ConvOperand* ops, int nops, const bv_conv& next) {
     const int n1 = ops[0].c.cout;
-    if (n1 % bv::kChainBN1 != 0 || n1 > 512) return false;
+    if (n1 % bv::kChainBN1 != 0 || n1 > 1024) return false;
     if (next.r != 1 || next.s != 1 || next.stride != 1 || next.pad != 0 || next.cin != n1) return false;
     if (next.cout != 64 && next.cout != 128 && next.cout != 256) return false;
     for (int i = 0; i < nops; ++i)
@@ -698,7 +698,8 @@ static int build_plan(bv_handle* h, const void* frames, int dtype, int B, int C,
             t1_ready = false;
             // Measured losses stay unchained: the strided-downsample tail of layer2.0 (six A k-blocks re-streamed per
             // chunk) and the 256-wide second GEMM into layer3 (its staging leaves too little residual prefetch depth).
-            const bool chain_pays = env_flag("BV_CHAIN_ALL") ||
+            const bool chain_l3 = env_flag("BV_CHAIN_L3") && c3.cout == 1024 && n3 == 1;
+            const bool chain_pays = env_flag("BV_CHAIN_ALL") || chain_l3 ||
                                     (!(n3 == 2 && ds.cin * ds.r * ds.s > 64) && h->w.conv1[blk + 1 < BV_NUM_BLOCKS ? blk + 1 : blk].cout <= 128);
             if (use_chain && chain_pays && blk + 1 < BV_NUM_BLOCKS && chain_supported(o3, n3, h->w.conv1[blk + 1])) {
                 PlanStep s;
