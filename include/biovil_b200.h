@@ -158,6 +158,10 @@ int32_t bv_conv_chain_nhwc(const void* x, int32_t batch, int32_t height, int32_t
                            const void* x2, int32_t height2, int32_t width2, const bv_conv* host_c2,
                            const void* residual, void* out1, const bv_conv* host_next, void* out2, bv_stream stream);
 
+/* Validation vehicle for the CTA-pair (tcgen05 cta_group::2) building blocks in csrc/pair_gemm.cuh:
+ *   out[M,N] (fp32) = a[M,K] (bf16) x w[N,K]^T (bf16);  N multiple of 32 in [32,256], K multiple of 64. */
+int32_t bv_pair_gemm_test(const void* a, const void* w, int32_t m, int32_t n, int32_t k, float* out, bv_stream stream);
+
 #ifdef __cplusplus
 }
 #endif

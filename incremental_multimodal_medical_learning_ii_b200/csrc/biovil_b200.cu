@@ -20,6 +20,7 @@
 #include "chain_gemm.cuh"
 #include "conv3x3_tap3.cuh"
 #include "conv_gemm.cuh"
+#include "pair_gemm.cuh"
 #include "resize.cuh"
 #include "stem_fused.cuh"
 
@@ -1122,6 +1123,41 @@ int32_t bv_smooth_heatmaps(const float* heat, int32_t B, int32_t gh, int32_t gw,
     p.radius = radius;
     bv::heat_smooth_kernel<<<B * L, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
     BV_CUDA(cudaGetLastError());
+    return BV_OK;
+}
+
+int32_t bv_pair_gemm_test(const void* a, const void* w, int32_t M, int32_t N, int32_t K, float* out, bv_stream stream) {
+    if (!a || !w || !out) return fail(BV_ERR_INVALID, "null argument");
+    if (M <= 0 || N < 32 || N > 256 || N % 32 || K <= 0 || K % 64) return fail(BV_ERR_INVALID, "unsupported pair GEMM shape");
+    int rc = device_setup();
+    if (rc) return rc;
+    bv::PairGemmParams p{};
+    if ((rc = make_tmap_2d(&p.tmA, a, (uint64_t)K, (uint64_t)M, 64, 128))) return rc;
+    if ((rc = make_tmap_2d(&p.tmB, w, (uint64_t)K, (uint64_t)N, 64, (uint32_t)(N / 2)))) return rc;
+    p.out = out;
+    p.M = M;
+    p.N = N;
+    p.K = K;
+    p.num_pair_tiles = (M + 255) / 256;
+    static bool attr = false;
+    if (!attr) {
+        BV_CUDA(cudaFuncSetAttribute(bv::pair_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bv::kPairSmemBytes));
+        attr = true;
+    }
+    cudaLaunchConfig_t cfg{};
+    const int pairs = std::min(p.num_pair_tiles, g_num_sms / 2);
+    cfg.gridDim = dim3(2 * pairs, 1, 1);
+    cfg.blockDim = dim3(bv::kPairThreads, 1, 1);
+    cfg.dynamicSmemBytes = bv::kPairSmemBytes;
+    cfg.stream = reinterpret_cast<cudaStream_t>(stream);
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    BV_CUDA(cudaLaunchKernelEx(&cfg, bv::pair_gemm_kernel, p));
     return BV_OK;
 }
 

@@ -174,3 +174,23 @@ def test_fused_stem_matches_unfused_path(setup, monkeypatch):
         relt = ((trunk_f - trunk_p).norm() / trunk_p.norm()).item()
         print(f"[{variant}] fused vs unfused stem {B}x{H}x{W}: embedding rel {rel:.2e}, trunk rel {relt:.2e}")
         assert rel <= 2e-3 and relt <= 1e-2      # two bf16 pipelines; both sit ~4e-3 from the fp32 oracle
+
+
+def test_batch_invariance_and_ragged_batches(setup):
+    """Size-independent property: a frame's embedding and scores do not depend on the batch it travels in (GEMM rows
+    are independent; tiles, chunks and persistent-CTA schedules change with the batch).  Covers odd batch sizes whose
+    GEMM row counts are not multiples of the 128-row tile at every layer (ragged last tiles in all kernels)."""
+    from incremental_multimodal_medical_learning_ii_b200 import frames as FR
+    variant, m, sd, golden = setup
+    prompts = FR.synthetic_prompt_embeddings(14, 1, 128, seed=29)
+    m.set_prompts(prompts, reduce="mean")
+    fr = FR.synthetic_frames_u8(100, 37, 480, kind="structured", seed=0).to(DEV)
+    full = m.embed_and_score(fr)
+    for n in (1, 7, 33):
+        part = m.embed_and_score(fr[:n].contiguous())
+        for k in ("global", "prob", "pred", "sim"):
+            assert torch.equal(part[k], full[k][:n]), f"[{variant}] batch of {n} differs from batch of 37 in {k}"
+    small = FR.synthetic_frames_u8(5, 9, 96, kind="iid", seed=1).to(DEV)          # 96x96: 3x3 patch grid, M = 9 * 9 at layer4
+    a = m.embed_and_score(small)
+    b = m.embed_and_score(small[2:5].contiguous())
+    assert torch.equal(a["global"][2:5], b["global"])
