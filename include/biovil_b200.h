@@ -158,6 +158,16 @@ int32_t bv_conv_chain_nhwc(const void* x, int32_t batch, int32_t height, int32_t
                            const void* x2, int32_t height2, int32_t width2, const bv_conv* host_c2,
                            const void* residual, void* out1, const bv_conv* host_next, void* out2, bv_stream stream);
 
+/* Fused layer1 Bottleneck tail on CTA pairs (l1_block.cuh), unit-test entry:
+ *   t2   = relu(conv3x3(t1, c2) + c2.bias)                       (64 -> 64 channels, stride 1, pad 1; never stored)
+ *   out1 = relu(conv1x1(t2, c3) + c3.bias + residual)  [B,H,W,256] bf16
+ *   out2 = relu(conv1x1(out1, next) + next.bias)       [B,H,W,64]  bf16
+ * Replaces Bottleneck.conv2/bn2/relu, conv3/bn3/+identity/relu and the next Bottleneck's conv1/bn1/relu
+ * (torchvision Bottleneck.forward under health_multimodal/image/model/resnet.py:39). */
+int32_t bv_l1_block_nhwc(const void* t1, int32_t batch, int32_t height, int32_t width, const bv_conv* host_c2,
+                         const bv_conv* host_c3, const void* residual, void* out1, const bv_conv* host_next, void* out2,
+                         bv_stream stream);
+
 /* Validation vehicle for the CTA-pair (tcgen05 cta_group::2) building blocks in csrc/pair_gemm.cuh:
  *   out[M,N] (fp32) = a[M,K] (bf16) x w[N,K]^T (bf16);  N multiple of 32 in [32,256], K multiple of 64. */
 int32_t bv_pair_gemm_test(const void* a, const void* w, int32_t m, int32_t n, int32_t k, float* out, bv_stream stream);

@@ -66,7 +66,7 @@ EXPORTED_SYMBOLS = (
     "bv_last_error", "bv_version", "bv_workspace_bytes", "bv_patch_grid", "bv_create", "bv_destroy",
     "bv_set_prompts", "bv_forward", "bv_score", "bv_last_forward_launches", "bv_set_profile", "bv_get_profile",
     "bv_conv2d_nhwc", "bv_conv_chain_nhwc", "bv_smooth_heatmaps",
-    "bv_resize_workspace_bytes", "bv_resize_center_crop_u8", "bv_pair_gemm_test",
+    "bv_resize_workspace_bytes", "bv_resize_center_crop_u8", "bv_pair_gemm_test", "bv_l1_block_nhwc",
 )
 
 _lib = None
@@ -137,6 +137,9 @@ def lib() -> ctypes.CDLL:
     l.bv_resize_center_crop_u8.restype = c_int32
     l.bv_resize_center_crop_u8.argtypes = [c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p,
                                            c_size_t, c_void_p]
+    l.bv_l1_block_nhwc.restype = c_int32
+    l.bv_l1_block_nhwc.argtypes = [c_void_p, c_int32, c_int32, c_int32, POINTER(BvConv), POINTER(BvConv), c_void_p, c_void_p,
+                                   POINTER(BvConv), c_void_p, c_void_p]
     l.bv_pair_gemm_test.restype = c_int32
     l.bv_pair_gemm_test.argtypes = [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p]
     l.bv_smooth_heatmaps.restype = c_int32

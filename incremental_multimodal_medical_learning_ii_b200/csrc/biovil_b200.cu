@@ -20,6 +20,7 @@
 #include "chain_gemm.cuh"
 #include "conv3x3_tap3.cuh"
 #include "conv_gemm.cuh"
+#include "l1_block.cuh"
 #include "pair_gemm.cuh"
 #include "resize.cuh"
 #include "stem_fused.cuh"
@@ -81,12 +82,16 @@ int make_tmap_2d(CUtensorMap* tm, const void* base, uint64_t inner, uint64_t out
 
 // NHWC activation tensor [N][H][W][C] seen by TMA as (C, W, H, N); 128 output pixels x 64 channels per load.
 int make_tmap_im2col(CUtensorMap* tm, const void* base, int N, int H, int W, int C, int R, int S, int stride,
-                     int pad, bool wide = false, int pixels = 0) {
+                     int pad, bool wide = false, int pixels = 0, bool widen_right = false) {
     cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
     cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
     int lower[2] = {-pad, -pad};
     int upper[2] = {pad - (S - 1), pad - (R - 1)};
     if (wide) upper[0] = pad;  // window origins -pad .. W-1+pad: the zero-padded image row, linear in memory order
+    if (widen_right) {         // 1x1 view of an OUTPUT-sized tensor in the same widened row space: pixels 0 .. W+1 per row
+        lower[0] = 0;
+        upper[0] = 2;
+    }
     cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
     CUresult r = g_encode_im2col(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides,
                                  lower, upper, bv::kBlockK, pixels > 0 ? pixels : (wide ? bv::kWideRows : bv::kBlockM), estr,
@@ -138,11 +143,19 @@ struct ChainLaunch {
     int k1;  // total K of the first GEMM (for cost accounting)
 };
 
-// One step of the forward plan: a single fused convolution or a chained pair.
+// Fused layer1 block on CTA pairs (l1_block.cuh): conv2 3x3 + conv3 + identity + next conv1.
+struct L1Launch {
+    bv::L1BlockParams p;
+    int grid;
+};
+
+// One step of the forward plan: a single fused convolution, a chained pair, or a fused layer1 block.
 struct PlanStep {
     bool chain = false;
+    bool l1 = false;
     ConvLaunch conv;
     ChainLaunch ch;
+    L1Launch l1b;
 };
 
 int g_num_sms = 0;
@@ -177,6 +190,8 @@ int device_setup() {
 #undef BV_SET_CHAIN_ATTR
         BV_CUDA(cudaFuncSetAttribute(bv::conv3x3_tap3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      bv::kTap3SmemBytes));
+        BV_CUDA(cudaFuncSetAttribute(bv::l1_block_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     bv::L1Cfg<64>::kSmemBytes));
         BV_CUDA(cudaFuncSetAttribute(bv::head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
         BV_CUDA(cudaFuncSetAttribute(bv::stem_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      bv::kStemSmemRequest));
@@ -402,6 +417,59 @@ int build_chain(ChainLaunch* L, int B, const ConvOperand* ops, int nops, const v
     return BV_OK;
 }
 
+bool l1_block_supported(const bv_conv& c2, const bv_conv& c3, const bv_conv& next) {
+    return c2.r == 3 && c2.s == 3 && c2.stride == 1 && c2.pad == 1 && c2.cin == 64 && c2.cout == 64 && c3.r == 1 &&
+           c3.s == 1 && c3.stride == 1 && c3.pad == 0 && c3.cin == 64 && c3.cout == 256 && next.r == 1 && next.s == 1 &&
+           next.stride == 1 && next.pad == 0 && next.cin == 256 && next.cout == 64;
+}
+
+// t1 [B,H,W,64] -> out1 = relu(conv3(relu(conv2(t1))) + residual) [B,H,W,256], out2 = relu(next(out1)) [B,H,W,64]
+int build_l1_block(L1Launch* L, int B, int H, int W, const void* t1, const bv_conv& c2, const bv_conv& c3,
+                   const void* residual, void* out1, const bv_conv& next, void* out2) {
+    if (!l1_block_supported(c2, c3, next)) return fail(BV_ERR_INVALID, "unsupported shapes for the fused layer1 block");
+    if (!residual) return fail(BV_ERR_INVALID, "the fused layer1 block needs an identity residual");
+    memset(&L->p, 0, sizeof(L->p));
+    bv::L1BlockParams& p = L->p;
+    const long long M = (long long)B * H * (W + 2);
+    if (M <= 0 || M > 0x7fffffffLL - 512) return fail(BV_ERR_INVALID, "M=%lld out of range", M);
+    int rc;
+    if ((rc = make_tmap_im2col(&p.tmA, t1, B, H, W, 64, 3, 3, 1, 1, true, 32))) return rc;
+    if ((rc = make_tmap_im2col(&p.tmRes, residual, B, H, W, 256, 1, 1, 1, 0, false, 32, true))) return rc;
+    if ((rc = make_tmap_2d(&p.tmW2, c2.w, 576, 64, bv::kBlockK, 32))) return rc;
+    if ((rc = make_tmap_2d(&p.tmW3, c3.w, 64, 256, bv::kBlockK, 128))) return rc;
+    if ((rc = make_tmap_2d(&p.tmW1, next.w, 256, 64, bv::kBlockK, 32))) return rc;
+    p.bias2 = c2.bias;
+    p.bias3 = c3.bias;
+    p.bias1 = next.bias;
+    p.out1 = reinterpret_cast<__nv_bfloat16*>(out1);
+    p.out2 = reinterpret_cast<__nv_bfloat16*>(out2);
+    p.Ho = H;
+    p.Wo = W;
+    p.Wwide = W + 2;
+    p.M = (int)M;
+    p.num_tiles = (int)((M + bv::kTap3Rows - 1) / bv::kTap3Rows);
+    p.num_pair_tiles = (p.num_tiles + 1) / 2;
+    L->grid = 2 * std::min(p.num_pair_tiles, g_num_sms / 2);
+    return BV_OK;
+}
+
+int launch_l1_block(const L1Launch& L, cudaStream_t st) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(L.grid, 1, 1);
+    cfg.blockDim = dim3(bv::kL1Threads, 1, 1);
+    cfg.dynamicSmemBytes = bv::L1Cfg<64>::kSmemBytes;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    BV_CUDA(cudaLaunchKernelEx(&cfg, bv::l1_block_kernel<64>, L.p));
+    return BV_OK;
+}
+
 int launch_chain(const ChainLaunch& L, cudaStream_t st) {
     switch (L.cfg) {
 #define BV_LAUNCH_CHAIN(id, N2, ST, NB)                                                                    \
@@ -436,7 +504,8 @@ Layout make_layout(int B, int C, int H, int W) {
     const size_t stem_out = (size_t)B * (hw / 4) * 64 * 2;    // [B,H/2,W/2,64]
     const size_t block_out = (size_t)B * (hw / 16) * 256 * 2;  // layer1 output, the largest block output
     const size_t t1 = (size_t)B * (hw / 16) * 128 * 2;         // layer2.0 conv1 output
-    const size_t t2 = (size_t)B * (hw / 16) * 64 * 2;          // layer1 conv2 output
+    const size_t t2 = t1;                                      // layer1 conv2 output; same size as t1: the fused layer1
+                                                               // block swaps the roles of the two scratch buffers
     const size_t tds = block_out;                              // un-fused downsample output (debug path)
     const size_t hid = (size_t)B * (hw / 1024) * 128 * 4;      // projector hidden, fp32
     size_t off = 0;
@@ -529,12 +598,24 @@ void chain_cost(const ChainLaunch& L, double* flops, double* bytes, char* name, 
     snprintf(name, n, "chain_gemm<%d> M=%d N1=%d K1=%d%s", L.n2, p.M, p.N1, L.k1, p.nseg > 1 ? " +ds" : " +res");
 }
 
+void l1_cost(const L1Launch& L, double* flops, double* bytes, char* name, size_t n) {
+    const double M = (double)L.p.M;   // widened rows (1.7 % padding outputs included in the issued FLOPs)
+    *flops = 2.0 * M * 64 * 576 + 2.0 * M * 256 * 64 + 2.0 * M * 64 * 256;
+    const double Mr = M / L.p.Wwide * L.p.Wo;
+    *bytes = Mr * 64 * 2 + Mr * 256 * 2 * 2 + Mr * 64 * 2 + (576.0 * 64 + 64 * 256 + 256 * 64) * 2;
+    snprintf(name, n, "l1_block<64> M=%d 3x3(64)+1x1(256)+res+1x1(64)", L.p.M);
+}
+
 void step_cost(const PlanStep& s, double* flops, double* bytes, char* name, size_t n) {
-    if (s.chain) chain_cost(s.ch, flops, bytes, name, n);
+    if (s.l1) l1_cost(s.l1b, flops, bytes, name, n);
+    else if (s.chain) chain_cost(s.ch, flops, bytes, name, n);
     else conv_cost(s.conv, flops, bytes, name, n);
 }
 
-int launch_step(const PlanStep& s, cudaStream_t st) { return s.chain ? launch_chain(s.ch, st) : launch_conv(s.conv, st); }
+int launch_step(const PlanStep& s, cudaStream_t st) {
+    if (s.l1) return launch_l1_block(s.l1b, st);
+    return s.chain ? launch_chain(s.ch, st) : launch_conv(s.conv, st);
+}
 }  // namespace
 
 extern "C" {
@@ -679,6 +760,20 @@ static int build_plan(bv_handle* h, const void* frames, int dtype, int B, int C,
             if (!t1_ready) {
                 ConvOperand o1{cur, ch, cw, c1};
                 if ((rc = push_conv(&o1, 1, nullptr, 1, t1, 0))) return rc;
+            }
+            // layer1 blocks with an identity residual whose successor's conv1 is 64 wide: the whole tail of the block
+            // (conv2 3x3, conv3 + identity, next conv1) is one CTA-pair kernel
+            if (env_flag("BV_L1_FUSED") && ds.w == nullptr && blk + 1 < BV_NUM_BLOCKS &&
+                l1_block_supported(c2, c3, h->w.conv1[blk + 1])) {
+                PlanStep s;
+                s.l1 = true;
+                if ((rc = build_l1_block(&s.l1b, B, ch, cw, t1, c2, c3, cur, nxt, h->w.conv1[blk + 1], t2))) return rc;
+                h->steps.push_back(s);
+                // the next block's conv1 output went to t2: swap the roles of the two scratch buffers
+                std::swap(t1, t2);
+                t1_ready = true;
+                std::swap(cur, nxt);
+                continue;
             }
             ConvOperand o2{t1, ch, cw, c2};
             if ((rc = push_conv(&o2, 1, nullptr, 1, t2, 0))) return rc;
@@ -1124,6 +1219,16 @@ int32_t bv_smooth_heatmaps(const float* heat, int32_t B, int32_t gh, int32_t gw,
     bv::heat_smooth_kernel<<<B * L, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
     BV_CUDA(cudaGetLastError());
     return BV_OK;
+}
+
+int32_t bv_l1_block_nhwc(const void* t1, int32_t B, int32_t H, int32_t W, const bv_conv* c2, const bv_conv* c3,
+                         const void* residual, void* out1, const bv_conv* next, void* out2, bv_stream stream) {
+    if (!t1 || !c2 || !c3 || !residual || !out1 || !next || !out2) return fail(BV_ERR_INVALID, "null argument");
+    int rc = device_setup();
+    if (rc) return rc;
+    L1Launch L;
+    if ((rc = build_l1_block(&L, B, H, W, t1, *c2, *c3, residual, out1, *next, out2))) return rc;
+    return launch_l1_block(L, reinterpret_cast<cudaStream_t>(stream));
 }
 
 int32_t bv_pair_gemm_test(const void* a, const void* w, int32_t M, int32_t N, int32_t K, float* out, bv_stream stream) {

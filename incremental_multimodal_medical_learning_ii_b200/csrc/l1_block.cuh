@@ -1,0 +1,491 @@
+// One kernel for the tail of a layer1 Bottleneck and the head of the next one, on CTA pairs:
+//
+//   t2  = relu(conv2_3x3(t1) + b2)                      G0: tap-fused, N = 192 (conv3x3_tap3.cuh)
+//   y   = relu(conv3_1x1(t2) + b3 + identity)           G1: N = 256, A = t2 tile written by the G0 epilogue   -> out1
+//   t1' = relu(next.conv1_1x1(y) + b1')                 G2: N = N2,  A = y tile written by the G1 epilogue    -> out2
+//
+// Replaces (reference): torchvision Bottleneck.forward conv2/bn2/relu, conv3/bn3/+identity/relu and the next
+// Bottleneck's conv1/bn1/relu under health_multimodal/image/model/resnet.py:39.  Neither t2 (0.94 GB per 512-frame
+// batch) nor the re-read of y for conv1 (3.77 GB) touches HBM: per block the kernel reads t1 and the residual and
+// writes y and t1' - 9.4 GB instead of 11.3 GB (two kernels) or 15.3 GB (three kernels).
+//
+// Why CTA pairs: the three weight matrices (72 + 32 + 32 KB) must stay resident next to the A ring and the staging
+// tiles; with tcgen05 cta_group::2 each CTA holds HALF of every B operand (68 KB), which is what makes it fit.
+// Each CTA of the pair owns its own 120-output tile (its 128 TMEM lanes): A loads, residual loads, epilogues and
+// stores are CTA-local, only the MMAs and their barriers are joint (protocol: pair_gemm.cuh).
+//
+// Row space: the "widened" pixel rows of the tap-fused 3x3 kernel (lane quarter g holds the 32 pixels that start at
+// output 30 g of the tile, 120 outputs per tile, padding columns q' >= Wo dropped on the way out).  The residual
+// arrives through a widened im2col tensor map as well, so it lands in the same row arrangement, already swizzled.
+//
+// Per tile t and CTA:     MMA thread (leader)              16 epilogue warps
+//                         G0(t)                            E0(t): D0 -> taps combined, bias, ReLU -> t2 tile (smem)
+//                         G1(t)      <- t2_ready           E1(t): D1 + bias + residual (in place in stg1), ReLU;
+//                         G0(t+1)                                 copy-out of y rows; sub-tiles feed G2
+//                         G2(t)      <- sub_written[j]     E0(t+1)
+//                                                          E2(t): D2 + bias, ReLU -> stg2 -> copy-out of t1' rows
+// Warp roles (608 threads): 0 TMA producer (weights once, A ring), 1 MMA issuer (leader CTA) / idle (peer),
+// 2..17 epilogue, 18 DMA (residual prefetch into the stg1 sub-tiles as they drain).
+#pragma once
+#include "conv3x3_tap3.cuh"
+#include "pair_gemm.cuh"
+
+namespace bv {
+
+constexpr int kL1Threads = 19 * 32;
+constexpr int kL1Stages = 3;
+constexpr int kL1DmaWarp = 18;
+// shared-memory map (bytes)
+constexpr int kL1OffA = 0;                                 // 3 x 16 KB A ring
+constexpr int kL1OffW2 = kL1OffA + kL1Stages * kABytes;    // 3 filter rows x [96 rows x 128 B]
+constexpr int kL1OffW3 = kL1OffW2 + 3 * 96 * 128;          // [128 rows x 128 B]
+constexpr int kL1OffW1 = kL1OffW3 + 128 * 128;             // 4 k-blocks x [N2/2 rows x 128 B]
+
+template <int N2>
+struct L1Cfg {
+    static_assert(N2 == 64, "second-GEMM width supported by the TMEM plan (D1 256 + D0 192 + D2 64 columns)");
+    static constexpr int kW1Bytes = 4 * (N2 / 2) * 128;
+    static constexpr int kOffT2 = kL1OffW1 + kW1Bytes;
+    static constexpr int kOffStg1 = kOffT2 + kABytes;          // 4 sub-tiles x 16 KB
+    static constexpr int kOffStg2 = kOffStg1 + 4 * kStagingBytes;
+    static constexpr int kOffRow = kOffStg2 + (N2 / 64) * kStagingBytes;   // [4 warp groups][2 tile parities][128] int
+    static constexpr int kOffBars = kOffRow + 4 * 2 * 128 * 4;
+    static constexpr int kNumBars = 2 * kL1Stages + 1 + 8 + 16;
+    static constexpr int kSmemBytes = kOffBars + kNumBars * 8 + 16;
+    static constexpr uint32_t kWeightBytes = 3 * 96 * 128 + 128 * 128 + kW1Bytes;
+    static_assert(kOffT2 % 1024 == 0 && kOffStg1 % 1024 == 0 && kOffStg2 % 1024 == 0, "operand tiles need 1024-byte alignment");
+    static_assert(kSmemBytes <= 232448, "exceeds the 227 KB of shared memory a CTA may use");
+};
+
+struct L1BlockParams {
+    CUtensorMap tmA;    // t1 [B,H,W,64], widened im2col (3x3, pad 1), 32 pixels x 64 channels per load
+    CUtensorMap tmRes;  // identity [B,H,W,256], widened im2col (1x1), 32 pixels x 64 channels per load
+    CUtensorMap tmW2;   // [64, 576]  box 64 x 32
+    CUtensorMap tmW3;   // [256, 64]  box 64 x 128
+    CUtensorMap tmW1;   // [N2, 256]  box 64 x N2/2
+    const float* bias2;
+    const float* bias3;
+    const float* bias1;
+    __nv_bfloat16* out1;  // [M, 256]
+    __nv_bfloat16* out2;  // [M, N2]
+    int Ho, Wo, Wwide;
+    int M;                // rows of the widened pixel space
+    int num_tiles;        // ceil(M / 120)
+    int num_pair_tiles;   // ceil(num_tiles / 2)
+};
+
+__device__ __forceinline__ void mbar_arrive_leader_release(uint64_t* bar) {
+    const uint32_t a = cluster_addr_of(bar, 0);
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];\n" ::"r"(a) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+    if (mbar_try_wait_cluster(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait_cluster(bar, parity)) {
+        if (clock64() - t0 > 4000000000LL) __trap();
+    }
+}
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;\n" ::: "memory"); }
+
+// im2col-mode load whose completion bytes are credited to the LEADER's barrier (pair MMAs consume it)
+__device__ __forceinline__ void tma_load_im2col_4d_pair(const CUtensorMap* m, uint64_t* bar, void* dst, int c, int w,
+                                                        int h, int n, uint16_t off_w, uint16_t off_h, uint64_t policy) {
+    const uint32_t bar_addr = smem_u32(bar) & kPeerBitMask;
+    asm volatile(
+        "cp.async.bulk.tensor.4d.im2col.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+        " [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8}, %9;\n" ::"r"(smem_u32(dst)),
+        "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_addr), "r"(c), "r"(w), "r"(h), "r"(n), "h"(off_w), "h"(off_h),
+        "l"(policy)
+        : "memory");
+}
+
+template <int N2>
+__global__ void __launch_bounds__(kL1Threads, 1) l1_block_kernel(const __grid_constant__ L1BlockParams p) {
+    using Cfg = L1Cfg<N2>;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    if ((smem_u32(smem) & 1023u) != 0u) __trap();
+    uint8_t* smem_a = smem + kL1OffA;
+    uint8_t* smem_w2 = smem + kL1OffW2;
+    uint8_t* smem_w3 = smem + kL1OffW3;
+    uint8_t* smem_w1 = smem + kL1OffW1;
+    uint8_t* t2_tile = smem + Cfg::kOffT2;
+    uint8_t* stg1 = smem + Cfg::kOffStg1;
+    uint8_t* stg2 = smem + Cfg::kOffStg2;
+    int* rowoff = reinterpret_cast<int*>(smem + Cfg::kOffRow);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kOffBars);
+    uint64_t* full_bar = bars;                    // [3] leader: A stage loaded in BOTH CTAs
+    uint64_t* empty_bar = bars + kL1Stages;       // [3] per CTA: stage consumed (multicast commit)
+    uint64_t* w_bar = bars + 2 * kL1Stages;       // leader: weights of both CTAs resident
+    uint64_t* d0_full = w_bar + 1;                // per CTA (multicast commit)
+    uint64_t* d0_empty = w_bar + 2;               // leader, 32 epilogue warps of the pair
+    uint64_t* t2_ready = w_bar + 3;               // leader, 32
+    uint64_t* t2_free = w_bar + 4;                // per CTA (multicast commit after G1)
+    uint64_t* d1_full = w_bar + 5;                // per CTA
+    uint64_t* d1_empty = w_bar + 6;               // leader, 32
+    uint64_t* d2_full = w_bar + 7;                // per CTA
+    uint64_t* d2_empty = w_bar + 8;               // leader, 32
+    uint64_t* sub_written = w_bar + 9;            // [4] leader, 8 (4 warps x 2 CTAs): y sub-tile j complete
+    uint64_t* sub_consumed = sub_written + 4;     // [4] per CTA (multicast commit after G2 k-block j)
+    uint64_t* copy_done = sub_consumed + 4;       // [4] per CTA, 4 warps: y sub-tile j copied out
+    uint64_t* res_ready = copy_done + 4;          // [4] per CTA: residual sub-tile j landed (TMA tx)
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + Cfg::kNumBars);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int pair = blockIdx.x >> 1;
+    const int num_pairs = gridDim.x >> 1;
+    const int T = (p.num_pair_tiles - pair + num_pairs - 1) / num_pairs;  // tiles this CTA processes
+    auto tile_of = [&](int t) { return 2 * (pair + t * num_pairs) + static_cast<int>(rank); };
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&p.tmA);
+        tma_prefetch_desc(&p.tmRes);
+        tma_prefetch_desc(&p.tmW2);
+        tma_prefetch_desc(&p.tmW3);
+        tma_prefetch_desc(&p.tmW1);
+        for (int i = 0; i < kL1Stages; ++i) {
+            mbar_init(&full_bar[i], 1);
+            mbar_init(&empty_bar[i], 1);
+        }
+        mbar_init(w_bar, 1);
+        mbar_init(d0_full, 1);
+        mbar_init(d0_empty, 32);
+        mbar_init(t2_ready, 32);
+        mbar_init(t2_free, 1);
+        mbar_init(d1_full, 1);
+        mbar_init(d1_empty, 32);
+        mbar_init(d2_full, 1);
+        mbar_init(d2_empty, 32);
+        for (int j = 0; j < 4; ++j) {
+            mbar_init(&sub_written[j], 8);
+            mbar_init(&sub_consumed[j], 1);
+            mbar_init(&copy_done[j], 4);
+            mbar_init(&res_ready[j], 1);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        tmem_alloc_pair(tmem_ptr, 512);
+        tmem_relinquish_pair();
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+    constexpr uint32_t kD1 = 0, kD0 = 256, kD2 = 448;   // TMEM column plan
+
+    // widened coordinates of the four 32-pixel groups of a tile (group g starts 30 g rows into the tile)
+    auto group_coords = [&](int tile, int (&gi)[4], int (&gp)[4], int (&gq)[4]) {
+        const int hww = p.Ho * p.Wwide;
+        const int m0 = tile * kTap3Rows;
+        gi[0] = m0 / hww;
+        const int rem = m0 - gi[0] * hww;
+        gp[0] = rem / p.Wwide;
+        gq[0] = rem - gp[0] * p.Wwide;
+#pragma unroll
+        for (int g = 1; g < 4; ++g) {
+            gi[g] = gi[g - 1];
+            gp[g] = gp[g - 1];
+            gq[g] = gq[g - 1] + kTap3Group;
+            while (gq[g] >= p.Wwide) {
+                gq[g] -= p.Wwide;
+                if (++gp[g] == p.Ho) {
+                    gp[g] = 0;
+                    ++gi[g];
+                }
+            }
+        }
+    };
+
+    if (T <= 0) {
+        // nothing to do (the host never launches more pairs than pair tiles)
+    } else if (warp == 0) {
+        // ===================== TMA producer: weights once, then the A ring =====================
+        if (elect_one()) {
+            if (rank == 0) mbar_arrive_expect_tx(w_bar, 2u * Cfg::kWeightBytes);
+            for (int tr = 0; tr < 3; ++tr)
+                for (int b = 0; b < 3; ++b) {   // this CTA's 96 of the 192 (tap, cout) rows of filter row tr
+                    const int n = 96 * static_cast<int>(rank) + 32 * b;
+                    tma_load_2d_pair(&p.tmW2, w_bar, smem_w2 + tr * 12288 + b * 4096, (tr * 3 + n / 64) * kBlockK, n % 64,
+                                     kEvictLast);
+                }
+            tma_load_2d_pair(&p.tmW3, w_bar, smem_w3, 0, 128 * static_cast<int>(rank), kEvictLast);
+            for (int kb = 0; kb < 4; ++kb)
+                tma_load_2d_pair(&p.tmW1, w_bar, smem_w1 + kb * (N2 / 2) * 128, kb * kBlockK, (N2 / 2) * static_cast<int>(rank),
+                                 kEvictLast);
+        }
+        __syncwarp();
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int t = 0; t < T; ++t) {
+            int gi[4], gp[4], gq[4];
+            group_coords(tile_of(t), gi, gp, gq);
+            for (int tr = 0; tr < 3; ++tr) {
+                mbar_wait(&empty_bar[stage], phase ^ 1u);
+                if (elect_one()) {
+                    uint8_t* dst = smem_a + stage * kABytes;
+                    if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2u * kABytes);
+#pragma unroll
+                    for (int g = 0; g < 4; ++g)
+                        tma_load_im2col_4d_pair(&p.tmA, &full_bar[stage], dst + g * 4096, 0, gq[g] - 1, gp[g] - 1, gi[g], 0,
+                                                static_cast<uint16_t>(tr), kEvictNormal);
+                }
+                __syncwarp();
+                if (++stage == kL1Stages) {
+                    stage = 0;
+                    phase ^= 1u;
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (leader CTA only) =====================
+        if (rank == 0) {
+            constexpr uint32_t idesc0 = umma_idesc_bf16_f32(256, kTap3N);
+            constexpr uint32_t idesc1 = umma_idesc_bf16_f32(256, 256);
+            constexpr uint32_t idesc2 = umma_idesc_bf16_f32(256, N2);
+            const uint32_t base = smem_u32(smem);
+            int stage = 0;
+            uint32_t phase = 0;
+            auto g0 = [&](int t) {
+                mbar_wait_cluster(d0_empty, (t & 1u) ^ 1u);
+                tc_fence_after();
+                for (int tr = 0; tr < 3; ++tr) {
+                    mbar_wait_cluster(&full_bar[stage], phase);
+                    tc_fence_after();
+                    if (elect_one()) {
+                        const uint64_t adesc = umma_desc_k_sw128(base + static_cast<uint32_t>(kL1OffA + stage * kABytes));
+                        const uint64_t bdesc = umma_desc_k_sw128(base + static_cast<uint32_t>(kL1OffW2 + tr * 12288));
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            umma_bf16_ss_pair(tmem_base + kD0, adesc + static_cast<uint64_t>(2 * k),
+                                              bdesc + static_cast<uint64_t>(2 * k), idesc0, (tr != 0 || k != 0) ? 1u : 0u);
+                        umma_commit_pair(&empty_bar[stage]);
+                        if (tr == 2) umma_commit_pair(d0_full);
+                    }
+                    __syncwarp();
+                    if (++stage == kL1Stages) {
+                        stage = 0;
+                        phase ^= 1u;
+                    }
+                }
+            };
+            auto g1 = [&](int t) {
+                mbar_wait_cluster(d1_empty, (t & 1u) ^ 1u);
+                mbar_wait_cluster(t2_ready, t & 1u);
+                tc_fence_after();
+                if (elect_one()) {
+                    const uint64_t adesc = umma_desc_k_sw128(base + static_cast<uint32_t>(Cfg::kOffT2));
+                    const uint64_t bdesc = umma_desc_k_sw128(base + static_cast<uint32_t>(kL1OffW3));
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        umma_bf16_ss_pair(tmem_base + kD1, adesc + static_cast<uint64_t>(2 * k),
+                                          bdesc + static_cast<uint64_t>(2 * k), idesc1, k != 0 ? 1u : 0u);
+                    umma_commit_pair(t2_free);
+                    umma_commit_pair(d1_full);
+                }
+                __syncwarp();
+            };
+            auto g2 = [&](int t) {
+                mbar_wait_cluster(d2_empty, (t & 1u) ^ 1u);
+                for (int j = 0; j < 4; ++j) {
+                    mbar_wait_cluster(&sub_written[j], t & 1u);
+                    tc_fence_after();
+                    if (elect_one()) {
+                        const uint64_t adesc = umma_desc_k_sw128(base + static_cast<uint32_t>(Cfg::kOffStg1 + j * kStagingBytes));
+                        const uint64_t bdesc = umma_desc_k_sw128(base + static_cast<uint32_t>(kL1OffW1 + j * (N2 / 2) * 128));
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            umma_bf16_ss_pair(tmem_base + kD2, adesc + static_cast<uint64_t>(2 * k),
+                                              bdesc + static_cast<uint64_t>(2 * k), idesc2, (j != 0 || k != 0) ? 1u : 0u);
+                        umma_commit_pair(&sub_consumed[j]);
+                        if (j == 3) umma_commit_pair(d2_full);
+                    }
+                    __syncwarp();
+                }
+            };
+            mbar_wait_cluster(w_bar, 0);
+            g0(0);
+            for (int t = 0; t < T; ++t) {
+                g1(t);
+                if (t + 1 < T) g0(t + 1);
+                g2(t);
+            }
+        }
+    } else if (warp == kL1DmaWarp) {
+        // ===================== DMA: residual prefetch into the stg1 sub-tiles =====================
+        if (lane == 0) {
+            for (int t = 0; t < T; ++t) {
+                int gi[4], gp[4], gq[4];
+                group_coords(tile_of(t), gi, gp, gq);
+                for (int j = 0; j < 4; ++j) {
+                    if (t > 0) {  // the previous tile's sub-tile j has been read by the second GEMM and copied out
+                        mbar_wait(&sub_consumed[j], (t - 1) & 1u);
+                        mbar_wait(&copy_done[j], (t - 1) & 1u);
+                    }
+                    mbar_arrive_expect_tx(&res_ready[j], kStagingBytes);
+#pragma unroll
+                    for (int g = 0; g < 4; ++g)
+                        tma_load_im2col_4d(&p.tmRes, &res_ready[j], stg1 + j * kStagingBytes + g * 4096, j * kChunkCols, gq[g],
+                                           gp[g], gi[g], 0, 0, kEvictFirst);
+                }
+            }
+        }
+    } else if (warp >= 2 && warp < 18) {
+        // ===================== epilogue warps =====================
+        const int quarter = warp & 3;
+        const int cg = (warp - 2) >> 2;                 // 16-column group (E0, E2) / y sub-tile (E1)
+        const int l = quarter * 32 + lane;              // TMEM lane = row of every smem tile
+        const int tid4 = ((warp - 2) & 3) * 32 + lane;  // index inside the four warps that share cg (any order)
+        const int tid16 = (warp - 2) * 32 + lane;
+        const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+        uint8_t* out1 = reinterpret_cast<uint8_t*>(p.out1);
+        uint8_t* out2 = reinterpret_cast<uint8_t*>(p.out2);
+        // widened row of this thread's lane, advanced without divisions from tile to tile
+        int row = tile_of(0) * kTap3Rows + quarter * kTap3Group + lane;
+        int line = row / p.Wwide;
+        int qq = row - line * p.Wwide;
+        const int step = 2 * num_pairs * kTap3Rows;
+        const int step_lines = step / p.Wwide, step_q = step - step_lines * p.Wwide;
+
+        auto e0 = [&](int t) {
+            mbar_wait(d0_full, t & 1u);
+            tc_fence_after();
+            uint32_t v0[16], v1[16], v2[16];
+            const uint32_t ta = lane_base + kD0 + static_cast<uint32_t>(cg * 16);
+            tmem_ld_32x16(ta, v0);
+            tmem_ld_32x16(ta + 64u, v1);
+            tmem_ld_32x16(ta + 128u, v2);
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_leader(d0_empty);
+            uint32_t w[8];
+            const float* bp = p.bias2 + cg * 16;
+#pragma unroll
+            for (int c = 0; c < 16; c += 2) {
+                float f[2];
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const float u1 = __shfl_down_sync(0xffffffffu, __uint_as_float(v1[c + u]), 1);
+                    const float u2 = __shfl_down_sync(0xffffffffu, __uint_as_float(v2[c + u]), 2);
+                    f[u] = (__uint_as_float(v0[c + u]) + u1) + (u2 + __ldg(bp + c + u));
+                }
+                __nv_bfloat162 h = __floats2bfloat162_rn(f[0], f[1]);
+                h = __hmax2(h, __floats2bfloat162_rn(0.0f, 0.0f));
+                w[c >> 1] = *reinterpret_cast<const uint32_t*>(&h);
+            }
+            mbar_wait(t2_free, (t & 1u) ^ 1u);   // the first GEMM-1 of the previous tile has read the t2 tile
+            uint8_t* rp = t2_tile + l * 128;
+            *reinterpret_cast<uint4*>(rp + (((2 * cg) ^ (l & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+            *reinterpret_cast<uint4*>(rp + (((2 * cg + 1) ^ (l & 7)) << 4)) = make_uint4(w[4], w[5], w[6], w[7]);
+            // output row table of this tile, one copy per group of four warps (each group is synchronised by its own
+            // named barrier before it reads the table)
+            rowoff[(cg * 2 + (t & 1)) * 128 + l] = (lane < kTap3Group && row < p.M && qq < p.Wo) ? line * p.Wo + qq : -1;
+            row += step;
+            line += step_lines;
+            qq += step_q;
+            if (qq >= p.Wwide) {
+                qq -= p.Wwide;
+                ++line;
+            }
+            fence_proxy_async_all();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_leader_release(t2_ready);
+        };
+        auto e1 = [&](int t) {
+            const int j = cg;
+            uint8_t* sub = stg1 + j * kStagingBytes;
+            mbar_wait(d1_full, t & 1u);
+            tc_fence_after();
+            mbar_wait(&res_ready[j], t & 1u);
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                uint32_t v[32];
+                tmem_ld_32x32(lane_base + kD1 + static_cast<uint32_t>(j * kChunkCols + half * 32), v);
+                tmem_ld_wait();
+                if (half == 1) {
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_leader(d1_empty);
+                }
+                chain_convert_row(v, p.bias3 + j * kChunkCols + half * 32, nullptr, true, sub + l * 128, half, l);
+            }
+            fence_proxy_async_all();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_leader_release(&sub_written[j]);
+            named_bar_sync(1 + j, 128);              // the four warps of this sub-tile (local rows all written)
+            const int* ro = rowoff + (cg * 2 + (t & 1)) * 128;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {            // 128 rows x 8 chunks of 16 B, four rows per warp instruction
+                const int item = i * 128 + tid4;
+                const int r = item >> 3, chunk = item & 7;
+                const int dst_row = ro[r];
+                const uint4 val = *reinterpret_cast<const uint4*>(sub + r * 128 + ((chunk ^ (r & 7)) << 4));
+                if (dst_row >= 0)
+                    *reinterpret_cast<uint4*>(out1 + static_cast<size_t>(dst_row) * 512 + j * 128 + chunk * 16) = val;
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&copy_done[j]);
+        };
+        auto e2 = [&](int t) {
+            mbar_wait(d2_full, t & 1u);
+            tc_fence_after();
+            uint32_t v[16];
+            tmem_ld_32x16(lane_base + kD2 + static_cast<uint32_t>(cg * 16), v);
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_leader(d2_empty);
+            uint32_t w[8];
+            const float* bp = p.bias1 + cg * 16;
+#pragma unroll
+            for (int c = 0; c < 16; c += 2) {
+                __nv_bfloat162 h = __floats2bfloat162_rn(__uint_as_float(v[c]) + __ldg(bp + c),
+                                                         __uint_as_float(v[c + 1]) + __ldg(bp + c + 1));
+                h = __hmax2(h, __floats2bfloat162_rn(0.0f, 0.0f));
+                w[c >> 1] = *reinterpret_cast<const uint32_t*>(&h);
+            }
+            uint8_t* rp = stg2 + l * 128;
+            *reinterpret_cast<uint4*>(rp + (((2 * cg) ^ (l & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+            *reinterpret_cast<uint4*>(rp + (((2 * cg + 1) ^ (l & 7)) << 4)) = make_uint4(w[4], w[5], w[6], w[7]);
+            named_bar_sync(5, 512);
+            const int* ro = rowoff + (cg * 2 + (t & 1)) * 128;
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const int item = i * 512 + tid16;
+                const int r = item >> 3, chunk = item & 7;
+                const int dst_row = ro[r];
+                const uint4 val = *reinterpret_cast<const uint4*>(stg2 + r * 128 + ((chunk ^ (r & 7)) << 4));
+                if (dst_row >= 0) *reinterpret_cast<uint4*>(out2 + static_cast<size_t>(dst_row) * 128 + chunk * 16) = val;
+            }
+            named_bar_sync(6, 512);                  // stg2 and this tile's row table may be overwritten
+        };
+        e0(0);
+        for (int t = 0; t < T; ++t) {
+            e1(t);
+            if (t + 1 < T) e0(t + 1);
+            e2(t);
+        }
+    }
+
+    tc_fence_before();
+    cluster_sync_all();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc_pair(tmem_base, 512);
+    }
+}
+
+}  // namespace bv

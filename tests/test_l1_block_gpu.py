@@ -1,0 +1,66 @@
+"""Fused layer1 Bottleneck tail on CTA pairs (csrc/l1_block.cuh) through ``bv_l1_block_nhwc``.
+
+Reference op: conv2(3x3)+bn2+relu -> conv3(1x1)+bn3+identity+relu -> next conv1(1x1)+bn1+relu of torchvision's
+Bottleneck (health_multimodal/image/model/resnet.py:39), fp32 ``F.conv2d`` on the same bf16-rounded operands with the
+two intermediate tensors rounded to bf16 exactly where the kernel rounds them.  Integer operands -> bit-exact."""
+import ctypes
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _ref(x_nhwc, w, b, pad):
+    return F.conv2d(x_nhwc.float().permute(0, 3, 1, 2), w.float(), b.float(), padding=pad).permute(0, 2, 3, 1)
+
+
+@pytest.mark.parametrize("B,H", [(1, 8), (2, 24), (3, 15), (2, 120), (20, 60)], ids=["tiny", "b2h24", "h15", "h120", "persistent"])
+@pytest.mark.parametrize("integer", [True, False], ids=["int", "gauss"])
+def test_l1_block(B, H, integer):
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    from incremental_multimodal_medical_learning_ii_b200 import _native as N
+    from incremental_multimodal_medical_learning_ii_b200 import packing
+    lib = N.lib()
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(B * 1000 + H)
+
+    def rnd(shape, lo, hi, scale):
+        return torch.randint(lo, hi, shape, generator=g).float() if integer else torch.randn(shape, generator=g) * scale
+
+    t1 = rnd((B, H, H, 64), 0, 3, 1.0).to(torch.bfloat16).to(dev)
+    w2 = rnd((64, 64, 3, 3), -1, 2, 576 ** -0.5).to(torch.bfloat16)
+    if integer:   # keep |conv2| small enough that every intermediate is an exact bf16 integer
+        w2 = (w2 * (torch.rand(w2.shape, generator=g) < 0.25)).to(torch.bfloat16)
+    b2 = rnd((64,), -2, 3, 1.0)
+    w3 = rnd((256, 64, 1, 1), -1, 2, 64 ** -0.5).to(torch.bfloat16)
+    if integer:
+        w3 = (w3 * (torch.rand(w3.shape, generator=g) < 0.25)).to(torch.bfloat16)
+    b3 = rnd((256,), -2, 3, 1.0)
+    w1 = rnd((64, 256, 1, 1), -1, 2, 256 ** -0.5).to(torch.bfloat16)
+    b1 = rnd((64,), -2, 3, 1.0)
+    res = rnd((B, H, H, 256), -2, 3, 1.0).to(torch.bfloat16).to(dev)
+    c2 = packing.pack_single_conv(w2, b2, 1, 1, dev)
+    c3 = packing.pack_single_conv(w3, b3, 1, 0, dev)
+    c1 = packing.pack_single_conv(w1, b1, 1, 0, dev)
+
+    t2 = torch.relu(_ref(t1, w2.to(dev), b2.to(dev), 1)).to(torch.bfloat16)
+    y = torch.relu(_ref(t2, w3.to(dev), b3.to(dev), 0) + res.float()).to(torch.bfloat16)
+    t1n = torch.relu(_ref(y, w1.to(dev), b1.to(dev), 0)).to(torch.bfloat16)
+    if integer:
+        assert t2.float().abs().max() <= 256 and y.float().abs().max() <= 256, "test data must stay exact in bf16"
+
+    out1 = torch.full((B, H, H, 256), float("nan"), device=dev, dtype=torch.bfloat16)
+    out2 = torch.full((B, H, H, 64), float("nan"), device=dev, dtype=torch.bfloat16)
+    N.check(lib.bv_l1_block_nhwc(N.ptr(t1), B, H, H, ctypes.byref(c2[0]), ctypes.byref(c3[0]), N.ptr(res), N.ptr(out1),
+                                 ctypes.byref(c1[0]), N.ptr(out2), N.current_stream_handle(dev)))
+    torch.cuda.synchronize()
+    assert not torch.isnan(out1.float()).any() and not torch.isnan(out2.float()).any(), "unwritten output rows"
+    if integer:
+        assert torch.equal(out1, y), f"out1 max abs diff {(out1.float() - y.float()).abs().max().item()}"
+        assert torch.equal(out2, t1n), f"out2 max abs diff {(out2.float() - t1n.float()).abs().max().item()}"
+    else:
+        torch.testing.assert_close(out1.float(), y.float(), rtol=2e-2, atol=2e-2)
+        torch.testing.assert_close(out2.float(), t1n.float(), rtol=3e-2, atol=3e-2)
