@@ -275,7 +275,7 @@ def run_ours(args):
         prof_runs.append(eng.get_profile())
     eng.set_profile(False)
     prof = prof_runs[-1]
-    is_conv = lambda name: name.startswith("conv_gemm") or name.startswith("chain_gemm")  # noqa: E731
+    is_conv = lambda name: name.startswith(("conv_gemm", "chain_gemm", "l1_block"))  # noqa: E731
     conv_ms = sum(ms for (name, fl, by, ms) in prof if is_conv(name))
     conv_flops_issued = sum(fl for (name, fl, by, ms) in prof if is_conv(name))
     conv_bytes = sum(by for (name, fl, by, ms) in prof if is_conv(name))

@@ -80,6 +80,20 @@ int make_tmap_2d(CUtensorMap* tm, const void* base, uint64_t inner, uint64_t out
     return BV_OK;
 }
 
+// NHWC tensor viewed as (C, W, lines = N*H), tiled mode, box = 64 channels x `px` pixels x 1 line, 128B swizzle.
+int make_tmap_lines(CUtensorMap* tm, const void* base, int lines, int W, int C, int px) {
+    cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)lines};
+    cuuint64_t strides[2] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2};
+    cuuint32_t box[3] = {64, (cuuint32_t)px, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = g_encode_tiled(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS)
+        return fail(BV_ERR_CUDA, "cuTensorMapEncodeTiled(3d) failed (%d) lines=%d W=%d C=%d", (int)r, lines, W, C);
+    return BV_OK;
+}
+
 // NHWC activation tensor [N][H][W][C] seen by TMA as (C, W, H, N); 128 output pixels x 64 channels per load.
 int make_tmap_im2col(CUtensorMap* tm, const void* base, int N, int H, int W, int C, int R, int S, int stride,
                      int pad, bool wide = false, int pixels = 0, bool widen_right = false) {
@@ -160,6 +174,7 @@ struct PlanStep {
 
 int g_num_sms = 0;
 bool g_attr_set = false;
+long long* g_dbg = nullptr;  // BV_TIMING=1: per-CTA wait-cycle counters of the most recent conv launch
 
 int device_setup() {
     if (g_num_sms > 0) return BV_OK;
@@ -305,7 +320,6 @@ int build_conv(ConvLaunch* L, int B, const ConvOperand* ops, int nops, const voi
     return BV_OK;
 }
 
-long long* g_dbg = nullptr;  // BV_TIMING=1: per-CTA wait-cycle counters of the most recent conv launch
 
 int launch_conv(const ConvLaunch& L0, cudaStream_t st) {
     ConvLaunch L = L0;
@@ -417,8 +431,8 @@ int build_chain(ChainLaunch* L, int B, const ConvOperand* ops, int nops, const v
     return BV_OK;
 }
 
-bool l1_block_supported(const bv_conv& c2, const bv_conv& c3, const bv_conv& next) {
-    return c2.r == 3 && c2.s == 3 && c2.stride == 1 && c2.pad == 1 && c2.cin == 64 && c2.cout == 64 && c3.r == 1 &&
+bool l1_block_supported(const bv_conv& c2, const bv_conv& c3, const bv_conv& next, int W) {
+    return W % bv::kTap3Group == 0 && c2.r == 3 && c2.s == 3 && c2.stride == 1 && c2.pad == 1 && c2.cin == 64 && c2.cout == 64 && c3.r == 1 &&
            c3.s == 1 && c3.stride == 1 && c3.pad == 0 && c3.cin == 64 && c3.cout == 256 && next.r == 1 && next.s == 1 &&
            next.stride == 1 && next.pad == 0 && next.cin == 256 && next.cout == 64;
 }
@@ -426,28 +440,29 @@ bool l1_block_supported(const bv_conv& c2, const bv_conv& c3, const bv_conv& nex
 // t1 [B,H,W,64] -> out1 = relu(conv3(relu(conv2(t1))) + residual) [B,H,W,256], out2 = relu(next(out1)) [B,H,W,64]
 int build_l1_block(L1Launch* L, int B, int H, int W, const void* t1, const bv_conv& c2, const bv_conv& c3,
                    const void* residual, void* out1, const bv_conv& next, void* out2) {
-    if (!l1_block_supported(c2, c3, next)) return fail(BV_ERR_INVALID, "unsupported shapes for the fused layer1 block");
+    if (!l1_block_supported(c2, c3, next, W))
+        return fail(BV_ERR_INVALID, "unsupported shapes for the fused layer1 block (64->64 3x3, 64->256, 256->64, width %% 30 == 0)");
     if (!residual) return fail(BV_ERR_INVALID, "the fused layer1 block needs an identity residual");
     memset(&L->p, 0, sizeof(L->p));
     bv::L1BlockParams& p = L->p;
-    const long long M = (long long)B * H * (W + 2);
-    if (M <= 0 || M > 0x7fffffffLL - 512) return fail(BV_ERR_INVALID, "M=%lld out of range", M);
+    const long long groups = (long long)B * H * (W / bv::kTap3Group);
+    if (groups <= 0 || groups > 0x7fffffffLL / 64) return fail(BV_ERR_INVALID, "too many rows (%lld lane quarters)", groups);
     int rc;
     if ((rc = make_tmap_im2col(&p.tmA, t1, B, H, W, 64, 3, 3, 1, 1, true, 32))) return rc;
-    if ((rc = make_tmap_im2col(&p.tmRes, residual, B, H, W, 256, 1, 1, 1, 0, false, 32, true))) return rc;
+    if ((rc = make_tmap_lines(&p.tmRes, residual, B * H, W, 256, 32))) return rc;
     if ((rc = make_tmap_2d(&p.tmW2, c2.w, 576, 64, bv::kBlockK, 32))) return rc;
     if ((rc = make_tmap_2d(&p.tmW3, c3.w, 64, 256, bv::kBlockK, 128))) return rc;
     if ((rc = make_tmap_2d(&p.tmW1, next.w, 256, 64, bv::kBlockK, 32))) return rc;
     p.bias2 = c2.bias;
     p.bias3 = c3.bias;
     p.bias1 = next.bias;
-    p.out1 = reinterpret_cast<__nv_bfloat16*>(out1);
-    p.out2 = reinterpret_cast<__nv_bfloat16*>(out2);
+    if ((rc = make_tmap_lines(&p.tmOut1, out1, B * H, W, 256, bv::kTap3Group))) return rc;
+    if ((rc = make_tmap_lines(&p.tmOut2, out2, B * H, W, 64, bv::kTap3Group))) return rc;
     p.Ho = H;
     p.Wo = W;
-    p.Wwide = W + 2;
-    p.M = (int)M;
-    p.num_tiles = (int)((M + bv::kTap3Rows - 1) / bv::kTap3Rows);
+    p.groups_per_line = W / bv::kTap3Group;
+    p.num_groups = (int)groups;
+    p.num_tiles = (int)((groups + 3) / 4);
     p.num_pair_tiles = (p.num_tiles + 1) / 2;
     L->grid = 2 * std::min(p.num_pair_tiles, g_num_sms / 2);
     return BV_OK;
@@ -466,7 +481,38 @@ int launch_l1_block(const L1Launch& L, cudaStream_t st) {
     at[0].val.clusterDim.z = 1;
     cfg.attrs = at;
     cfg.numAttrs = 1;
-    BV_CUDA(cudaLaunchKernelEx(&cfg, bv::l1_block_kernel<64>, L.p));
+    bv::L1BlockParams prm = L.p;
+    if (env_flag("BV_TIMING")) {
+        if (!g_dbg) cudaMalloc(&g_dbg, 4 * 8 * 1024);
+        cudaMemsetAsync(g_dbg, 0, 4 * 8 * 1024, st);
+        prm.dbg = g_dbg;
+    }
+    BV_CUDA(cudaLaunchKernelEx(&cfg, bv::l1_block_kernel<64>, prm));
+    if (prm.dbg) {
+        static long long host[8 * 128];
+        const int pairs = L.grid / 2;
+        cudaStreamSynchronize(st);
+        cudaMemcpy(host, g_dbg, sizeof(long long) * 8 * pairs, cudaMemcpyDeviceToHost);
+        double a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        for (int i = 0; i < pairs; ++i)
+            for (int j = 0; j < 8; ++j) a[j] += (double)host[i * 8 + j] / pairs;
+        fprintf(stderr, "[timing] l1_block: mma thread %.0f cyc; waits: d0_empty %.1f%% full %.1f%% d1_empty %.1f%% t2_ready %.1f%% "
+                        "d2_empty %.1f%% sub_written %.1f%%\n",
+                a[0], 100 * a[1] / a[0], 100 * a[2] / a[0], 100 * a[3] / a[0], 100 * a[4] / a[0], 100 * a[5] / a[0],
+                100 * a[6] / a[0]);
+        static long long h2[74 * 13];
+        cudaMemcpy(h2, g_dbg + 1024, sizeof(h2), cudaMemcpyDeviceToHost);
+        double e[12] = {0}, tot = 0;
+        for (int i = 0; i < pairs; ++i) {
+            for (int j = 0; j < 12; ++j) e[j] += (double)h2[i * 12 + j] / pairs;
+            tot += (double)h2[74 * 12 + i] / pairs;
+        }
+        const char* nm[12] = {"wait d0_full", "e0 compute+write", "wait t2_free", "wait d1_full", "wait res_ready", "e1 compute",
+                              "e1 group barrier", "e1 copy-out", "wait d2_full", "e2 compute+copy", "e2 barrier", "between"};
+        fprintf(stderr, "[timing] l1_block epilogue warp 2 (%.0f cyc):", tot);
+        for (int j = 0; j < 12; ++j) fprintf(stderr, " %s %.1f%%;", nm[j], 100 * e[j] / tot);
+        fprintf(stderr, "\n");
+    }
     return BV_OK;
 }
 
@@ -599,11 +645,10 @@ void chain_cost(const ChainLaunch& L, double* flops, double* bytes, char* name, 
 }
 
 void l1_cost(const L1Launch& L, double* flops, double* bytes, char* name, size_t n) {
-    const double M = (double)L.p.M;   // widened rows (1.7 % padding outputs included in the issued FLOPs)
-    *flops = 2.0 * M * 64 * 576 + 2.0 * M * 256 * 64 + 2.0 * M * 64 * 256;
-    const double Mr = M / L.p.Wwide * L.p.Wo;
+    const double Mr = (double)L.p.num_groups * bv::kTap3Group;   // output pixels
+    *flops = 2.0 * Mr * 64 * 576 + 2.0 * Mr * 256 * 64 + 2.0 * Mr * 64 * 256;
     *bytes = Mr * 64 * 2 + Mr * 256 * 2 * 2 + Mr * 64 * 2 + (576.0 * 64 + 64 * 256 + 256 * 64) * 2;
-    snprintf(name, n, "l1_block<64> M=%d 3x3(64)+1x1(256)+res+1x1(64)", L.p.M);
+    snprintf(name, n, "l1_block<64> M=%.0f 3x3(64)+1x1(256)+res+1x1(64)", Mr);
 }
 
 void step_cost(const PlanStep& s, double* flops, double* bytes, char* name, size_t n) {
@@ -764,7 +809,7 @@ static int build_plan(bv_handle* h, const void* frames, int dtype, int B, int C,
             // layer1 blocks with an identity residual whose successor's conv1 is 64 wide: the whole tail of the block
             // (conv2 3x3, conv3 + identity, next conv1) is one CTA-pair kernel
             if (env_flag("BV_L1_FUSED") && ds.w == nullptr && blk + 1 < BV_NUM_BLOCKS &&
-                l1_block_supported(c2, c3, h->w.conv1[blk + 1])) {
+                l1_block_supported(c2, c3, h->w.conv1[blk + 1], cw)) {
                 PlanStep s;
                 s.l1 = true;
                 if ((rc = build_l1_block(&s.l1b, B, ch, cw, t1, c2, c3, cur, nxt, h->w.conv1[blk + 1], t2))) return rc;

@@ -14,9 +14,12 @@
 // Each CTA of the pair owns its own 120-output tile (its 128 TMEM lanes): A loads, residual loads, epilogues and
 // stores are CTA-local, only the MMAs and their barriers are joint (protocol: pair_gemm.cuh).
 //
-// Row space: the "widened" pixel rows of the tap-fused 3x3 kernel (lane quarter g holds the 32 pixels that start at
-// output 30 g of the tile, 120 outputs per tile, padding columns q' >= Wo dropped on the way out).  The residual
-// arrives through a widened im2col tensor map as well, so it lands in the same row arrangement, already swizzled.
+// Row space: as in the tap-fused 3x3 kernel a TMEM lane quarter holds 32 consecutive pixels of one image line and
+// yields 30 outputs (the tap combination needs rows j+1, j+2).  Here the quarters are aligned to the image lines: the
+// image width must be a multiple of 30 (layer1 of a 480-pixel frame: 120 = one tile per line), quarter k of a line
+// covers outputs 30k .. 30k+29, so no quarter straddles a line and there are no padding outputs.  Residual loads
+// (32 pixels) and output stores (30 pixels) are plain tiled 3-D TMA boxes over (C, W, B*H), always in bounds at
+// their origin.  Other widths take the two-kernel path.
 //
 // Per tile t and CTA:     MMA thread (leader)              16 epilogue warps
 //                         G0(t)                            E0(t): D0 -> taps combined, bias, ReLU -> t2 tile (smem)
@@ -24,17 +27,21 @@
 //                         G0(t+1)                                 copy-out of y rows; sub-tiles feed G2
 //                         G2(t)      <- sub_written[j]     E0(t+1)
 //                                                          E2(t): D2 + bias, ReLU -> stg2 -> copy-out of t1' rows
-// Warp roles (608 threads): 0 TMA producer (weights once, A ring), 1 MMA issuer (leader CTA) / idle (peer),
-// 2..17 epilogue, 18 DMA (residual prefetch into the stg1 sub-tiles as they drain).
+// Warp roles (640 threads): 0 TMA producer (weights once, A ring), 1 MMA issuer (leader CTA) / idle (peer),
+// 2..17 epilogue, 18 loader (residual prefetch into the stg1 sub-tiles as they drain), 19 storer (y and t1' leave
+// through tiled 3-D TMA stores of [1 line x 30 pixels x 64 channels]: the two overlap rows of each lane quarter are
+// not part of the box and the padding columns are out of bounds, so neither is written; per-thread copy-out loops
+// stalled the epilogue warps on the store queue for 40 % of their time).
 #pragma once
 #include "conv3x3_tap3.cuh"
 #include "pair_gemm.cuh"
 
 namespace bv {
 
-constexpr int kL1Threads = 19 * 32;
+constexpr int kL1Threads = 20 * 32;
 constexpr int kL1Stages = 3;
 constexpr int kL1DmaWarp = 18;
+constexpr int kL1StoreWarp = 19;
 // shared-memory map (bytes)
 constexpr int kL1OffA = 0;                                 // 3 x 16 KB A ring
 constexpr int kL1OffW2 = kL1OffA + kL1Stages * kABytes;    // 3 filter rows x [96 rows x 128 B]
@@ -48,9 +55,8 @@ struct L1Cfg {
     static constexpr int kOffT2 = kL1OffW1 + kW1Bytes;
     static constexpr int kOffStg1 = kOffT2 + kABytes;          // 4 sub-tiles x 16 KB
     static constexpr int kOffStg2 = kOffStg1 + 4 * kStagingBytes;
-    static constexpr int kOffRow = kOffStg2 + (N2 / 64) * kStagingBytes;   // [4 warp groups][2 tile parities][128] int
-    static constexpr int kOffBars = kOffRow + 4 * 2 * 128 * 4;
-    static constexpr int kNumBars = 2 * kL1Stages + 1 + 8 + 16;
+    static constexpr int kOffBars = kOffStg2 + (N2 / 64) * kStagingBytes;
+    static constexpr int kNumBars = 2 * kL1Stages + 1 + 8 + 20 + 2;
     static constexpr int kSmemBytes = kOffBars + kNumBars * 8 + 16;
     static constexpr uint32_t kWeightBytes = 3 * 96 * 128 + 128 * 128 + kW1Bytes;
     static_assert(kOffT2 % 1024 == 0 && kOffStg1 % 1024 == 0 && kOffStg2 % 1024 == 0, "operand tiles need 1024-byte alignment");
@@ -59,19 +65,21 @@ struct L1Cfg {
 
 struct L1BlockParams {
     CUtensorMap tmA;    // t1 [B,H,W,64], widened im2col (3x3, pad 1), 32 pixels x 64 channels per load
-    CUtensorMap tmRes;  // identity [B,H,W,256], widened im2col (1x1), 32 pixels x 64 channels per load
+    CUtensorMap tmRes;  // identity as (256, W, B*H), tiled, box 64 channels x 32 pixels x 1 line
     CUtensorMap tmW2;   // [64, 576]  box 64 x 32
     CUtensorMap tmW3;   // [256, 64]  box 64 x 128
     CUtensorMap tmW1;   // [N2, 256]  box 64 x N2/2
+    CUtensorMap tmOut1; // y   as (256, W, B*H), tiled, box 64 channels x 30 pixels x 1 line
+    CUtensorMap tmOut2; // t1' as (N2,  W, B*H), tiled, box 64 channels x 30 pixels x 1 line
     const float* bias2;
     const float* bias3;
     const float* bias1;
-    __nv_bfloat16* out1;  // [M, 256]
-    __nv_bfloat16* out2;  // [M, N2]
-    int Ho, Wo, Wwide;
-    int M;                // rows of the widened pixel space
-    int num_tiles;        // ceil(M / 120)
+    int Ho, Wo;
+    int groups_per_line;  // Wo / 30
+    int num_groups;       // B * Ho * Wo / 30 lane quarters of work
+    int num_tiles;        // ceil(num_groups / 4)
     int num_pair_tiles;   // ceil(num_tiles / 2)
+    long long* dbg;       // optional [pairs][8] cycle counters of the leader's MMA thread (BV_TIMING)
 };
 
 __device__ __forceinline__ void mbar_arrive_leader_release(uint64_t* bar) {
@@ -110,6 +118,32 @@ __device__ __forceinline__ void tma_load_im2col_4d_pair(const CUtensorMap* m, ui
         : "memory");
 }
 
+// Tiled 3-D store of a [1 line][30 pixels][64 channels] box of an NHWC tensor viewed as (C, W, B*H); pixels whose
+// column falls outside [0, W) are out of bounds and are not written - that is how the padding columns of the widened
+// row space (and the part of a lane quarter that belongs to the neighbouring image line) are dropped.
+// (im2col-mode TMA stores, which would express this directly, raise "illegal instruction" on this driver/GPU.)
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, const void* src, int c, int w, int line) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];\n" ::"l"(
+                     reinterpret_cast<uint64_t>(m)),
+                 "r"(smem_u32(src)), "r"(c), "r"(w), "r"(line)
+                 : "memory");
+}
+
+__device__ __forceinline__ void tma_load_3d(const CUtensorMap* m, uint64_t* bar, void* dst, int c, int w, int line,
+                                            uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+        " [%0], [%1, {%3, %4, %5}], [%2], %6;\n" ::"r"(smem_u32(dst)),
+        "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c), "r"(w), "r"(line), "l"(policy)
+        : "memory");
+}
+// Pull one box into L2 (no smem destination, no completion tracking).
+__device__ __forceinline__ void tma_prefetch_l2_3d(const CUtensorMap* m, int c, int w, int line) {
+    asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];\n" ::"l"(reinterpret_cast<uint64_t>(m)),
+                 "r"(c), "r"(w), "r"(line)
+                 : "memory");
+}
+
 template <int N2>
 __global__ void __launch_bounds__(kL1Threads, 1) l1_block_kernel(const __grid_constant__ L1BlockParams p) {
     using Cfg = L1Cfg<N2>;
@@ -122,7 +156,6 @@ __global__ void __launch_bounds__(kL1Threads, 1) l1_block_kernel(const __grid_co
     uint8_t* t2_tile = smem + Cfg::kOffT2;
     uint8_t* stg1 = smem + Cfg::kOffStg1;
     uint8_t* stg2 = smem + Cfg::kOffStg2;
-    int* rowoff = reinterpret_cast<int*>(smem + Cfg::kOffRow);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kOffBars);
     uint64_t* full_bar = bars;                    // [3] leader: A stage loaded in BOTH CTAs
     uint64_t* empty_bar = bars + kL1Stages;       // [3] per CTA: stage consumed (multicast commit)
@@ -137,8 +170,11 @@ __global__ void __launch_bounds__(kL1Threads, 1) l1_block_kernel(const __grid_co
     uint64_t* d2_empty = w_bar + 8;               // leader, 32
     uint64_t* sub_written = w_bar + 9;            // [4] leader, 8 (4 warps x 2 CTAs): y sub-tile j complete
     uint64_t* sub_consumed = sub_written + 4;     // [4] per CTA (multicast commit after G2 k-block j)
-    uint64_t* copy_done = sub_consumed + 4;       // [4] per CTA, 4 warps: y sub-tile j copied out
-    uint64_t* res_ready = copy_done + 4;          // [4] per CTA: residual sub-tile j landed (TMA tx)
+    uint64_t* store_done = sub_consumed + 4;      // [4] per CTA: the TMA stores of y sub-tile j have read smem
+    uint64_t* res_ready = store_done + 4;         // [4] per CTA: residual sub-tile j landed (TMA tx)
+    uint64_t* y_local = res_ready + 4;            // [4] per CTA, 4 warps: y sub-tile j written (for the storer)
+    uint64_t* e2_local = y_local + 4;             // per CTA, 16 warps: t1' tile written
+    uint64_t* stg2_free = e2_local + 1;           // per CTA: the TMA stores of t1' have read smem
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + Cfg::kNumBars);
 
     const int warp = threadIdx.x >> 5;
@@ -155,6 +191,8 @@ __global__ void __launch_bounds__(kL1Threads, 1) l1_block_kernel(const __grid_co
         tma_prefetch_desc(&p.tmW2);
         tma_prefetch_desc(&p.tmW3);
         tma_prefetch_desc(&p.tmW1);
+        tma_prefetch_desc(&p.tmOut1);
+        tma_prefetch_desc(&p.tmOut2);
         for (int i = 0; i < kL1Stages; ++i) {
             mbar_init(&full_bar[i], 1);
             mbar_init(&empty_bar[i], 1);
@@ -168,11 +206,14 @@ __global__ void __launch_bounds__(kL1Threads, 1) l1_block_kernel(const __grid_co
         mbar_init(d1_empty, 32);
         mbar_init(d2_full, 1);
         mbar_init(d2_empty, 32);
+        mbar_init(e2_local, 16);
+        mbar_init(stg2_free, 1);
         for (int j = 0; j < 4; ++j) {
             mbar_init(&sub_written[j], 8);
             mbar_init(&sub_consumed[j], 1);
-            mbar_init(&copy_done[j], 4);
+            mbar_init(&store_done[j], 1);
             mbar_init(&res_ready[j], 1);
+            mbar_init(&y_local[j], 4);
         }
         fence_barrier_init();
     }
@@ -186,25 +227,18 @@ __global__ void __launch_bounds__(kL1Threads, 1) l1_block_kernel(const __grid_co
     const uint32_t tmem_base = *tmem_ptr;
     constexpr uint32_t kD1 = 0, kD0 = 256, kD2 = 448;   // TMEM column plan
 
-    // widened coordinates of the four 32-pixel groups of a tile (group g starts 30 g rows into the tile)
-    auto group_coords = [&](int tile, int (&gi)[4], int (&gp)[4], int (&gq)[4]) {
-        const int hww = p.Ho * p.Wwide;
-        const int m0 = tile * kTap3Rows;
-        gi[0] = m0 / hww;
-        const int rem = m0 - gi[0] * hww;
-        gp[0] = rem / p.Wwide;
-        gq[0] = rem - gp[0] * p.Wwide;
+    // image line (global over the batch) and first output column of the four lane quarters of a tile
+    auto group_coords = [&](int tile, int (&gl)[4], int (&gq)[4]) {
+        const int g0 = tile * 4;
+        gl[0] = g0 / p.groups_per_line;
+        gq[0] = (g0 - gl[0] * p.groups_per_line) * kTap3Group;
 #pragma unroll
         for (int g = 1; g < 4; ++g) {
-            gi[g] = gi[g - 1];
-            gp[g] = gp[g - 1];
+            gl[g] = gl[g - 1];
             gq[g] = gq[g - 1] + kTap3Group;
-            while (gq[g] >= p.Wwide) {
-                gq[g] -= p.Wwide;
-                if (++gp[g] == p.Ho) {
-                    gp[g] = 0;
-                    ++gi[g];
-                }
+            if (gq[g] >= p.Wo) {
+                gq[g] = 0;
+                ++gl[g];
             }
         }
     };
@@ -230,8 +264,13 @@ __global__ void __launch_bounds__(kL1Threads, 1) l1_block_kernel(const __grid_co
         int stage = 0;
         uint32_t phase = 0;
         for (int t = 0; t < T; ++t) {
-            int gi[4], gp[4], gq[4];
-            group_coords(tile_of(t), gi, gp, gq);
+            int gl[4], gq[4], gi[4], gp[4];
+            group_coords(tile_of(t), gl, gq);
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                gi[g] = gl[g] / p.Ho;
+                gp[g] = gl[g] - gi[g] * p.Ho;
+            }
             for (int tr = 0; tr < 3; ++tr) {
                 mbar_wait(&empty_bar[stage], phase ^ 1u);
                 if (elect_one()) {
@@ -258,11 +297,18 @@ __global__ void __launch_bounds__(kL1Threads, 1) l1_block_kernel(const __grid_co
             const uint32_t base = smem_u32(smem);
             int stage = 0;
             uint32_t phase = 0;
+            long long tw[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // total, d0_empty, full, d1_empty, t2_ready, d2_empty, sub_written
+            const long long t_begin = clock64();
+            auto timed_wait = [&](uint64_t* bar, uint32_t parity, int slot) {
+                const long long a = clock64();
+                mbar_wait_cluster(bar, parity);
+                tw[slot] += clock64() - a;
+            };
             auto g0 = [&](int t) {
-                mbar_wait_cluster(d0_empty, (t & 1u) ^ 1u);
+                timed_wait(d0_empty, (t & 1u) ^ 1u, 1);
                 tc_fence_after();
                 for (int tr = 0; tr < 3; ++tr) {
-                    mbar_wait_cluster(&full_bar[stage], phase);
+                    timed_wait(&full_bar[stage], phase, 2);
                     tc_fence_after();
                     if (elect_one()) {
                         const uint64_t adesc = umma_desc_k_sw128(base + static_cast<uint32_t>(kL1OffA + stage * kABytes));
@@ -282,8 +328,8 @@ __global__ void __launch_bounds__(kL1Threads, 1) l1_block_kernel(const __grid_co
                 }
             };
             auto g1 = [&](int t) {
-                mbar_wait_cluster(d1_empty, (t & 1u) ^ 1u);
-                mbar_wait_cluster(t2_ready, t & 1u);
+                timed_wait(d1_empty, (t & 1u) ^ 1u, 3);
+                timed_wait(t2_ready, t & 1u, 4);
                 tc_fence_after();
                 if (elect_one()) {
                     const uint64_t adesc = umma_desc_k_sw128(base + static_cast<uint32_t>(Cfg::kOffT2));
@@ -298,9 +344,9 @@ __global__ void __launch_bounds__(kL1Threads, 1) l1_block_kernel(const __grid_co
                 __syncwarp();
             };
             auto g2 = [&](int t) {
-                mbar_wait_cluster(d2_empty, (t & 1u) ^ 1u);
+                timed_wait(d2_empty, (t & 1u) ^ 1u, 5);
                 for (int j = 0; j < 4; ++j) {
-                    mbar_wait_cluster(&sub_written[j], t & 1u);
+                    timed_wait(&sub_written[j], t & 1u, 6);
                     tc_fence_after();
                     if (elect_one()) {
                         const uint64_t adesc = umma_desc_k_sw128(base + static_cast<uint32_t>(Cfg::kOffStg1 + j * kStagingBytes));
@@ -322,45 +368,90 @@ __global__ void __launch_bounds__(kL1Threads, 1) l1_block_kernel(const __grid_co
                 if (t + 1 < T) g0(t + 1);
                 g2(t);
             }
+            if (p.dbg && lane == 0) {
+                tw[0] = clock64() - t_begin;
+                for (int i = 0; i < 8; ++i) p.dbg[pair * 8 + i] = tw[i];
+            }
         }
     } else if (warp == kL1DmaWarp) {
         // ===================== DMA: residual prefetch into the stg1 sub-tiles =====================
+        // The y staging tile is single-buffered, so a residual sub-tile can only be requested once the previous tile's
+        // sub-tile has drained; its HBM latency would be exposed every tile.  The NEXT tile's residual is therefore
+        // pulled into L2 one tile ahead (short distance: the lines are still there when the real load follows).
         if (lane == 0) {
             for (int t = 0; t < T; ++t) {
-                int gi[4], gp[4], gq[4];
-                group_coords(tile_of(t), gi, gp, gq);
+                int gl[4], gq[4];
+                group_coords(tile_of(t), gl, gq);
+                if (t + 1 < T) {
+                    int nl[4], nq[4];
+                    group_coords(tile_of(t + 1), nl, nq);
+                    for (int j = 0; j < 4; ++j)
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) tma_prefetch_l2_3d(&p.tmRes, j * kChunkCols, nq[g], nl[g]);
+                }
                 for (int j = 0; j < 4; ++j) {
-                    if (t > 0) {  // the previous tile's sub-tile j has been read by the second GEMM and copied out
+                    if (t > 0) {  // the previous tile's sub-tile j has been read by the second GEMM and stored
                         mbar_wait(&sub_consumed[j], (t - 1) & 1u);
-                        mbar_wait(&copy_done[j], (t - 1) & 1u);
+                        mbar_wait(&store_done[j], (t - 1) & 1u);
                     }
                     mbar_arrive_expect_tx(&res_ready[j], kStagingBytes);
 #pragma unroll
                     for (int g = 0; g < 4; ++g)
-                        tma_load_im2col_4d(&p.tmRes, &res_ready[j], stg1 + j * kStagingBytes + g * 4096, j * kChunkCols, gq[g],
-                                           gp[g], gi[g], 0, 0, kEvictFirst);
+                        tma_load_3d(&p.tmRes, &res_ready[j], stg1 + j * kStagingBytes + g * 4096, j * kChunkCols, gq[g], gl[g],
+                                    kEvictFirst);
                 }
             }
+        }
+    } else if (warp == kL1StoreWarp) {
+        // ===================== storer: y sub-tiles and the t1' tile leave through im2col-mode TMA stores =====================
+        if (lane == 0) {
+            for (int t = 0; t < T; ++t) {
+                int gl[4], gq[4];
+                group_coords(tile_of(t), gl, gq);
+                for (int j = 0; j < 4; ++j) {
+                    mbar_wait(&y_local[j], t & 1u);
+#pragma unroll
+                    for (int g = 0; g < 4; ++g)
+                        tma_store_3d(&p.tmOut1, stg1 + j * kStagingBytes + g * 4096, j * kChunkCols, gq[g], gl[g]);
+                    tma_store_commit();
+                }
+                // bulk groups complete in order: allow the 3 - j most recent ones to be pending
+                tma_store_wait_read<3>();
+                mbar_arrive(&store_done[0]);
+                tma_store_wait_read<2>();
+                mbar_arrive(&store_done[1]);
+                tma_store_wait_read<1>();
+                mbar_arrive(&store_done[2]);
+                tma_store_wait_read<0>();
+                mbar_arrive(&store_done[3]);
+                mbar_wait(e2_local, t & 1u);
+#pragma unroll
+                for (int g = 0; g < 4; ++g) tma_store_3d(&p.tmOut2, stg2 + g * 4096, 0, gq[g], gl[g]);
+                tma_store_commit();
+                tma_store_wait_read<0>();
+                mbar_arrive(stg2_free);
+            }
+            tma_store_wait_all<0>();
         }
     } else if (warp >= 2 && warp < 18) {
         // ===================== epilogue warps =====================
         const int quarter = warp & 3;
         const int cg = (warp - 2) >> 2;                 // 16-column group (E0, E2) / y sub-tile (E1)
         const int l = quarter * 32 + lane;              // TMEM lane = row of every smem tile
-        const int tid4 = ((warp - 2) & 3) * 32 + lane;  // index inside the four warps that share cg (any order)
-        const int tid16 = (warp - 2) * 32 + lane;
         const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
-        uint8_t* out1 = reinterpret_cast<uint8_t*>(p.out1);
-        uint8_t* out2 = reinterpret_cast<uint8_t*>(p.out2);
-        // widened row of this thread's lane, advanced without divisions from tile to tile
-        int row = tile_of(0) * kTap3Rows + quarter * kTap3Group + lane;
-        int line = row / p.Wwide;
-        int qq = row - line * p.Wwide;
-        const int step = 2 * num_pairs * kTap3Rows;
-        const int step_lines = step / p.Wwide, step_q = step - step_lines * p.Wwide;
 
+        long long te[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+        long long tl = clock64();
+        const long long te_begin = tl;
+        auto lap = [&](int slot) {   // cycles since the previous lap go to `slot`
+            const long long now = clock64();
+            te[slot] += now - tl;
+            tl = now;
+        };
         auto e0 = [&](int t) {
+            lap(11);
             mbar_wait(d0_full, t & 1u);
+            lap(0);
             tc_fence_after();
             uint32_t v0[16], v1[16], v2[16];
             const uint32_t ta = lane_base + kD0 + static_cast<uint32_t>(cg * 16);
@@ -386,30 +477,29 @@ __global__ void __launch_bounds__(kL1Threads, 1) l1_block_kernel(const __grid_co
                 h = __hmax2(h, __floats2bfloat162_rn(0.0f, 0.0f));
                 w[c >> 1] = *reinterpret_cast<const uint32_t*>(&h);
             }
+            lap(1);
             mbar_wait(t2_free, (t & 1u) ^ 1u);   // the first GEMM-1 of the previous tile has read the t2 tile
+            lap(2);
             uint8_t* rp = t2_tile + l * 128;
             *reinterpret_cast<uint4*>(rp + (((2 * cg) ^ (l & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
             *reinterpret_cast<uint4*>(rp + (((2 * cg + 1) ^ (l & 7)) << 4)) = make_uint4(w[4], w[5], w[6], w[7]);
-            // output row table of this tile, one copy per group of four warps (each group is synchronised by its own
-            // named barrier before it reads the table)
-            rowoff[(cg * 2 + (t & 1)) * 128 + l] = (lane < kTap3Group && row < p.M && qq < p.Wo) ? line * p.Wo + qq : -1;
-            row += step;
-            line += step_lines;
-            qq += step_q;
-            if (qq >= p.Wwide) {
-                qq -= p.Wwide;
-                ++line;
-            }
-            fence_proxy_async_all();
+            // cta-scope release on purpose: a cluster-scope release would also wait for this thread's outstanding GLOBAL
+            // stores of the previous copy-out (measured: 45 % of the MMA thread's time went into this barrier); the data
+            // the pair MMA reads is this SM's own shared memory, ordered by the proxy fence above
+            fence_proxy_async_smem();
             __syncwarp();
-            if (lane == 0) mbar_arrive_leader_release(t2_ready);
+            if (lane == 0) mbar_arrive_leader(t2_ready);
+            lap(1);
         };
         auto e1 = [&](int t) {
             const int j = cg;
             uint8_t* sub = stg1 + j * kStagingBytes;
+            lap(11);
             mbar_wait(d1_full, t & 1u);
+            lap(3);
             tc_fence_after();
             mbar_wait(&res_ready[j], t & 1u);
+            lap(4);
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
                 uint32_t v[32];
@@ -422,25 +512,16 @@ __global__ void __launch_bounds__(kL1Threads, 1) l1_block_kernel(const __grid_co
                 }
                 chain_convert_row(v, p.bias3 + j * kChunkCols + half * 32, nullptr, true, sub + l * 128, half, l);
             }
-            fence_proxy_async_all();
+            fence_proxy_async_smem();
             __syncwarp();
-            if (lane == 0) mbar_arrive_leader_release(&sub_written[j]);
-            named_bar_sync(1 + j, 128);              // the four warps of this sub-tile (local rows all written)
-            const int* ro = rowoff + (cg * 2 + (t & 1)) * 128;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {            // 128 rows x 8 chunks of 16 B, four rows per warp instruction
-                const int item = i * 128 + tid4;
-                const int r = item >> 3, chunk = item & 7;
-                const int dst_row = ro[r];
-                const uint4 val = *reinterpret_cast<const uint4*>(sub + r * 128 + ((chunk ^ (r & 7)) << 4));
-                if (dst_row >= 0)
-                    *reinterpret_cast<uint4*>(out1 + static_cast<size_t>(dst_row) * 512 + j * 128 + chunk * 16) = val;
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&copy_done[j]);
+            if (lane == 0) mbar_arrive_leader(&sub_written[j]);
+            if (lane == 0) mbar_arrive(&y_local[j]);
+            lap(5);
         };
         auto e2 = [&](int t) {
+            lap(11);
             mbar_wait(d2_full, t & 1u);
+            lap(8);
             tc_fence_after();
             uint32_t v[16];
             tmem_ld_32x16(lane_base + kD2 + static_cast<uint32_t>(cg * 16), v);
@@ -457,26 +538,24 @@ __global__ void __launch_bounds__(kL1Threads, 1) l1_block_kernel(const __grid_co
                 h = __hmax2(h, __floats2bfloat162_rn(0.0f, 0.0f));
                 w[c >> 1] = *reinterpret_cast<const uint32_t*>(&h);
             }
+            mbar_wait(stg2_free, (t & 1u) ^ 1u);   // the previous tile's t1' stores have read the staging tile
             uint8_t* rp = stg2 + l * 128;
             *reinterpret_cast<uint4*>(rp + (((2 * cg) ^ (l & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
             *reinterpret_cast<uint4*>(rp + (((2 * cg + 1) ^ (l & 7)) << 4)) = make_uint4(w[4], w[5], w[6], w[7]);
-            named_bar_sync(5, 512);
-            const int* ro = rowoff + (cg * 2 + (t & 1)) * 128;
-#pragma unroll
-            for (int i = 0; i < 2; ++i) {
-                const int item = i * 512 + tid16;
-                const int r = item >> 3, chunk = item & 7;
-                const int dst_row = ro[r];
-                const uint4 val = *reinterpret_cast<const uint4*>(stg2 + r * 128 + ((chunk ^ (r & 7)) << 4));
-                if (dst_row >= 0) *reinterpret_cast<uint4*>(out2 + static_cast<size_t>(dst_row) * 128 + chunk * 16) = val;
-            }
-            named_bar_sync(6, 512);                  // stg2 and this tile's row table may be overwritten
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(e2_local);
+            lap(9);
         };
         e0(0);
         for (int t = 0; t < T; ++t) {
             e1(t);
             if (t + 1 < T) e0(t + 1);
             e2(t);
+        }
+        if (p.dbg && rank == 0 && warp == 2 && lane == 0) {
+            for (int i = 0; i < 12; ++i) p.dbg[1024 + pair * 12 + i] = te[i];
+            p.dbg[1024 + 74 * 12 + pair] = clock64() - te_begin;
         }
     }
 

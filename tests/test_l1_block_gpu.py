@@ -16,7 +16,9 @@ def _ref(x_nhwc, w, b, pad):
     return F.conv2d(x_nhwc.float().permute(0, 3, 1, 2), w.float(), b.float(), padding=pad).permute(0, 2, 3, 1)
 
 
-@pytest.mark.parametrize("B,H", [(1, 8), (2, 24), (3, 15), (2, 120), (20, 60)], ids=["tiny", "b2h24", "h15", "h120", "persistent"])
+# the kernel needs an image width that is a multiple of 30 (lane quarters aligned to image lines)
+@pytest.mark.parametrize("B,H", [(1, 30), (3, 30), (2, 60), (2, 120), (20, 60), (5, 90)],
+                         ids=["tiny", "b3h30", "h60", "h120", "persistent", "h90"])
 @pytest.mark.parametrize("integer", [True, False], ids=["int", "gauss"])
 def test_l1_block(B, H, integer):
     torch.backends.cudnn.allow_tf32 = False
@@ -64,3 +66,19 @@ def test_l1_block(B, H, integer):
     else:
         torch.testing.assert_close(out1.float(), y.float(), rtol=2e-2, atol=2e-2)
         torch.testing.assert_close(out2.float(), t1n.float(), rtol=3e-2, atol=3e-2)
+
+
+def test_l1_block_rejects_other_widths():
+    from incremental_multimodal_medical_learning_ii_b200 import _native as N
+    from incremental_multimodal_medical_learning_ii_b200 import packing
+    lib = N.lib()
+    dev = torch.device("cuda:0")
+    z = lambda *s: torch.zeros(*s, dtype=torch.bfloat16)  # noqa: E731
+    c2 = packing.pack_single_conv(z(64, 64, 3, 3), torch.zeros(64), 1, 1, dev)
+    c3 = packing.pack_single_conv(z(256, 64, 1, 1), torch.zeros(256), 1, 0, dev)
+    c1 = packing.pack_single_conv(z(64, 256, 1, 1), torch.zeros(64), 1, 0, dev)
+    t1, res = z(1, 16, 16, 64).to(dev), z(1, 16, 16, 256).to(dev)
+    out1, out2 = z(1, 16, 16, 256).to(dev), z(1, 16, 16, 64).to(dev)
+    rc = lib.bv_l1_block_nhwc(N.ptr(t1), 1, 16, 16, ctypes.byref(c2[0]), ctypes.byref(c3[0]), N.ptr(res), N.ptr(out1),
+                              ctypes.byref(c1[0]), N.ptr(out2), N.current_stream_handle(dev))
+    assert rc == N.BV_ERR_INVALID
