@@ -808,7 +808,7 @@ static int build_plan(bv_handle* h, const void* frames, int dtype, int B, int C,
             }
             // layer1 blocks with an identity residual whose successor's conv1 is 64 wide: the whole tail of the block
             // (conv2 3x3, conv3 + identity, next conv1) is one CTA-pair kernel
-            if (env_flag("BV_L1_FUSED") && ds.w == nullptr && blk + 1 < BV_NUM_BLOCKS &&
+            if (!env_flag("BV_NO_L1_FUSED") && ds.w == nullptr && blk + 1 < BV_NUM_BLOCKS &&
                 l1_block_supported(c2, c3, h->w.conv1[blk + 1], cw)) {
                 PlanStep s;
                 s.l1 = true;

@@ -57,7 +57,8 @@ struct L1Cfg {
     static constexpr int kOffStg2 = kOffStg1 + 4 * kStagingBytes;
     static constexpr int kOffBars = kOffStg2 + (N2 / 64) * kStagingBytes;
     static constexpr int kNumBars = 2 * kL1Stages + 1 + 8 + 20 + 2;
-    static constexpr int kSmemBytes = kOffBars + kNumBars * 8 + 16;
+    static constexpr int kOffBias = (kOffBars + kNumBars * 8 + 16 + 15) / 16 * 16;               // fp32: bias3[256] | bias2[64] | bias1[N2]
+    static constexpr int kSmemBytes = kOffBias + (256 + 64 + N2) * 4;
     static constexpr uint32_t kWeightBytes = 3 * 96 * 128 + 128 * 128 + kW1Bytes;
     static_assert(kOffT2 % 1024 == 0 && kOffStg1 % 1024 == 0 && kOffStg2 % 1024 == 0, "operand tiles need 1024-byte alignment");
     static_assert(kSmemBytes <= 232448, "exceeds the 227 KB of shared memory a CTA may use");
@@ -144,6 +145,46 @@ __device__ __forceinline__ void tma_prefetch_l2_3d(const CUtensorMap* m, int c, 
                  : "memory");
 }
 
+// packed fp32x2 add (sm_100): halves the FADD count of the epilogues
+__device__ __forceinline__ float2 add2(float2 a, float2 b) {
+    float2 d;
+    asm("{\n\t.reg .b64 ra, rb, rd;\n\t"
+        "mov.b64 ra, {%2, %3};\n\t"
+        "mov.b64 rb, {%4, %5};\n\t"
+        "add.rn.f32x2 rd, ra, rb;\n\t"
+        "mov.b64 {%0, %1}, rd;\n\t}\n"
+        : "=f"(d.x), "=f"(d.y)
+        : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return d;
+}
+
+// y sub-tile epilogue for 64 accumulator columns of one row: + bias + residual (in place in the swizzled staging row),
+// ReLU after the bf16 rounding (max commutes with the rounding), bf16 pack.  `bias_s` points into shared memory.
+__device__ __forceinline__ void l1_convert_row64(const uint32_t (&v)[64], const float* __restrict__ bias_s, uint8_t* row_ptr,
+                                                 int l) {
+    const float4* bp = reinterpret_cast<const float4*>(bias_s);
+    const __nv_bfloat162 zero2 = __floats2bfloat162_rn(0.0f, 0.0f);
+#pragma unroll
+    for (int jj = 0; jj < 8; ++jj) {  // 16-byte group = 8 channels
+        uint4* sp = reinterpret_cast<uint4*>(row_ptr + ((jj ^ (l & 7)) << 4));
+        const uint4 rv = *sp;
+        const uint32_t r[4] = {rv.x, rv.y, rv.z, rv.w};
+        const float4 b0 = bp[2 * jj], b1 = bp[2 * jj + 1];
+        const float2 bb[4] = {make_float2(b0.x, b0.y), make_float2(b0.z, b0.w), make_float2(b1.x, b1.y), make_float2(b1.z, b1.w)};
+        uint32_t w[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            float2 a = make_float2(__uint_as_float(v[8 * jj + 2 * e]), __uint_as_float(v[8 * jj + 2 * e + 1]));
+            a = add2(a, bb[e]);
+            a = add2(a, make_float2(__uint_as_float(r[e] << 16), __uint_as_float(r[e] & 0xFFFF0000u)));
+            __nv_bfloat162 h = __floats2bfloat162_rn(a.x, a.y);
+            h = __hmax2(h, zero2);
+            w[e] = *reinterpret_cast<const uint32_t*>(&h);
+        }
+        *sp = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+}
+
 template <int N2>
 __global__ void __launch_bounds__(kL1Threads, 1) l1_block_kernel(const __grid_constant__ L1BlockParams p) {
     using Cfg = L1Cfg<N2>;
@@ -176,6 +217,9 @@ __global__ void __launch_bounds__(kL1Threads, 1) l1_block_kernel(const __grid_co
     uint64_t* e2_local = y_local + 4;             // per CTA, 16 warps: t1' tile written
     uint64_t* stg2_free = e2_local + 1;           // per CTA: the TMA stores of t1' have read smem
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + Cfg::kNumBars);
+    float* bias_s = reinterpret_cast<float*>(smem + Cfg::kOffBias);
+    for (int i = threadIdx.x; i < 256 + 64 + N2; i += kL1Threads)
+        bias_s[i] = (i < 256) ? __ldg(p.bias3 + i) : (i < 320 ? __ldg(p.bias2 + i - 256) : __ldg(p.bias1 + i - 320));
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -463,16 +507,18 @@ __global__ void __launch_bounds__(kL1Threads, 1) l1_block_kernel(const __grid_co
             __syncwarp();
             if (lane == 0) mbar_arrive_leader(d0_empty);
             uint32_t w[8];
-            const float* bp = p.bias2 + cg * 16;
+            const float* bp = bias_s + 256 + cg * 16;
 #pragma unroll
             for (int c = 0; c < 16; c += 2) {
-                float f[2];
-#pragma unroll
-                for (int u = 0; u < 2; ++u) {
-                    const float u1 = __shfl_down_sync(0xffffffffu, __uint_as_float(v1[c + u]), 1);
-                    const float u2 = __shfl_down_sync(0xffffffffu, __uint_as_float(v2[c + u]), 2);
-                    f[u] = (__uint_as_float(v0[c + u]) + u1) + (u2 + __ldg(bp + c + u));
-                }
+                float2 u1, u2;
+                u1.x = __shfl_down_sync(0xffffffffu, __uint_as_float(v1[c]), 1);
+                u1.y = __shfl_down_sync(0xffffffffu, __uint_as_float(v1[c + 1]), 1);
+                u2.x = __shfl_down_sync(0xffffffffu, __uint_as_float(v2[c]), 2);
+                u2.y = __shfl_down_sync(0xffffffffu, __uint_as_float(v2[c + 1]), 2);
+                const float2 a = add2(make_float2(__uint_as_float(v0[c]), __uint_as_float(v0[c + 1])), u1);
+                const float2 b = add2(u2, *reinterpret_cast<const float2*>(bp + c));
+                const float2 f2 = add2(a, b);
+                const float f[2] = {f2.x, f2.y};
                 __nv_bfloat162 h = __floats2bfloat162_rn(f[0], f[1]);
                 h = __hmax2(h, __floats2bfloat162_rn(0.0f, 0.0f));
                 w[c >> 1] = *reinterpret_cast<const uint32_t*>(&h);
@@ -500,17 +546,15 @@ __global__ void __launch_bounds__(kL1Threads, 1) l1_block_kernel(const __grid_co
             tc_fence_after();
             mbar_wait(&res_ready[j], t & 1u);
             lap(4);
-#pragma unroll
-            for (int half = 0; half < 2; ++half) {
-                uint32_t v[32];
-                tmem_ld_32x32(lane_base + kD1 + static_cast<uint32_t>(j * kChunkCols + half * 32), v);
+            {
+                uint32_t v[64];
+                tmem_ld_32x32(lane_base + kD1 + static_cast<uint32_t>(j * kChunkCols), *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
+                tmem_ld_32x32(lane_base + kD1 + static_cast<uint32_t>(j * kChunkCols + 32), *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
                 tmem_ld_wait();
-                if (half == 1) {
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive_leader(d1_empty);
-                }
-                chain_convert_row(v, p.bias3 + j * kChunkCols + half * 32, nullptr, true, sub + l * 128, half, l);
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_leader(d1_empty);
+                l1_convert_row64(v, bias_s + j * kChunkCols, sub + l * 128, l);
             }
             fence_proxy_async_smem();
             __syncwarp();
@@ -530,11 +574,12 @@ __global__ void __launch_bounds__(kL1Threads, 1) l1_block_kernel(const __grid_co
             __syncwarp();
             if (lane == 0) mbar_arrive_leader(d2_empty);
             uint32_t w[8];
-            const float* bp = p.bias1 + cg * 16;
+            const float* bp = bias_s + 320 + cg * 16;
 #pragma unroll
             for (int c = 0; c < 16; c += 2) {
-                __nv_bfloat162 h = __floats2bfloat162_rn(__uint_as_float(v[c]) + __ldg(bp + c),
-                                                         __uint_as_float(v[c + 1]) + __ldg(bp + c + 1));
+                const float2 a = add2(make_float2(__uint_as_float(v[c]), __uint_as_float(v[c + 1])),
+                                      *reinterpret_cast<const float2*>(bp + c));
+                __nv_bfloat162 h = __floats2bfloat162_rn(a.x, a.y);
                 h = __hmax2(h, __floats2bfloat162_rn(0.0f, 0.0f));
                 w[c >> 1] = *reinterpret_cast<const uint32_t*>(&h);
             }
