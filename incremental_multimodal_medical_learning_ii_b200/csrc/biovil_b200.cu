@@ -509,6 +509,17 @@ int launch_l1_block(const L1Launch& L, cudaStream_t st) {
         }
         const char* nm[12] = {"wait d0_full", "e0 compute+write", "wait t2_free", "wait d1_full", "wait res_ready", "e1 compute",
                               "e1 group barrier", "e1 copy-out", "wait d2_full", "e2 compute+copy", "e2 barrier", "between"};
+        static long long tr[64];
+        cudaMemcpy(tr, g_dbg + 2048, sizeof(tr), cudaMemcpyDeviceToHost);
+        const char* en[13] = {"G0 issued", "t2_ready seen", "G1 issued", "sub_written0", "sub_written1", "sub_written2", "sub_written3",
+                              "G2 issued", "E0: d0_full seen", "E0: t2_ready arrived", "E1: d1_full seen", "E1: res_ready seen", "E1 done"};
+        const long long base = tr[1];
+        for (int t = 0; t < 2; ++t)
+            for (int e = 0; e < 13; ++e) fprintf(stderr, "[trace] tile %d %-22s %8lld\n", 10 + t, en[e], tr[t * 32 + e] - base);
+        for (int t = 0; t < 2; ++t)
+            for (int e = 0; e < 5; ++e)
+                fprintf(stderr, "[trace-ns] tile %d %-22s leader %8lld  peer %8lld\n", 10 + t, en[8 + e], tr[t * 32 + 16 + e] - tr[16],
+                        tr[t * 32 + 24 + e] - tr[16]);
         fprintf(stderr, "[timing] l1_block epilogue warp 2 (%.0f cyc):", tot);
         for (int j = 0; j < 12; ++j) fprintf(stderr, " %s %.1f%%;", nm[j], 100 * e[j] / tot);
         fprintf(stderr, "\n");

@@ -27,8 +27,9 @@
 //                         G0(t+1)                                 copy-out of y rows; sub-tiles feed G2
 //                         G2(t)      <- sub_written[j]     E0(t+1)
 //                                                          E2(t): D2 + bias, ReLU -> stg2 -> copy-out of t1' rows
-// Warp roles (640 threads): 0 TMA producer (weights once, A ring), 1 MMA issuer (leader CTA) / idle (peer),
-// 2..17 epilogue, 18 loader (residual prefetch into the stg1 sub-tiles as they drain), 19 storer (y and t1' leave
+// Warp roles (768 threads): 0 TMA producer (weights once, A ring), 1 MMA issuer (leader CTA) / idle (peer),
+// 2..17 epilogue of G0/G1, 20..23 epilogue of G2 (its long wait for the second GEMM must not stall the others),
+// 18 loader (residual prefetch into the stg1 sub-tiles as they drain), 19 storer (y and t1' leave
 // through tiled 3-D TMA stores of [1 line x 30 pixels x 64 channels]: the two overlap rows of each lane quarter are
 // not part of the box and the padding columns are out of bounds, so neither is written; per-thread copy-out loops
 // stalled the epilogue warps on the store queue for 40 % of their time).
@@ -38,10 +39,11 @@
 
 namespace bv {
 
-constexpr int kL1Threads = 20 * 32;
+constexpr int kL1Threads = 24 * 32;
 constexpr int kL1Stages = 3;
 constexpr int kL1DmaWarp = 18;
 constexpr int kL1StoreWarp = 19;
+constexpr int kL1E2Warp0 = 20;   // warps 20..23: epilogue of the second GEMM, one warp per TMEM lane quarter
 // shared-memory map (bytes)
 constexpr int kL1OffA = 0;                                 // 3 x 16 KB A ring
 constexpr int kL1OffW2 = kL1OffA + kL1Stages * kABytes;    // 3 filter rows x [96 rows x 128 B]
@@ -158,23 +160,25 @@ __device__ __forceinline__ float2 add2(float2 a, float2 b) {
     return d;
 }
 
-// y sub-tile epilogue for 64 accumulator columns of one row: + bias + residual (in place in the swizzled staging row),
-// ReLU after the bf16 rounding (max commutes with the rounding), bf16 pack.  `bias_s` points into shared memory.
-__device__ __forceinline__ void l1_convert_row64(const uint32_t (&v)[64], const float* __restrict__ bias_s, uint8_t* row_ptr,
-                                                 int l) {
+// y sub-tile epilogue for 32 accumulator columns (half of a 64-column sub-tile) of one row: + bias + residual (in place
+// in the swizzled staging row), ReLU after the bf16 rounding (max commutes with the rounding), bf16 pack.
+// `bias_s` points into shared memory at the first of the 32 columns.
+__device__ __forceinline__ void l1_convert_row32(const uint32_t (&v)[32], const float* __restrict__ bias_s, uint8_t* row_ptr,
+                                                 int l, int half) {
     const float4* bp = reinterpret_cast<const float4*>(bias_s);
     const __nv_bfloat162 zero2 = __floats2bfloat162_rn(0.0f, 0.0f);
 #pragma unroll
-    for (int jj = 0; jj < 8; ++jj) {  // 16-byte group = 8 channels
+    for (int j4 = 0; j4 < 4; ++j4) {  // 16-byte group = 8 channels
+        const int jj = half * 4 + j4;
         uint4* sp = reinterpret_cast<uint4*>(row_ptr + ((jj ^ (l & 7)) << 4));
         const uint4 rv = *sp;
         const uint32_t r[4] = {rv.x, rv.y, rv.z, rv.w};
-        const float4 b0 = bp[2 * jj], b1 = bp[2 * jj + 1];
+        const float4 b0 = bp[2 * j4], b1 = bp[2 * j4 + 1];
         const float2 bb[4] = {make_float2(b0.x, b0.y), make_float2(b0.z, b0.w), make_float2(b1.x, b1.y), make_float2(b1.z, b1.w)};
         uint32_t w[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-            float2 a = make_float2(__uint_as_float(v[8 * jj + 2 * e]), __uint_as_float(v[8 * jj + 2 * e + 1]));
+            float2 a = make_float2(__uint_as_float(v[8 * j4 + 2 * e]), __uint_as_float(v[8 * j4 + 2 * e + 1]));
             a = add2(a, bb[e]);
             a = add2(a, make_float2(__uint_as_float(r[e] << 16), __uint_as_float(r[e] & 0xFFFF0000u)));
             __nv_bfloat162 h = __floats2bfloat162_rn(a.x, a.y);
@@ -249,8 +253,8 @@ __global__ void __launch_bounds__(kL1Threads, 1) l1_block_kernel(const __grid_co
         mbar_init(d1_full, 1);
         mbar_init(d1_empty, 32);
         mbar_init(d2_full, 1);
-        mbar_init(d2_empty, 32);
-        mbar_init(e2_local, 16);
+        mbar_init(d2_empty, 8);
+        mbar_init(e2_local, 4);
         mbar_init(stg2_free, 1);
         for (int j = 0; j < 4; ++j) {
             mbar_init(&sub_written[j], 8);
@@ -348,6 +352,9 @@ __global__ void __launch_bounds__(kL1Threads, 1) l1_block_kernel(const __grid_co
                 mbar_wait_cluster(bar, parity);
                 tw[slot] += clock64() - a;
             };
+            auto trace = [&](int t, int ev) {
+                if (p.dbg && pair == 0 && t >= 10 && t < 12 && lane == 0) p.dbg[2048 + (t - 10) * 32 + ev] = clock64();
+            };
             auto g0 = [&](int t) {
                 timed_wait(d0_empty, (t & 1u) ^ 1u, 1);
                 tc_fence_after();
@@ -364,6 +371,7 @@ __global__ void __launch_bounds__(kL1Threads, 1) l1_block_kernel(const __grid_co
                         umma_commit_pair(&empty_bar[stage]);
                         if (tr == 2) umma_commit_pair(d0_full);
                     }
+                    if (tr == 2) trace(t, 0);   // G0 issued
                     __syncwarp();
                     if (++stage == kL1Stages) {
                         stage = 0;
@@ -374,6 +382,7 @@ __global__ void __launch_bounds__(kL1Threads, 1) l1_block_kernel(const __grid_co
             auto g1 = [&](int t) {
                 timed_wait(d1_empty, (t & 1u) ^ 1u, 3);
                 timed_wait(t2_ready, t & 1u, 4);
+                trace(t, 1);   // t2_ready seen
                 tc_fence_after();
                 if (elect_one()) {
                     const uint64_t adesc = umma_desc_k_sw128(base + static_cast<uint32_t>(Cfg::kOffT2));
@@ -386,11 +395,13 @@ __global__ void __launch_bounds__(kL1Threads, 1) l1_block_kernel(const __grid_co
                     umma_commit_pair(d1_full);
                 }
                 __syncwarp();
+                trace(t, 2);   // G1 issued
             };
             auto g2 = [&](int t) {
                 timed_wait(d2_empty, (t & 1u) ^ 1u, 5);
                 for (int j = 0; j < 4; ++j) {
                     timed_wait(&sub_written[j], t & 1u, 6);
+                    trace(t, 3 + j);   // sub_written[j] seen
                     tc_fence_after();
                     if (elect_one()) {
                         const uint64_t adesc = umma_desc_k_sw128(base + static_cast<uint32_t>(Cfg::kOffStg1 + j * kStagingBytes));
@@ -403,6 +414,7 @@ __global__ void __launch_bounds__(kL1Threads, 1) l1_block_kernel(const __grid_co
                         if (j == 3) umma_commit_pair(d2_full);
                     }
                     __syncwarp();
+                    if (j == 3) trace(t, 7);   // G2 issued
                 }
             };
             mbar_wait_cluster(w_bar, 0);
@@ -477,8 +489,45 @@ __global__ void __launch_bounds__(kL1Threads, 1) l1_block_kernel(const __grid_co
             }
             tma_store_wait_all<0>();
         }
+    } else if (warp >= kL1E2Warp0) {
+        // ===================== epilogue of the second GEMM: D2 -> + bias, ReLU -> stg2 (one warp per lane quarter) =====================
+        const int quarter = warp & 3;
+        const int l = quarter * 32 + lane;
+        const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+        const __nv_bfloat162 zero2 = __floats2bfloat162_rn(0.0f, 0.0f);
+        for (int t = 0; t < T; ++t) {
+            mbar_wait(d2_full, t & 1u);
+            tc_fence_after();
+            uint32_t w[N2 / 2];
+#pragma unroll
+            for (int c16 = 0; c16 < N2 / 16; ++c16) {
+                uint32_t v[16];
+                tmem_ld_32x16(lane_base + kD2 + static_cast<uint32_t>(c16 * 16), v);
+                tmem_ld_wait();
+                const float* bp = bias_s + 320 + c16 * 16;
+#pragma unroll
+                for (int c = 0; c < 16; c += 2) {
+                    const float2 a = add2(make_float2(__uint_as_float(v[c]), __uint_as_float(v[c + 1])),
+                                          *reinterpret_cast<const float2*>(bp + c));
+                    __nv_bfloat162 h = __floats2bfloat162_rn(a.x, a.y);
+                    h = __hmax2(h, zero2);
+                    w[c16 * 8 + (c >> 1)] = *reinterpret_cast<const uint32_t*>(&h);
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_leader(d2_empty);
+            mbar_wait(stg2_free, (t & 1u) ^ 1u);   // the previous tile's t1' stores have read the staging tile
+            uint8_t* rp = stg2 + l * 128;
+#pragma unroll
+            for (int ch = 0; ch < N2 / 8; ++ch)
+                *reinterpret_cast<uint4*>(rp + ((ch ^ (l & 7)) << 4)) = make_uint4(w[4 * ch], w[4 * ch + 1], w[4 * ch + 2], w[4 * ch + 3]);
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(e2_local);
+        }
     } else if (warp >= 2 && warp < 18) {
-        // ===================== epilogue warps =====================
+        // ===================== epilogue warps of the first two GEMMs =====================
         const int quarter = warp & 3;
         const int cg = (warp - 2) >> 2;                 // 16-column group (E0, E2) / y sub-tile (E1)
         const int l = quarter * 32 + lane;              // TMEM lane = row of every smem tile
@@ -492,9 +541,17 @@ __global__ void __launch_bounds__(kL1Threads, 1) l1_block_kernel(const __grid_co
             te[slot] += now - tl;
             tl = now;
         };
+        auto gtime = []() { unsigned long long g; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g)); return static_cast<long long>(g); };
+        auto etrace = [&](int t, int ev) {
+            if (p.dbg && pair == 0 && rank == 0 && warp == 2 && lane == 0 && t >= 10 && t < 12) p.dbg[2048 + (t - 10) * 32 + ev] = clock64();
+            // wall-clock (ns) copies for cross-SM comparison: leader at [16 + ev - 8], peer at [24 + ev - 8]
+            if (p.dbg && pair == 0 && warp == 2 && lane == 0 && t >= 10 && t < 12 && ev >= 8)
+                p.dbg[2048 + (t - 10) * 32 + (rank == 0 ? 16 : 24) + (ev - 8)] = gtime();
+        };
         auto e0 = [&](int t) {
             lap(11);
             mbar_wait(d0_full, t & 1u);
+            etrace(t, 8);    // d0_full seen
             lap(0);
             tc_fence_after();
             uint32_t v0[16], v1[16], v2[16];
@@ -535,6 +592,7 @@ __global__ void __launch_bounds__(kL1Threads, 1) l1_block_kernel(const __grid_co
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive_leader(t2_ready);
+            etrace(t, 9);    // t2_ready arrived
             lap(1);
         };
         auto e1 = [&](int t) {
@@ -542,61 +600,35 @@ __global__ void __launch_bounds__(kL1Threads, 1) l1_block_kernel(const __grid_co
             uint8_t* sub = stg1 + j * kStagingBytes;
             lap(11);
             mbar_wait(d1_full, t & 1u);
+            etrace(t, 10);   // d1_full seen
             lap(3);
             tc_fence_after();
             mbar_wait(&res_ready[j], t & 1u);
+            etrace(t, 11);   // res_ready seen
             lap(4);
-            {
-                uint32_t v[64];
-                tmem_ld_32x32(lane_base + kD1 + static_cast<uint32_t>(j * kChunkCols), *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
-                tmem_ld_32x32(lane_base + kD1 + static_cast<uint32_t>(j * kChunkCols + 32), *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                uint32_t v[32];
+                tmem_ld_32x32(lane_base + kD1 + static_cast<uint32_t>(j * kChunkCols + half * 32), v);
                 tmem_ld_wait();
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive_leader(d1_empty);
-                l1_convert_row64(v, bias_s + j * kChunkCols, sub + l * 128, l);
+                if (half == 1) {
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_leader(d1_empty);
+                }
+                l1_convert_row32(v, bias_s + j * kChunkCols + half * 32, sub + l * 128, l, half);
             }
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive_leader(&sub_written[j]);
             if (lane == 0) mbar_arrive(&y_local[j]);
+            etrace(t, 12);   // E1 done
             lap(5);
-        };
-        auto e2 = [&](int t) {
-            lap(11);
-            mbar_wait(d2_full, t & 1u);
-            lap(8);
-            tc_fence_after();
-            uint32_t v[16];
-            tmem_ld_32x16(lane_base + kD2 + static_cast<uint32_t>(cg * 16), v);
-            tmem_ld_wait();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive_leader(d2_empty);
-            uint32_t w[8];
-            const float* bp = bias_s + 320 + cg * 16;
-#pragma unroll
-            for (int c = 0; c < 16; c += 2) {
-                const float2 a = add2(make_float2(__uint_as_float(v[c]), __uint_as_float(v[c + 1])),
-                                      *reinterpret_cast<const float2*>(bp + c));
-                __nv_bfloat162 h = __floats2bfloat162_rn(a.x, a.y);
-                h = __hmax2(h, __floats2bfloat162_rn(0.0f, 0.0f));
-                w[c >> 1] = *reinterpret_cast<const uint32_t*>(&h);
-            }
-            mbar_wait(stg2_free, (t & 1u) ^ 1u);   // the previous tile's t1' stores have read the staging tile
-            uint8_t* rp = stg2 + l * 128;
-            *reinterpret_cast<uint4*>(rp + (((2 * cg) ^ (l & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
-            *reinterpret_cast<uint4*>(rp + (((2 * cg + 1) ^ (l & 7)) << 4)) = make_uint4(w[4], w[5], w[6], w[7]);
-            fence_proxy_async_smem();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(e2_local);
-            lap(9);
         };
         e0(0);
         for (int t = 0; t < T; ++t) {
             e1(t);
             if (t + 1 < T) e0(t + 1);
-            e2(t);
         }
         if (p.dbg && rank == 0 && warp == 2 && lane == 0) {
             for (int i = 0; i < 12; ++i) p.dbg[1024 + pair * 12 + i] = te[i];
