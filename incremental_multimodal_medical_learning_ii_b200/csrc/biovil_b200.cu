@@ -482,6 +482,8 @@ int launch_l1_block(const L1Launch& L, cudaStream_t st) {
     cfg.attrs = at;
     cfg.numAttrs = 1;
     bv::L1BlockParams prm = L.p;
+    // measured (ncu): the L2 prefetch adds 0.6 GB of DRAM reads per launch and does not change the duration
+    prm.l2_prefetch = env_flag("BV_L1_PREFETCH") ? 1 : 0;
     if (env_flag("BV_TIMING")) {
         if (!g_dbg) cudaMalloc(&g_dbg, 4 * 8 * 1024);
         cudaMemsetAsync(g_dbg, 0, 4 * 8 * 1024, st);

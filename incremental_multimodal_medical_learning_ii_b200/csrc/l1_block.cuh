@@ -22,11 +22,10 @@
 // their origin.  Other widths take the two-kernel path.
 //
 // Per tile t and CTA:     MMA thread (leader)              16 epilogue warps
-//                         G0(t)                            E0(t): D0 -> taps combined, bias, ReLU -> t2 tile (smem)
-//                         G1(t)      <- t2_ready           E1(t): D1 + bias + residual (in place in stg1), ReLU;
-//                         G0(t+1)                                 copy-out of y rows; sub-tiles feed G2
-//                         G2(t)      <- sub_written[j]     E0(t+1)
-//                                                          E2(t): D2 + bias, ReLU -> stg2 -> copy-out of t1' rows
+//                         G1(t)      <- t2_ready(t)        E1(t):   D1 + bias + identity (in place in stg1), ReLU;
+//                         G0(t+1)                                   the y sub-tiles feed G2 and the TMA stores
+//                         G2(t)      <- sub_written[j]     E0(t+1): D0 -> taps combined, bias, ReLU -> t2 tile (smem)
+//                                                          E2(t) (own warps): D2 + bias, ReLU -> stg2 -> TMA stores
 // Warp roles (768 threads): 0 TMA producer (weights once, A ring), 1 MMA issuer (leader CTA) / idle (peer),
 // 2..17 epilogue of G0/G1, 20..23 epilogue of G2 (its long wait for the second GEMM must not stall the others),
 // 18 loader (residual prefetch into the stg1 sub-tiles as they drain), 19 storer (y and t1' leave
@@ -82,6 +81,7 @@ struct L1BlockParams {
     int num_groups;       // B * Ho * Wo / 30 lane quarters of work
     int num_tiles;        // ceil(num_groups / 4)
     int num_pair_tiles;   // ceil(num_tiles / 2)
+    int l2_prefetch;      // pull the next tile's identity rows into L2 one tile ahead
     long long* dbg;       // optional [pairs][8] cycle counters of the leader's MMA thread (BV_TIMING)
 };
 
@@ -189,6 +189,33 @@ __device__ __forceinline__ void l1_convert_row32(const uint32_t (&v)[32], const 
     }
 }
 
+// 16 accumulator columns (two 16-byte groups, index g2 = 0..3 inside the 64-column sub-tile) of one row
+__device__ __forceinline__ void l1_convert_row16(const uint32_t (&v)[16], const float* __restrict__ bias_s, uint8_t* row_ptr,
+                                                 int l, int g2) {
+    const float4* bp = reinterpret_cast<const float4*>(bias_s);
+    const __nv_bfloat162 zero2 = __floats2bfloat162_rn(0.0f, 0.0f);
+#pragma unroll
+    for (int j2 = 0; j2 < 2; ++j2) {
+        const int jj = g2 * 2 + j2;
+        uint4* sp = reinterpret_cast<uint4*>(row_ptr + ((jj ^ (l & 7)) << 4));
+        const uint4 rv = *sp;
+        const uint32_t r[4] = {rv.x, rv.y, rv.z, rv.w};
+        const float4 b0 = bp[2 * j2], b1 = bp[2 * j2 + 1];
+        const float2 bb[4] = {make_float2(b0.x, b0.y), make_float2(b0.z, b0.w), make_float2(b1.x, b1.y), make_float2(b1.z, b1.w)};
+        uint32_t w[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            float2 a = make_float2(__uint_as_float(v[8 * j2 + 2 * e]), __uint_as_float(v[8 * j2 + 2 * e + 1]));
+            a = add2(a, bb[e]);
+            a = add2(a, make_float2(__uint_as_float(r[e] << 16), __uint_as_float(r[e] & 0xFFFF0000u)));
+            __nv_bfloat162 h = __floats2bfloat162_rn(a.x, a.y);
+            h = __hmax2(h, zero2);
+            w[e] = *reinterpret_cast<const uint32_t*>(&h);
+        }
+        *sp = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+}
+
 template <int N2>
 __global__ void __launch_bounds__(kL1Threads, 1) l1_block_kernel(const __grid_constant__ L1BlockParams p) {
     using Cfg = L1Cfg<N2>;
@@ -213,11 +240,11 @@ __global__ void __launch_bounds__(kL1Threads, 1) l1_block_kernel(const __grid_co
     uint64_t* d1_empty = w_bar + 6;               // leader, 32
     uint64_t* d2_full = w_bar + 7;                // per CTA
     uint64_t* d2_empty = w_bar + 8;               // leader, 32
-    uint64_t* sub_written = w_bar + 9;            // [4] leader, 8 (4 warps x 2 CTAs): y sub-tile j complete
+    uint64_t* sub_written = w_bar + 9;            // [4] leader, 32 (16 warps x 2 CTAs): y sub-tile j complete
     uint64_t* sub_consumed = sub_written + 4;     // [4] per CTA (multicast commit after G2 k-block j)
     uint64_t* store_done = sub_consumed + 4;      // [4] per CTA: the TMA stores of y sub-tile j have read smem
     uint64_t* res_ready = store_done + 4;         // [4] per CTA: residual sub-tile j landed (TMA tx)
-    uint64_t* y_local = res_ready + 4;            // [4] per CTA, 4 warps: y sub-tile j written (for the storer)
+    uint64_t* y_local = res_ready + 4;            // [4] per CTA, 16 warps: y sub-tile j written (for the storer)
     uint64_t* e2_local = y_local + 4;             // per CTA, 16 warps: t1' tile written
     uint64_t* stg2_free = e2_local + 1;           // per CTA: the TMA stores of t1' have read smem
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + Cfg::kNumBars);
@@ -257,11 +284,11 @@ __global__ void __launch_bounds__(kL1Threads, 1) l1_block_kernel(const __grid_co
         mbar_init(e2_local, 4);
         mbar_init(stg2_free, 1);
         for (int j = 0; j < 4; ++j) {
-            mbar_init(&sub_written[j], 8);
+            mbar_init(&sub_written[j], 32);
             mbar_init(&sub_consumed[j], 1);
             mbar_init(&store_done[j], 1);
             mbar_init(&res_ready[j], 1);
-            mbar_init(&y_local[j], 4);
+            mbar_init(&y_local[j], 16);
         }
         fence_barrier_init();
     }
@@ -417,6 +444,9 @@ __global__ void __launch_bounds__(kL1Threads, 1) l1_block_kernel(const __grid_co
                     if (j == 3) trace(t, 7);   // G2 issued
                 }
             };
+            // (Running E0(t+1) before E1(t) - to fill the wait for the identity rows - with G0/G1 one tile further ahead was
+            // measured 10 % slower: the identity tile is the critical resource either way and the longer MMA queue
+            // delays the G2 that frees it.)
             mbar_wait_cluster(w_bar, 0);
             g0(0);
             for (int t = 0; t < T; ++t) {
@@ -438,7 +468,7 @@ __global__ void __launch_bounds__(kL1Threads, 1) l1_block_kernel(const __grid_co
             for (int t = 0; t < T; ++t) {
                 int gl[4], gq[4];
                 group_coords(tile_of(t), gl, gq);
-                if (t + 1 < T) {
+                if (p.l2_prefetch && t + 1 < T) {
                     int nl[4], nq[4];
                     group_coords(tile_of(t + 1), nl, nq);
                     for (int j = 0; j < 4; ++j)
@@ -595,33 +625,36 @@ __global__ void __launch_bounds__(kL1Threads, 1) l1_block_kernel(const __grid_co
             etrace(t, 9);    // t2_ready arrived
             lap(1);
         };
+        // All 16 warps work on ONE 64-column sub-tile at a time (warp (quarter, cg) converts 16 of its columns), so
+        // sub-tile 0 is complete after a quarter of E1: its second-GEMM k-block, its TMA store and - most important -
+        // the reload of the NEXT tile's identity rows into it start while sub-tiles 1..3 are still being converted.
         auto e1 = [&](int t) {
-            const int j = cg;
-            uint8_t* sub = stg1 + j * kStagingBytes;
             lap(11);
             mbar_wait(d1_full, t & 1u);
             etrace(t, 10);   // d1_full seen
             lap(3);
             tc_fence_after();
-            mbar_wait(&res_ready[j], t & 1u);
-            etrace(t, 11);   // res_ready seen
-            lap(4);
-#pragma unroll
-            for (int half = 0; half < 2; ++half) {
-                uint32_t v[32];
-                tmem_ld_32x32(lane_base + kD1 + static_cast<uint32_t>(j * kChunkCols + half * 32), v);
+#pragma unroll 1
+            for (int j = 0; j < 4; ++j) {
+                uint8_t* sub = stg1 + j * kStagingBytes;
+                uint32_t v[16];
+                tmem_ld_32x16(lane_base + kD1 + static_cast<uint32_t>(j * kChunkCols + cg * 16), v);
+                mbar_wait(&res_ready[j], t & 1u);
+                if (j == 0) etrace(t, 11);   // res_ready seen
                 tmem_ld_wait();
-                if (half == 1) {
+                if (j == 3) {
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive_leader(d1_empty);
                 }
-                l1_convert_row32(v, bias_s + j * kChunkCols + half * 32, sub + l * 128, l, half);
+                l1_convert_row16(v, bias_s + j * kChunkCols + cg * 16, sub + l * 128, l, cg);
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) {
+                    mbar_arrive_leader(&sub_written[j]);
+                    mbar_arrive(&y_local[j]);
+                }
             }
-            fence_proxy_async_smem();
-            __syncwarp();
-            if (lane == 0) mbar_arrive_leader(&sub_written[j]);
-            if (lane == 0) mbar_arrive(&y_local[j]);
             etrace(t, 12);   // E1 done
             lap(5);
         };
