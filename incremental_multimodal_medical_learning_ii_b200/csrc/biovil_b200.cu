@@ -133,7 +133,7 @@ struct ConvOperand {
 enum ConvCfg { kCfg256Deep = 0, kCfg256Res, kCfg128Res, kCfg128Deep, kCfg64, kCfg64BRes, kCfg64Wide, kCfg64Tap3, kNumCfg };
 // kCfg64Tap3 is a different kernel (conv3x3_tap3.cuh): the three horizontal taps of a filter row in one N = 192 MMA
 #define BV_FOR_EACH_CFG(X)                                                                                        \
-    X(kCfg256Deep, 256, 4, 2, false, false) X(kCfg256Res, 256, 3, 4, false, false)                                \
+    X(kCfg256Deep, 256, 4, 2, false, false) X(kCfg256Res, 256, 3, 5, false, false)                                \
     X(kCfg128Res, 128, 3, 7, false, false) X(kCfg128Deep, 128, 6, 2, false, false) X(kCfg64, 64, 8, 2, false, false) \
     X(kCfg64BRes, 64, 6, 2, true, false) X(kCfg64Wide, 64, 6, 2, true, true)
 const int kCfgBN[kNumCfg] = {256, 256, 128, 128, 64, 64, 64, 64};
@@ -147,7 +147,8 @@ struct ConvLaunch {
 
 // Chained conv3 -> next conv1 kernel: <N2, STAGES, NB1> per width of the second GEMM (see ChainCfg).
 // cfg 3: the downsample tail streams two A k-blocks per chunk and carries no residual -> deeper ring, fewer staging tiles
-#define BV_FOR_EACH_CHAIN(X) X(0, 64, 3, 7) X(1, 128, 3, 6) X(2, 256, 3, 4) X(3, 64, 4, 5)
+// cfg 4: four chunks per tile (N1 = 512) want staging depth more than ring depth (experiment)
+#define BV_FOR_EACH_CHAIN(X) X(0, 64, 3, 7) X(1, 128, 3, 6) X(2, 256, 3, 4) X(3, 64, 4, 5) X(4, 128, 2, 8)
 
 struct ChainLaunch {
     bv::ChainParams p;
@@ -426,6 +427,7 @@ int build_chain(ChainLaunch* L, int B, const ConvOperand* ops, int nops, const v
     p.l2_prefetch = env_flag("BV_L2_PREFETCH") ? 1 : 0;
     L->n2 = N2;
     L->cfg = (N2 == 64) ? ((nops == 2 && !env_flag("BV_CHAIN_NO_DEEP")) ? 3 : 0) : (N2 == 128 ? 1 : 2);
+    if (N2 == 128 && N1 == 512 && env_flag("BV_CHAIN_L2_DEEPSTG")) L->cfg = 4;
     L->k1 = k1;
     L->grid = std::min(p.num_m_blocks, g_num_sms);
     return BV_OK;
