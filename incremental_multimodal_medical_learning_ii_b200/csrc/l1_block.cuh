@@ -39,12 +39,14 @@
 namespace bv {
 
 constexpr int kL1Threads = 24 * 32;
-constexpr int kL1Stages = 3;
+constexpr int kL1Stages = 2;      // A ring (a tile needs three stages: the third load waits for the first MMA group)
+constexpr int kL1YBufs = 5;       // y / identity staging sub-tiles: 4 per tile + 1, so that the identity rows of the next
+                                  // tile's sub-tile j only wait for THIS tile's sub-tile j-1 to drain
 constexpr int kL1DmaWarp = 18;
 constexpr int kL1StoreWarp = 19;
 constexpr int kL1E2Warp0 = 20;   // warps 20..23: epilogue of the second GEMM, one warp per TMEM lane quarter
 // shared-memory map (bytes)
-constexpr int kL1OffA = 0;                                 // 3 x 16 KB A ring
+constexpr int kL1OffA = 0;                                 // kL1Stages x 16 KB A ring
 constexpr int kL1OffW2 = kL1OffA + kL1Stages * kABytes;    // 3 filter rows x [96 rows x 128 B]
 constexpr int kL1OffW3 = kL1OffW2 + 3 * 96 * 128;          // [128 rows x 128 B]
 constexpr int kL1OffW1 = kL1OffW3 + 128 * 128;             // 4 k-blocks x [N2/2 rows x 128 B]
@@ -55,9 +57,9 @@ struct L1Cfg {
     static constexpr int kW1Bytes = 4 * (N2 / 2) * 128;
     static constexpr int kOffT2 = kL1OffW1 + kW1Bytes;
     static constexpr int kOffStg1 = kOffT2 + kABytes;          // 4 sub-tiles x 16 KB
-    static constexpr int kOffStg2 = kOffStg1 + 4 * kStagingBytes;
+    static constexpr int kOffStg2 = kOffStg1 + kL1YBufs * kStagingBytes;
     static constexpr int kOffBars = kOffStg2 + (N2 / 64) * kStagingBytes;
-    static constexpr int kNumBars = 2 * kL1Stages + 1 + 8 + 20 + 2;
+    static constexpr int kNumBars = 2 * kL1Stages + 1 + 8 + 24 + kL1YBufs + 2;
     static constexpr int kOffBias = (kOffBars + kNumBars * 8 + 16 + 15) / 16 * 16;               // fp32: bias3[256] | bias2[64] | bias1[N2]
     static constexpr int kSmemBytes = kOffBias + (256 + 64 + N2) * 4;
     static constexpr uint32_t kWeightBytes = 3 * 96 * 128 + 128 * 128 + kW1Bytes;
@@ -241,10 +243,12 @@ __global__ void __launch_bounds__(kL1Threads, 1) l1_block_kernel(const __grid_co
     uint64_t* d2_full = w_bar + 7;                // per CTA
     uint64_t* d2_empty = w_bar + 8;               // leader, 32
     uint64_t* sub_written = w_bar + 9;            // [4] leader, 32 (16 warps x 2 CTAs): y sub-tile j complete
-    uint64_t* sub_consumed = sub_written + 4;     // [4] per CTA (multicast commit after G2 k-block j)
-    uint64_t* store_done = sub_consumed + 4;      // [4] per CTA: the TMA stores of y sub-tile j have read smem
-    uint64_t* res_ready = store_done + 4;         // [4] per CTA: residual sub-tile j landed (TMA tx)
-    uint64_t* y_local = res_ready + 4;            // [4] per CTA, 16 warps: y sub-tile j written (for the storer)
+    // the loader waits on these one tile (five sub-tiles) behind the MMA / storer that complete them: two barrier sets,
+    // used by even and odd tiles, keep a waiter from ever being two phases behind the barrier (parity aliasing)
+    uint64_t* sub_consumed = sub_written + 4;     // [2][4] per CTA (multicast commit after G2 k-block j)
+    uint64_t* store_done = sub_consumed + 8;      // [2][4] per CTA: the TMA stores of y sub-tile j have read smem
+    uint64_t* res_ready = store_done + 8;         // [kL1YBufs] per CTA, per staging BUFFER: identity rows landed (TMA tx)
+    uint64_t* y_local = res_ready + kL1YBufs;            // [4] per CTA, 16 warps: y sub-tile j written (for the storer)
     uint64_t* e2_local = y_local + 4;             // per CTA, 16 warps: t1' tile written
     uint64_t* stg2_free = e2_local + 1;           // per CTA: the TMA stores of t1' have read smem
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + Cfg::kNumBars);
@@ -282,12 +286,14 @@ __global__ void __launch_bounds__(kL1Threads, 1) l1_block_kernel(const __grid_co
         mbar_init(d2_full, 1);
         mbar_init(d2_empty, 8);
         mbar_init(e2_local, 4);
+        for (int b = 0; b < kL1YBufs; ++b) mbar_init(&res_ready[b], 1);
         mbar_init(stg2_free, 1);
         for (int j = 0; j < 4; ++j) {
             mbar_init(&sub_written[j], 32);
             mbar_init(&sub_consumed[j], 1);
+            mbar_init(&sub_consumed[4 + j], 1);
             mbar_init(&store_done[j], 1);
-            mbar_init(&res_ready[j], 1);
+            mbar_init(&store_done[4 + j], 1);
             mbar_init(&y_local[j], 16);
         }
         fence_barrier_init();
@@ -431,13 +437,14 @@ __global__ void __launch_bounds__(kL1Threads, 1) l1_block_kernel(const __grid_co
                     trace(t, 3 + j);   // sub_written[j] seen
                     tc_fence_after();
                     if (elect_one()) {
-                        const uint64_t adesc = umma_desc_k_sw128(base + static_cast<uint32_t>(Cfg::kOffStg1 + j * kStagingBytes));
+                        const uint64_t adesc =
+                            umma_desc_k_sw128(base + static_cast<uint32_t>(Cfg::kOffStg1 + ((4 * t + j) % kL1YBufs) * kStagingBytes));
                         const uint64_t bdesc = umma_desc_k_sw128(base + static_cast<uint32_t>(kL1OffW1 + j * (N2 / 2) * 128));
 #pragma unroll
                         for (int k = 0; k < 4; ++k)
                             umma_bf16_ss_pair(tmem_base + kD2, adesc + static_cast<uint64_t>(2 * k),
                                               bdesc + static_cast<uint64_t>(2 * k), idesc2, (j != 0 || k != 0) ? 1u : 0u);
-                        umma_commit_pair(&sub_consumed[j]);
+                        umma_commit_pair(&sub_consumed[(t & 1) * 4 + j]);
                         if (j == 3) umma_commit_pair(d2_full);
                     }
                     __syncwarp();
@@ -476,14 +483,19 @@ __global__ void __launch_bounds__(kL1Threads, 1) l1_block_kernel(const __grid_co
                         for (int g = 0; g < 4; ++g) tma_prefetch_l2_3d(&p.tmRes, j * kChunkCols, nq[g], nl[g]);
                 }
                 for (int j = 0; j < 4; ++j) {
-                    if (t > 0) {  // the previous tile's sub-tile j has been read by the second GEMM and stored
-                        mbar_wait(&sub_consumed[j], (t - 1) & 1u);
-                        mbar_wait(&store_done[j], (t - 1) & 1u);
+                    // sub-tile g = 4t + j lives in buffer g % 5; its previous tenant was sub-tile g - 5 = (t - 1, j - 1)
+                    // (or (t - 2, 3) for j = 0): wait until the second GEMM has read it and its TMA store has drained
+                    const int g = 4 * t + j, gprev = g - kL1YBufs;
+                    if (gprev >= 0) {
+                        const int tp = gprev >> 2, jp = gprev & 3;
+                        mbar_wait(&sub_consumed[(tp & 1) * 4 + jp], (tp >> 1) & 1u);
+                        mbar_wait(&store_done[(tp & 1) * 4 + jp], (tp >> 1) & 1u);
                     }
-                    mbar_arrive_expect_tx(&res_ready[j], kStagingBytes);
+                    const int b = g % kL1YBufs;
+                    mbar_arrive_expect_tx(&res_ready[b], kStagingBytes);
 #pragma unroll
-                    for (int g = 0; g < 4; ++g)
-                        tma_load_3d(&p.tmRes, &res_ready[j], stg1 + j * kStagingBytes + g * 4096, j * kChunkCols, gq[g], gl[g],
+                    for (int q = 0; q < 4; ++q)
+                        tma_load_3d(&p.tmRes, &res_ready[b], stg1 + b * kStagingBytes + q * 4096, j * kChunkCols, gq[q], gl[q],
                                     kEvictFirst);
                 }
             }
@@ -498,18 +510,20 @@ __global__ void __launch_bounds__(kL1Threads, 1) l1_block_kernel(const __grid_co
                     mbar_wait(&y_local[j], t & 1u);
 #pragma unroll
                     for (int g = 0; g < 4; ++g)
-                        tma_store_3d(&p.tmOut1, stg1 + j * kStagingBytes + g * 4096, j * kChunkCols, gq[g], gl[g]);
+                        tma_store_3d(&p.tmOut1, stg1 + ((4 * t + j) % kL1YBufs) * kStagingBytes + g * 4096, j * kChunkCols, gq[g],
+                                     gl[g]);
                     tma_store_commit();
                 }
                 // bulk groups complete in order: allow the 3 - j most recent ones to be pending
+                uint64_t* sd = store_done + (t & 1) * 4;
                 tma_store_wait_read<3>();
-                mbar_arrive(&store_done[0]);
+                mbar_arrive(&sd[0]);
                 tma_store_wait_read<2>();
-                mbar_arrive(&store_done[1]);
+                mbar_arrive(&sd[1]);
                 tma_store_wait_read<1>();
-                mbar_arrive(&store_done[2]);
+                mbar_arrive(&sd[2]);
                 tma_store_wait_read<0>();
-                mbar_arrive(&store_done[3]);
+                mbar_arrive(&sd[3]);
                 mbar_wait(e2_local, t & 1u);
 #pragma unroll
                 for (int g = 0; g < 4; ++g) tma_store_3d(&p.tmOut2, stg2 + g * 4096, 0, gq[g], gl[g]);
@@ -636,10 +650,11 @@ __global__ void __launch_bounds__(kL1Threads, 1) l1_block_kernel(const __grid_co
             tc_fence_after();
 #pragma unroll 1
             for (int j = 0; j < 4; ++j) {
-                uint8_t* sub = stg1 + j * kStagingBytes;
+                const int yb = (4 * t + j) % kL1YBufs;
+                uint8_t* sub = stg1 + yb * kStagingBytes;
                 uint32_t v[16];
                 tmem_ld_32x16(lane_base + kD1 + static_cast<uint32_t>(j * kChunkCols + cg * 16), v);
-                mbar_wait(&res_ready[j], t & 1u);
+                mbar_wait(&res_ready[yb], ((4 * t + j) / kL1YBufs) & 1u);
                 if (j == 0) etrace(t, 11);   // res_ready seen
                 tmem_ld_wait();
                 if (j == 3) {
