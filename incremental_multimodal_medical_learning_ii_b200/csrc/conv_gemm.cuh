@@ -86,11 +86,15 @@ struct ConvGemmParams {
 // the L2->SM traffic, and those layers are L2-bandwidth-bound.
 constexpr int kMaxResidentKB = 9;
 
-template <int BN, int STAGES, int NBUF, bool BRES = false, bool WIDE = false>
+// MT = m-tiles (128 rows each) that share one B tile per ring stage.  MT = 2 halves the weight traffic per output row
+// and doubles the MMA work behind every stage (layer2's 3x3 convolutions sit between the L2->SM path and the TMA
+// latency with MT = 1: 576 KB of operand loads per 128x128 tile); it needs 2 x BN <= 256 TMEM columns per stage.
+template <int BN, int STAGES, int NBUF, bool BRES = false, bool WIDE = false, int MT = 1>
 struct ConvGemmCfg {
     static_assert(!WIDE || BRES, "the wide 3x3 mode keeps the weights resident");
+    static_assert(MT == 1 || (MT == 2 && BN == 128 && !BRES && !WIDE), "two m-tiles per stage: BN = 128, streamed weights only");
     static constexpr int kBBytes = BN * kBlockK * 2;
-    static constexpr int kAStage = WIDE ? kWideABytes : kABytes;
+    static constexpr int kAStage = WIDE ? kWideABytes : MT * kABytes;
     static constexpr int kStageBytes = kAStage + (BRES ? 0 : kBBytes);
     static constexpr int kResidentBytes = BRES ? kMaxResidentKB * kBBytes : 0;
     static constexpr int kStages = STAGES;
@@ -107,9 +111,9 @@ struct ConvGemmCfg {
     static_assert(kSmemBytes <= 232448, "exceeds the 227 KB of shared memory a CTA may use");
 };
 
-template <int BN, int STAGES, int NBUF, bool BRES = false, bool WIDE = false>
+template <int BN, int STAGES, int NBUF, bool BRES = false, bool WIDE = false, int MT = 1>
 __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
-    using Cfg = ConvGemmCfg<BN, STAGES, NBUF, BRES, WIDE>;
+    using Cfg = ConvGemmCfg<BN, STAGES, NBUF, BRES, WIDE, MT>;
     constexpr int kAStage = Cfg::kAStage;
     constexpr int kStages = Cfg::kStages;
     constexpr int kBufs = NBUF;
@@ -135,7 +139,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int num_tiles = p.num_m_blocks * p.num_n_blocks;
+    // a "tile" below is MT consecutive m-blocks x one n-block
+    const int num_tiles = ((p.num_m_blocks + MT - 1) / MT) * p.num_n_blocks;
     // ring stages consumed per tile (kSegWide: one per filter row and channel block) / resident weight k-blocks
     const int total_kb = WIDE ? 3 * p.seg[0].cblocks : p.seg[0].kblocks + (p.nseg > 1 ? p.seg[1].kblocks : 0);
     const int total_wkb = p.seg[0].kblocks + (p.nseg > 1 ? p.seg[1].kblocks : 0);
@@ -220,10 +225,15 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
                 }
                 continue;
             }
-            const int img = m0 / hw;
-            const int rem = m0 - img * hw;
-            const int op = rem / p.Wo;
-            const int oq = rem - op * p.Wo;
+            int img[MT], op[MT], oq[MT];
+#pragma unroll
+            for (int u = 0; u < MT; ++u) {
+                const int mu = (m_blk * MT + u) * kBlockM;
+                img[u] = mu / hw;
+                const int rem = mu - img[u] * hw;
+                op[u] = rem / p.Wo;
+                oq[u] = rem - op[u] * p.Wo;
+            }
             for (int s = 0; s < p.nseg; ++s) {
                 const ConvSeg sg = p.seg[s];
                 int tap = 0, cb = 0, kofs = 0, tr = 0, ts = 0;
@@ -233,13 +243,17 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
                     t_empty += clock64() - tw;
                     if (elect_one()) {
                         mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
-                        void* dst_a = smem_a + stage * kAStage;
-                        if (sg.mode == kSegTiled) {
-                            tma_load_2d(&p.tmA[s], &full_bar[stage], dst_a, cb * kBlockK, m0, kEvictNormal);
-                        } else {
-                            tma_load_im2col_4d(&p.tmA[s], &full_bar[stage], dst_a, cb * kBlockK,
-                                               sg.lower + oq * sg.stride, sg.lower + op * sg.stride, img,
-                                               static_cast<uint16_t>(ts), static_cast<uint16_t>(tr), kEvictNormal);
+#pragma unroll
+                        for (int u = 0; u < MT; ++u) {
+                            void* dst_a = smem_a + stage * kAStage + u * kABytes;
+                            if (sg.mode == kSegTiled) {
+                                tma_load_2d(&p.tmA[s], &full_bar[stage], dst_a, cb * kBlockK, (m_blk * MT + u) * kBlockM,
+                                            kEvictNormal);
+                            } else {
+                                tma_load_im2col_4d(&p.tmA[s], &full_bar[stage], dst_a, cb * kBlockK,
+                                                   sg.lower + oq[u] * sg.stride, sg.lower + op[u] * sg.stride, img[u],
+                                                   static_cast<uint16_t>(ts), static_cast<uint16_t>(tr), kEvictNormal);
+                            }
                         }
                         if constexpr (!BRES)
                             tma_load_2d(&p.tmB[s], &full_bar[stage], smem_b + stage * Cfg::kBBytes, kofs, n_blk * BN,
@@ -312,16 +326,20 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
                         if (kb == total_kb - 1) umma_commit(&tmem_full[acc]);
                     }
                 } else if (elect_one()) {
-                    const uint64_t adesc = umma_desc_k_sw128(a_base + static_cast<uint32_t>(stage * kAStage));
                     const uint64_t bdesc =
                         umma_desc_k_sw128(b_base + static_cast<uint32_t>((BRES ? kb : stage) * Cfg::kBBytes));
 #pragma unroll
-                    for (int k = 0; k < kBlockK / 16; ++k) {
-                        // K step ks = 4*kb + k goes to partial accumulator (ks & amask); its first visit overwrites.
-                        // +32 bytes per UMMA_K=16 step inside the 128-byte swizzle span (>>4 encoded => +2).
-                        umma_bf16_ss(d_tmem + static_cast<uint32_t>((k & amask) * BN),
-                                     adesc + static_cast<uint64_t>(2 * k), bdesc + static_cast<uint64_t>(2 * k), idesc,
-                                     (kb != 0 || k >= nacc) ? 1u : 0u);
+                    for (int u = 0; u < MT; ++u) {
+                        const uint64_t adesc = umma_desc_k_sw128(a_base + static_cast<uint32_t>(stage * kAStage + u * kABytes));
+#pragma unroll
+                        for (int k = 0; k < kBlockK / 16; ++k) {
+                            // K step ks = 4*kb + k goes to partial accumulator (ks & amask); its first visit overwrites.
+                            // +32 bytes per UMMA_K=16 step inside the 128-byte swizzle span (>>4 encoded => +2).
+                            // With MT = 2 (nacc == 1) m-tile u accumulates in columns [u * BN, (u + 1) * BN) of the stage.
+                            umma_bf16_ss(d_tmem + static_cast<uint32_t>((MT == 1 ? (k & amask) : u) * BN),
+                                         adesc + static_cast<uint64_t>(2 * k), bdesc + static_cast<uint64_t>(2 * k), idesc,
+                                         (kb != 0 || k >= nacc) ? 1u : 0u);
+                        }
                     }
                     umma_commit(&empty_bar[stage]);  // frees this smem stage once the MMAs have read it
                     if (kb == total_kb - 1) umma_commit(&tmem_full[acc]);  // accumulators complete -> epilogue
@@ -344,12 +362,12 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
             const bool has_res = p.residual != nullptr;
             const int my_tiles = (num_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) /
                                  static_cast<int>(gridDim.x);
-            const int total = my_tiles * kChunks;  // sub-tiles this CTA produces
+            const int total = my_tiles * MT * kChunks;  // sub-tiles this CTA produces
             auto coords = [&](int g, int& row0, int& col0) {
-                const int tile = static_cast<int>(blockIdx.x) + (g / kChunks) * static_cast<int>(gridDim.x);
+                const int tile = static_cast<int>(blockIdx.x) + (g / (MT * kChunks)) * static_cast<int>(gridDim.x);
                 const int m_blk = tile / p.num_n_blocks;
                 const int n_blk = tile - m_blk * p.num_n_blocks;
-                row0 = m_blk * kBlockM;
+                row0 = (m_blk * MT + (g / kChunks) % MT) * kBlockM;
                 col0 = n_blk * BN + (g % kChunks) * kChunkCols;
             };
             // every lane runs the loop; lane 0 (always the same lane: bulk async-groups are per thread) issues
@@ -402,13 +420,14 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
             const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
                                    static_cast<uint32_t>(acc * Cfg::kAccStageCols);
 #pragma unroll 1
-            for (int c = 0; c < kChunks; ++c, ++g) {
+            for (int cu = 0; cu < MT * kChunks; ++cu, ++g) {   // m-tile u of the stage, 64-column sub-tile c
+                const int u = cu / kChunks, c = cu - u * kChunks;
                 const int b = g % kBufs;
                 uint8_t* row_ptr = staging + b * kStagingBytes + r_in_tile * 128;
                 mbar_wait(&buf_ready[b], (g / kBufs) & 1u);
                 {
                     uint32_t v[32];
-                    tmem_ld_32x32(t_row + static_cast<uint32_t>(c * kChunkCols + half * 32), v);
+                    tmem_ld_32x32(t_row + static_cast<uint32_t>(u * BN + c * kChunkCols + half * 32), v);
                     tmem_ld_wait();
                     for (int a = 1; a < p.nacc; ++a) {  // add the other partial accumulators
                         uint32_t u[32];
@@ -479,7 +498,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
             const uint32_t acc_phase = (it >> 1) & 1u;
             mbar_wait(&tmem_full[acc], acc_phase);
             tc_fence_after();
-            int row = m_blk * kBlockM + quarter * 32 + lane;
+            for (int u = 0; u < MT; ++u) {
+            int row = (m_blk * MT + u) * kBlockM + quarter * 32 + lane;
             bool row_ok = row < p.M;
             if constexpr (WIDE) {
                 // widened row -> real output pixel; the two columns q' >= Wo of each image row are padding outputs
@@ -490,7 +510,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
             }
             const size_t row_off = static_cast<size_t>(row) * p.N + static_cast<size_t>(n_blk) * BN;
             const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
-                                   static_cast<uint32_t>(acc * Cfg::kAccStageCols);
+                                   static_cast<uint32_t>(acc * Cfg::kAccStageCols + u * (MT == 1 ? 0 : BN));
 #pragma unroll 1
             for (int c = (warp - 2) >> 2; c < BN / 32; c += 2) {
                 uint32_t v[32];
@@ -564,6 +584,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
                         }
                     }
                 }
+            }
             }
             tc_fence_before();
             __syncwarp();

@@ -213,3 +213,26 @@ def test_narrow_3x3_configurations(env, cfg, H, monkeypatch):
     out = _conv_native(lib, N, x, conv, relu=True, out_fp32=False)
     assert not torch.isnan(out.float()).any()
     assert torch.equal(out, ref), f"max abs diff {(out.float() - ref.float()).abs().max().item()}"
+
+
+@pytest.mark.parametrize("case", [(1, 15, 128, 128, 3, 1, 1), (3, 30, 128, 128, 3, 2, 1), (5, 60, 128, 128, 3, 1, 1),
+                                  (2, 15, 1024, 128, 1, 1, 0), (7, 30, 128, 128, 3, 1, 1)],
+                         ids=["one_block", "s2_ragged", "many_tiles", "1x1_longK", "odd_blocks"])
+def test_two_m_tiles_per_stage(env, case, monkeypatch):
+    """kCfg128M2: two 128-row m-tiles share every weight stage (MT = 2), against the single-tile configuration and
+    the fp32 reference; block counts that are odd exercise the half-empty last stage."""
+    N, lib, packing = env
+    B, H, cin, cout, k, stride, pad = case
+    gen = torch.Generator().manual_seed(B * 100 + H)
+    dev = torch.device("cuda:0")
+    x = torch.randint(-2, 3, (B, H, H, cin), generator=gen).float().to(torch.bfloat16).to(dev)
+    w = torch.randint(-1, 2, (cout, cin, k, k), generator=gen).float().to(torch.bfloat16)
+    b = torch.randint(-2, 3, (cout,), generator=gen).float()
+    conv = packing.pack_single_conv(w, b, stride, pad, dev)
+    ref = torch.relu(_ref(x, w.to(dev), b.to(dev), stride, pad)).to(torch.bfloat16)
+    monkeypatch.setenv("BV_FORCE_CFG", "8")
+    out = _conv_native(lib, N, x, conv, relu=True, out_fp32=False)
+    assert not torch.isnan(out.float()).any(), "unwritten rows"
+    assert torch.equal(out, ref), f"max abs diff {(out.float() - ref.float()).abs().max().item()}"
+    monkeypatch.setenv("BV_FORCE_CFG", "3")
+    assert torch.equal(_conv_native(lib, N, x, conv, relu=True, out_fp32=False), ref)
