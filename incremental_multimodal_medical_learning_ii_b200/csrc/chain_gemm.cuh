@@ -22,17 +22,21 @@
 // The MMA warp issues G1(q) BEFORE G2(q-1), so the tensor core always has the next chunk's first GEMM queued while
 // the epilogue converts the previous one.
 //
-// Warp roles (384 threads, 1 CTA / SM, persistent): 0 TMA producer, 1 MMA issuer (+TMEM alloc), 2..9 epilogue math,
-// 10 DMA for out1 (residual prefetch + stores), 11 DMA for out2.
+// Warp roles (640 threads, 1 CTA / SM, persistent): 0 TMA producer, 1 MMA issuer (+TMEM alloc), 2..17 epilogue math
+// (the epilogue is a chain of latencies - TMEM load, smem read-modify-write, barrier - so it is spread over 16 warps
+// of 16 columns each; with 8 warps the no-residual block was epilogue-bound), 18 DMA for out1 (residual prefetch +
+// stores), 19 DMA for out2.
 #pragma once
 #include "conv_gemm.cuh"
 
 namespace bv {
 
 constexpr int kChainBN1 = 128;                  // columns of N1 per chunk
-constexpr int kChainThreads = 384;
+constexpr int kChainEpiWarps = 16;              // four per TMEM lane quarter, 16 of a sub-tile's 64 columns each
+constexpr int kChainThreads = (2 + kChainEpiWarps + 2) * 32;
 constexpr int kChainStageBytes = 32 * 1024;     // [A 16 KB | B 16 KB]; a G2 stage holds only weights (N2 x 128 B)
-constexpr int kChainDma2Warp = 11;
+constexpr int kChainDma1Warp = 2 + kChainEpiWarps;
+constexpr int kChainDma2Warp = 3 + kChainEpiWarps;
 
 struct ChainParams {
     CUtensorMap tmA[2];   // GEMM1 A operands (segment 0: conv3 input, segment 1: downsample input)
@@ -63,14 +67,15 @@ struct ChainCfg {
     static_assert(kSmemBytes <= 232448, "exceeds the 227 KB of shared memory a CTA may use");
 };
 
-// bias + optional in-place residual + ReLU + bf16 pack of 32 accumulator columns into a swizzled staging row
-__device__ __forceinline__ void chain_convert_row(const uint32_t (&v)[32], const float* __restrict__ bias_a,
-                                                  const float* __restrict__ bias_b, bool has_res, uint8_t* row_ptr,
-                                                  int half, int r_in_tile) {
+// bias (+ second bias of the fused downsample) + optional in-place residual + ReLU + bf16 pack of
+// 16 accumulator columns (16-byte groups 2 cg and 2 cg + 1 of the 64-column sub-tile) of one row
+__device__ __forceinline__ void chain_convert_row16(const uint32_t (&v)[16], const float* __restrict__ bias_a,
+                                                    const float* __restrict__ bias_b, bool has_res, uint8_t* row_ptr,
+                                                    int cg, int r_in_tile) {
     const float4* bp = reinterpret_cast<const float4*>(bias_a);
     const float4* bp2 = reinterpret_cast<const float4*>(bias_b);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {  // 16-byte group = 8 channels
+    for (int j = 0; j < 2; ++j) {
         float f[8];
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
@@ -84,7 +89,7 @@ __device__ __forceinline__ void chain_convert_row(const uint32_t (&v)[32], const
             f[4 * q + 2] = __uint_as_float(v[8 * j + 4 * q + 2]) + bb.z;
             f[4 * q + 3] = __uint_as_float(v[8 * j + 4 * q + 3]) + bb.w;
         }
-        const int jj = half * 4 + j;  // 128B swizzle: 16-byte group jj of row r lives at position jj ^ (r & 7)
+        const int jj = cg * 2 + j;
         uint4* sp = reinterpret_cast<uint4*>(row_ptr + ((jj ^ (r_in_tile & 7)) << 4));
         if (has_res) {
             const uint4 rv = *sp;
@@ -103,6 +108,16 @@ __device__ __forceinline__ void chain_convert_row(const uint32_t (&v)[32], const
         }
         *sp = make_uint4(w[0], w[1], w[2], w[3]);
     }
+}
+
+__device__ __forceinline__ void chain_tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
 }
 
 template <int N2, int STAGES, int NB1>
@@ -155,18 +170,18 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_gemm_kernel(const __gr
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&d1_full[i], 1);
-            mbar_init(&d1_empty[i], kEpiWarps);
+            mbar_init(&d1_empty[i], kChainEpiWarps);
             mbar_init(&d2_full[i], 1);
-            mbar_init(&d2_empty[i], kEpiWarps);
+            mbar_init(&d2_empty[i], kChainEpiWarps);
         }
         for (int i = 0; i < NB1; ++i) {
             mbar_init(&buf_ready[i], 1);
-            mbar_init(&buf_written[i], kEpiWarps);
+            mbar_init(&buf_written[i], kChainEpiWarps);
             mbar_init(&buf_consumed[i], 1);
         }
         for (int i = 0; i < kNB2; ++i) {
             mbar_init(&buf2_ready[i], 1);
-            mbar_init(&buf2_written[i], kEpiWarps);
+            mbar_init(&buf2_written[i], kChainEpiWarps);
         }
         fence_barrier_init();
     }
@@ -335,7 +350,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_gemm_kernel(const __gr
             if (q >= 1) g2(q - 1);
         }
         g2(Q - 1);
-    } else if (warp == kDmaWarp) {
+    } else if (warp == kChainDma1Warp) {
         // ===================== DMA 1: residual prefetch + out1 stores =====================
         if (lane == 0) {
             const int total = 2 * Q;  // staging sub-tiles
@@ -409,9 +424,9 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_gemm_kernel(const __gr
             tma_store_wait_all<0>();
         }
     } else {
-        // ===================== epilogue math (warps 2..9) =====================
+        // ===================== epilogue math (warps 2..17) =====================
         const int quarter = warp & 3;
-        const int half = (warp - 2) >> 2;
+        const int cg = (warp - 2) >> 2;      // 16-column group of every 64-column sub-tile
         const int r_in_tile = quarter * 32 + lane;
         const bool has_res = p.has_res != 0;
         const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
@@ -424,12 +439,12 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_gemm_kernel(const __gr
             tc_fence_after();
 #pragma unroll 1
             for (int sub = 0; sub < kNB2; ++sub) {
-                uint32_t v[32];
-                tmem_ld_32x32(lane_base + 256u + static_cast<uint32_t>(acc2 * 128 + sub * kChunkCols + half * 32), v);
+                uint32_t v[16];
+                chain_tmem_ld_32x16(lane_base + 256u + static_cast<uint32_t>(acc2 * 128 + sub * kChunkCols + cg * 16), v);
                 mbar_wait(&buf2_ready[sub], it & 1u);
                 tmem_ld_wait();
-                chain_convert_row(v, p.bias2 + sub * kChunkCols + half * 32, nullptr, false,
-                                  stg2 + sub * kStagingBytes + r_in_tile * 128, half, r_in_tile);
+                chain_convert_row16(v, p.bias2 + sub * kChunkCols + cg * 16, nullptr, false,
+                                    stg2 + sub * kStagingBytes + r_in_tile * 128, cg, r_in_tile);
                 fence_proxy_async_smem();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&buf2_written[sub]);
@@ -447,13 +462,13 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_gemm_kernel(const __gr
             for (int sub = 0; sub < 2; ++sub) {
                 const int g = 2 * q + sub;
                 const int b = g % NB1;
-                uint32_t v[32];
-                tmem_ld_32x32(lane_base + static_cast<uint32_t>(d * kChainBN1 + sub * kChunkCols + half * 32), v);
+                uint32_t v[16];
+                chain_tmem_ld_32x16(lane_base + static_cast<uint32_t>(d * kChainBN1 + sub * kChunkCols + cg * 16), v);
                 mbar_wait(&buf_ready[b], (g / NB1) & 1u);
                 tmem_ld_wait();
-                const int col = c * kChainBN1 + sub * kChunkCols + half * 32;
-                chain_convert_row(v, p.bias1[0] + col, (p.nseg > 1) ? p.bias1[1] + col : nullptr, has_res,
-                                  stg1 + b * kStagingBytes + r_in_tile * 128, half, r_in_tile);
+                const int col = c * kChainBN1 + sub * kChunkCols + cg * 16;
+                chain_convert_row16(v, p.bias1[0] + col, (p.nseg > 1) ? p.bias1[1] + col : nullptr, has_res,
+                                    stg1 + b * kStagingBytes + r_in_tile * 128, cg, r_in_tile);
                 fence_proxy_async_smem();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&buf_written[b]);
