@@ -133,9 +133,9 @@ struct ConvOperand {
 enum ConvCfg { kCfg256Deep = 0, kCfg256Res, kCfg128Res, kCfg128Deep, kCfg64, kCfg64BRes, kCfg64Wide, kCfg64Tap3, kCfg128M2, kNumCfg };
 // kCfg64Tap3 is a different kernel (conv3x3_tap3.cuh): the three horizontal taps of a filter row in one N = 192 MMA
 #define BV_FOR_EACH_CFG(X)                                                                                        \
-    X(kCfg256Deep, 256, 4, 2, false, false, 1) X(kCfg256Res, 256, 3, 5, false, false, 1)                                \
-    X(kCfg128Res, 128, 3, 7, false, false, 1) X(kCfg128Deep, 128, 6, 2, false, false, 1) X(kCfg64, 64, 8, 2, false, false, 1) \
-    X(kCfg64BRes, 64, 6, 2, true, false, 1) X(kCfg64Wide, 64, 6, 2, true, true, 1) X(kCfg128M2, 128, 4, 2, false, false, 2)
+    X(kCfg256Deep, 256, 4, 2, false, false, 1, 8) X(kCfg256Res, 256, 3, 5, false, false, 1, 16)                               \
+    X(kCfg128Res, 128, 3, 7, false, false, 1, 16) X(kCfg128Deep, 128, 6, 2, false, false, 1, 16) X(kCfg64, 64, 8, 2, false, false, 1, 16) \
+    X(kCfg64BRes, 64, 6, 2, true, false, 1, 16) X(kCfg64Wide, 64, 6, 2, true, true, 1, 16) X(kCfg128M2, 128, 4, 2, false, false, 2, 16)
 const int kCfgBN[kNumCfg] = {256, 256, 128, 128, 64, 64, 64, 64, 128};
 const int kCfgMT[kNumCfg] = {1, 1, 1, 1, 1, 1, 1, 1, 2};
 
@@ -193,10 +193,10 @@ int device_setup() {
     int rc = resolve_driver();
     if (rc) return rc;
     if (!g_attr_set) {
-#define BV_SET_ATTR(id, BN, ST, NB, BR, WD, MT)                                                     \
-    BV_CUDA(cudaFuncSetAttribute(bv::conv_gemm_kernel<BN, ST, NB, BR, WD, MT>,                      \
+#define BV_SET_ATTR(id, BN, ST, NB, BR, WD, MT, EP)                                                 \
+    BV_CUDA(cudaFuncSetAttribute(bv::conv_gemm_kernel<BN, ST, NB, BR, WD, MT, EP>,                  \
                                  cudaFuncAttributeMaxDynamicSharedMemorySize,                       \
-                                 bv::ConvGemmCfg<BN, ST, NB, BR, WD, MT>::kSmemBytes));
+                                 bv::ConvGemmCfg<BN, ST, NB, BR, WD, MT, EP>::kSmemBytes));
         BV_FOR_EACH_CFG(BV_SET_ATTR)
 #undef BV_SET_ATTR
 #define BV_SET_CHAIN_ATTR(id, N2, ST, NB)                                                              \
@@ -336,10 +336,11 @@ int launch_conv(const ConvLaunch& L0, cudaStream_t st) {
         L.p.dbg = g_dbg;
     }
     switch (L.cfg) {
-#define BV_LAUNCH(id, BN, ST, NB, BR, WD, MT)                                                             \
+#define BV_LAUNCH(id, BN, ST, NB, BR, WD, MT, EP)                                                         \
     case id:                                                                                              \
-        bv::conv_gemm_kernel<BN, ST, NB, BR, WD, MT>                                                      \
-            <<<L.grid, bv::kGemmThreads, bv::ConvGemmCfg<BN, ST, NB, BR, WD, MT>::kSmemBytes, st>>>(L.p); \
+        bv::conv_gemm_kernel<BN, ST, NB, BR, WD, MT, EP>                                                  \
+            <<<L.grid, bv::ConvGemmCfg<BN, ST, NB, BR, WD, MT, EP>::kThreads,                             \
+               bv::ConvGemmCfg<BN, ST, NB, BR, WD, MT, EP>::kSmemBytes, st>>>(L.p);                       \
         break;
         BV_FOR_EACH_CFG(BV_LAUNCH)
 #undef BV_LAUNCH

@@ -25,10 +25,11 @@
 // Warp roles (352 threads, 1 CTA / SM, persistent over tiles):
 //   warp 0     : TMA producer (one elected lane)           smem ring  full[]/empty[]
 //   warp 1     : TMEM allocator + tcgen05.mma issuer        TMEM ring  tmem_full[]/tmem_empty[] (2 accumulators)
-//   warps 2..9 : epilogue math: TMEM -> registers -> bias/residual/ReLU -> bf16, IN PLACE in a 128B-swizzled
+//   warps 2..17: epilogue math: TMEM -> registers -> bias/residual/ReLU -> bf16, IN PLACE in a 128B-swizzled
 //                staging tile of 128 rows x 64 channels (the residual was TMA-loaded into that same tile);
-//                two warps per TMEM lane quarter, each taking 32 of the 64 channels of a sub-tile
-//   warp 10    : epilogue DMA (one lane): TMA-loads the residual sub-tile ahead of the math warps and TMA-stores
+//                four warps per TMEM lane quarter, each taking 16 of the 64 channels of a sub-tile (the epilogue is
+//                a chain of latencies, so it is spread over many warps)
+//   warp 18    : epilogue DMA (one lane): TMA-loads the residual sub-tile ahead of the math warps and TMA-stores
 //                finished sub-tiles, so global traffic of the epilogue is full 128-byte rows, never per-thread rows
 // (fp32 output, used only by the tiny projector conv, keeps a direct per-thread store path.)
 #pragma once
@@ -38,9 +39,9 @@ namespace bv {
 
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;  // 64 bf16 = one 128-byte swizzle span
-constexpr int kGemmThreads = 352;
-constexpr int kDmaWarp = 10;
-constexpr int kEpiWarps = 8;
+constexpr int kMaxEpiWarps = 16;                     // epilogue warps are a per-configuration choice: 8 or 16
+constexpr int kGemmMaxThreads = (3 + kMaxEpiWarps) * 32;
+constexpr int gemm_threads(int epi_warps) { return (3 + epi_warps) * 32; }
 constexpr int kChunkCols = 64;                       // bf16 columns per staging sub-tile (128 bytes per row)
 constexpr int kStagingBytes = kBlockM * kChunkCols * 2;  // 16 KB
 constexpr int kABytes = kBlockM * kBlockK * 2;
@@ -89,8 +90,14 @@ constexpr int kMaxResidentKB = 9;
 // MT = m-tiles (128 rows each) that share one B tile per ring stage.  MT = 2 halves the weight traffic per output row
 // and doubles the MMA work behind every stage (layer2's 3x3 convolutions sit between the L2->SM path and the TMA
 // latency with MT = 1: 576 KB of operand loads per 128x128 tile); it needs 2 x BN <= 256 TMEM columns per stage.
-template <int BN, int STAGES, int NBUF, bool BRES = false, bool WIDE = false, int MT = 1>
+// EPI = epilogue warps (8: two per TMEM lane quarter, 32 columns of a sub-tile each; 16: four per quarter, 16 columns each).
+// The epilogue is a chain of latencies, so memory-bound configurations gain from 16 warps (layer2/3 conv3 + identity:
+// -5..-11 %); the compute-bound 256-wide long-K configuration loses 3-9 % to the extra resident threads and keeps 8.
+template <int BN, int STAGES, int NBUF, bool BRES = false, bool WIDE = false, int MT = 1, int EPI = 16>
 struct ConvGemmCfg {
+    static_assert(EPI == 8 || EPI == 16, "epilogue warps");
+    static constexpr int kEpiWarps = EPI;
+    static constexpr int kThreads = gemm_threads(EPI);
     static_assert(!WIDE || BRES, "the wide 3x3 mode keeps the weights resident");
     static_assert(MT == 1 || (MT == 2 && BN == 128 && !BRES && !WIDE), "two m-tiles per stage: BN = 128, streamed weights only");
     static constexpr int kBBytes = BN * kBlockK * 2;
@@ -111,9 +118,22 @@ struct ConvGemmCfg {
     static_assert(kSmemBytes <= 232448, "exceeds the 227 KB of shared memory a CTA may use");
 };
 
-template <int BN, int STAGES, int NBUF, bool BRES = false, bool WIDE = false, int MT = 1>
-__global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
-    using Cfg = ConvGemmCfg<BN, STAGES, NBUF, BRES, WIDE, MT>;
+__device__ __forceinline__ void tmem_ld_32x16b(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
+
+template <int BN, int STAGES, int NBUF, bool BRES = false, bool WIDE = false, int MT = 1, int EPI = 16>
+__global__ void __launch_bounds__(gemm_threads(EPI), 1) conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
+    using Cfg = ConvGemmCfg<BN, STAGES, NBUF, BRES, WIDE, MT, EPI>;
+    constexpr int kEpiWarps = EPI;
+    constexpr int kDmaWarp = 2 + EPI;
+    constexpr int kWarpCols = kChunkCols / (EPI / 4);   // columns of a 64-column sub-tile per epilogue warp
     constexpr int kAStage = Cfg::kAStage;
     constexpr int kStages = Cfg::kStages;
     constexpr int kBufs = NBUF;
@@ -403,9 +423,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
             }
         }
     } else if (!p.out_fp32 && !WIDE) {
-        // ===================== epilogue math (warps 2..9), staged bf16 output =====================
+        // ===================== epilogue math (warps 2..17), staged bf16 output =====================
         const int quarter = warp & 3;        // TMEM lane quarter this warp may access
-        const int half = (warp - 2) >> 2;    // which 32 of the sub-tile's 64 channels this warp converts
+        const int cg = (warp - 2) >> 2;      // which kWarpCols of the sub-tile's 64 channels this warp converts
         const int r_in_tile = quarter * 32 + lane;
         const bool has_res = p.residual != nullptr;
         int it = 0;
@@ -426,21 +446,23 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
                 uint8_t* row_ptr = staging + b * kStagingBytes + r_in_tile * 128;
                 mbar_wait(&buf_ready[b], (g / kBufs) & 1u);
                 {
-                    uint32_t v[32];
-                    tmem_ld_32x32(t_row + static_cast<uint32_t>(u * BN + c * kChunkCols + half * 32), v);
+                    uint32_t v[kWarpCols];
+                    if constexpr (kWarpCols == 32) tmem_ld_32x32(t_row + static_cast<uint32_t>(u * BN + c * kChunkCols + cg * kWarpCols), v);
+                    else tmem_ld_32x16b(t_row + static_cast<uint32_t>(u * BN + c * kChunkCols + cg * kWarpCols), v);
                     tmem_ld_wait();
                     for (int a = 1; a < p.nacc; ++a) {  // add the other partial accumulators
-                        uint32_t u[32];
-                        tmem_ld_32x32(t_row + static_cast<uint32_t>(a * BN + c * kChunkCols + half * 32), u);
+                        uint32_t w2[kWarpCols];
+                        if constexpr (kWarpCols == 32) tmem_ld_32x32(t_row + static_cast<uint32_t>(a * BN + c * kChunkCols + cg * kWarpCols), w2);
+                        else tmem_ld_32x16b(t_row + static_cast<uint32_t>(a * BN + c * kChunkCols + cg * kWarpCols), w2);
                         tmem_ld_wait();
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(u[j]));
+                        for (int j = 0; j < kWarpCols; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(w2[j]));
                     }
-                    const int col = n_blk * BN + c * kChunkCols + half * 32;
+                    const int col = n_blk * BN + c * kChunkCols + cg * kWarpCols;
                     const float4* bp = reinterpret_cast<const float4*>(p.bias[0] + col);
                     const float4* bp2 = (p.nseg > 1) ? reinterpret_cast<const float4*>(p.bias[1] + col) : nullptr;
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {  // 16-byte group = 8 channels
+                    for (int j = 0; j < kWarpCols / 8; ++j) {  // 16-byte group = 8 channels
                         float f[8];
 #pragma unroll
                         for (int q = 0; q < 2; ++q) {
@@ -455,7 +477,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
                             f[4 * q + 3] = __uint_as_float(v[8 * j + 4 * q + 3]) + bb.w;
                         }
                         // 128B swizzle: 16-byte group jj of row r lives at group position jj ^ (r & 7)
-                        const int jj = half * 4 + j;
+                        const int jj = cg * (kWarpCols / 8) + j;
                         uint4* sp = reinterpret_cast<uint4*>(row_ptr + ((jj ^ (r_in_tile & 7)) << 4));
                         if (has_res) {
                             const uint4 rv = *sp;
@@ -488,7 +510,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
             if (lane == 0) mbar_arrive(&tmem_empty[acc]);
         }
     } else {
-        // ===================== epilogue, direct fp32 stores: warp pair splits the BN/32 column chunks =====
+        // ===================== epilogue, direct fp32 stores: the warps of a lane quarter split the BN/32 column chunks =====
         const int quarter = warp & 3;  // TMEM lane quarter this warp may access
         int it = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
@@ -512,7 +534,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
             const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
                                    static_cast<uint32_t>(acc * Cfg::kAccStageCols + u * (MT == 1 ? 0 : BN));
 #pragma unroll 1
-            for (int c = (warp - 2) >> 2; c < BN / 32; c += 2) {
+            for (int c = (warp - 2) >> 2; c < BN / 32; c += kEpiWarps / 4) {
                 uint32_t v[32];
                 tmem_ld_32x32(t_row + static_cast<uint32_t>(c * 32), v);
                 for (int a = 1; a < p.nacc; ++a) {
