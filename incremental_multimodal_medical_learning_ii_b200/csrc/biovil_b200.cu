@@ -862,7 +862,8 @@ static int build_plan(bv_handle* h, const void* frames, int dtype, int B, int C,
             // Measured losses stay unchained: the strided-downsample tail of layer2.0 (six A k-blocks re-streamed per
             // chunk) and the 256-wide second GEMM into layer3 (its staging leaves too little residual prefetch depth).
             const bool chain_l3 = env_flag("BV_CHAIN_L3") && c3.cout == 1024 && n3 == 1;
-            const bool chain_pays = env_flag("BV_CHAIN_ALL") || chain_l3 ||
+            const bool chain_256 = env_flag("BV_CHAIN_256") && n3 == 1 && c3.cout == 512;   // layer2 -> layer3 transition
+            const bool chain_pays = env_flag("BV_CHAIN_ALL") || chain_l3 || chain_256 ||
                                     (!(n3 == 2 && ds.cin * ds.r * ds.s > 64) && h->w.conv1[blk + 1 < BV_NUM_BLOCKS ? blk + 1 : blk].cout <= 128);
             if (use_chain && chain_pays && blk + 1 < BV_NUM_BLOCKS && chain_supported(o3, n3, h->w.conv1[blk + 1])) {
                 PlanStep s;
