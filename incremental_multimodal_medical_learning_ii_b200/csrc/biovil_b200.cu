@@ -477,6 +477,29 @@ int build_l1_block(L1Launch* L, int B, int H, int W, const void* t1, const bv_co
     return BV_OK;
 }
 
+// Can the device co-schedule CTA pairs of the fused layer1 kernel at all (cluster launch, 224 KB of smem per CTA)?
+// Queried once; when it cannot (MIG slice, odd SM count per TPC) the plan keeps the two-kernel path for that block.
+bool l1_block_launchable() {
+    static int cached = -1;
+    if (cached >= 0) return cached == 1;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(2, 1, 1);
+    cfg.blockDim = dim3(bv::kL1Threads, 1, 1);
+    cfg.dynamicSmemBytes = bv::L1Cfg<64>::kSmemBytes;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    int clusters = 0;
+    const cudaError_t e = cudaOccupancyMaxActiveClusters(&clusters, bv::l1_block_kernel<64>, &cfg);
+    if (e != cudaSuccess) cudaGetLastError();
+    cached = (e == cudaSuccess && clusters >= 1) ? 1 : 0;
+    return cached == 1;
+}
+
 int launch_l1_block(const L1Launch& L, cudaStream_t st) {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(L.grid, 1, 1);
@@ -830,7 +853,7 @@ static int build_plan(bv_handle* h, const void* frames, int dtype, int B, int C,
             }
             // layer1 blocks with an identity residual whose successor's conv1 is 64 wide: the whole tail of the block
             // (conv2 3x3, conv3 + identity, next conv1) is one CTA-pair kernel
-            if (!env_flag("BV_NO_L1_FUSED") && ds.w == nullptr && blk + 1 < BV_NUM_BLOCKS &&
+            if (!env_flag("BV_NO_L1_FUSED") && l1_block_launchable() && ds.w == nullptr && blk + 1 < BV_NUM_BLOCKS &&
                 l1_block_supported(c2, c3, h->w.conv1[blk + 1], cw)) {
                 PlanStep s;
                 s.l1 = true;
