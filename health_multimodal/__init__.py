@@ -1,7 +1,6 @@
 """Drop-in alias: ``health_multimodal.image`` resolves to the B200-native implementation, so the reference's scripts
 (``chexpert-get-embedding.py:7``, ``test_first_emb.py:14``, ``trash/lower_bound_mcs.py:13``: ``from
-health_multimodal.image import get_biovil_resnet``) run unchanged with this repository on ``PYTHONPATH``.  Only the image
-side is provided: the text encoder (CXR-BERT) is outside the hot path and is consumed through its ``[P,128]`` outputs."""
+health_multimodal.image import get_biovil_resnet``) run unchanged with this repository on ``PYTHONPATH``.  The image side and the image/text similarity arithmetic (``health_multimodal.vlp``) are provided: the text encoder (CXR-BERT) is outside the hot path and is consumed through its ``[P,128]`` outputs."""
 import importlib
 import sys
 
@@ -13,3 +12,7 @@ _SUBMODULES = ("", ".model", ".model.model", ".model.resnet", ".model.modules", 
 for _sub in _SUBMODULES:
     sys.modules[f"{__name__}.image{_sub}"] = importlib.import_module(_IMPL + _sub)
 image = sys.modules[f"{__name__}.image"]
+# joint image/text inference (reference health_multimodal/vlp): the image half + similarity arithmetic
+for _sub in ("", ".inference_engine"):
+    sys.modules[f"{__name__}.vlp{_sub}"] = importlib.import_module("incremental_multimodal_medical_learning_ii_b200.vlp" + _sub)
+vlp = sys.modules[f"{__name__}.vlp"]

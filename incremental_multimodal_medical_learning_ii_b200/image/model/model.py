@@ -300,7 +300,7 @@ class ImageModel(nn.Module):
         return self._run(frames, score=True, heat=heat, patch=patch, normalize_patch=True)
 
     @torch.no_grad()
-    def smooth_heatmaps(self, heat: torch.Tensor, sigma: float = 1.5) -> torch.Tensor:
+    def smooth_heatmaps(self, heat: torch.Tensor, sigma: float = 1.5) -> torch.Tensor:  # `self` is not used
         """Gaussian smoothing of ``[B,H',W',L]`` similarity maps on the GPU with the semantics of
         ``ndimage.gaussian_filter(map, sigma=(sigma, sigma), order=0)`` (vlp/inference_engine.py:107-109)."""
         if heat.dim() != 4 or not heat.is_cuda:

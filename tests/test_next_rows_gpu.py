@@ -82,3 +82,62 @@ def test_extract_to_store_end_to_end(tmp_path):
     resized = torch.from_numpy(np.stack([R.resize_center_crop(f.numpy(), 128, 96) for f in raw])).unsqueeze(1)
     direct = model(resized.cuda()).projected_global_embedding.cpu()
     assert torch.equal(flat.tensors[0], direct)            # same kernels on the same bytes: identical embeddings
+
+
+class _FakeTextEngine:
+    """Stands in for the reference's TextInferenceEngine (CXR-BERT is outside this repository): fixed embeddings."""
+
+    class _M:
+        training = False
+
+    model = _M()
+
+    def __init__(self, table):
+        self.table = table
+
+    def get_embeddings_from_prompt(self, prompts, normalize=True):
+        prompts = [prompts] if isinstance(prompts, str) else prompts
+        e = torch.stack([self.table[p] for p in prompts])
+        return torch.nn.functional.normalize(e, dim=1) if normalize else e
+
+
+def test_image_text_inference_engine_vs_oracle(tmp_path):
+    """health_multimodal/vlp/inference_engine.py:31-111 end to end on an image file: similarity score and smoothed,
+    resized similarity map against the oracle encoder + scipy + the reference's resize/pad arithmetic."""
+    import numpy as np
+    from PIL import Image
+    import weights as Wt
+    from incremental_multimodal_medical_learning_ii_b200.image import ImageInferenceEngine, get_biovil_resnet
+    from incremental_multimodal_medical_learning_ii_b200.image.data.transforms import create_chest_xray_transform_for_inference
+    from incremental_multimodal_medical_learning_ii_b200.vlp import ImageTextInferenceEngine
+    sd = Wt.make_state_dict(27, randomize_bn=True)
+    model = get_biovil_resnet(None)
+    model.load_state_dict(sd)
+    model.eval().to("cuda:0")
+    rng = np.random.default_rng(3)
+    base = rng.integers(0, 256, size=(20, 24)).astype(np.float32)
+    img = np.clip(np.kron(base, np.ones((10, 10), np.float32)) + rng.integers(0, 40, size=(200, 240)), 0, 255).astype(np.uint8)
+    path = tmp_path / "cxr.png"
+    Image.fromarray(img, mode="L").save(path)
+    transform = create_chest_xray_transform_for_inference(resize=128, center_crop_size=96)
+    engine = ImageTextInferenceEngine(ImageInferenceEngine(model, transform),
+                                      _FakeTextEngine({"effusion": torch.randn(128, generator=torch.Generator().manual_seed(1)),
+                                                       "no effusion": torch.randn(128, generator=torch.Generator().manual_seed(2))}))
+    x = transform(Image.open(path).convert("L")).unsqueeze(0)                       # [1,3,96,96] fp32, the reference input
+    ref_g = O.normalized_global_embedding(sd, x)[0]
+    t = engine.text_inference_engine.get_embeddings_from_prompt(["effusion", "no effusion"], normalize=False).mean(dim=0)
+    ref_score = float(ref_g @ torch.nn.functional.normalize(t, dim=0))
+    got = engine.get_similarity_score_from_raw_data(path, ["effusion", "no effusion"])
+    assert abs(got - ref_score) <= 2e-3
+
+    ref_patch = O.patchwise_projected_embeddings(sd, x, normalize=True)[0]          # [3,3,128]
+    te = engine.text_inference_engine.get_embeddings_from_prompt("effusion")
+    ref_map = O.gaussian_smooth_map((ref_patch.reshape(-1, 128) @ te.t()).reshape(1, 3, 3), 1.5)[0]
+    ref_full = ImageTextInferenceEngine.convert_similarity_to_image_size(ref_map, width=240, height=200, resize_size=128,
+                                                                         crop_size=96)
+    got_full = engine.get_similarity_map_from_raw_data(path, "effusion")
+    assert got_full.shape == (200, 240)
+    assert np.array_equal(np.isnan(got_full), np.isnan(ref_full))
+    assert np.nanmax(np.abs(got_full - ref_full)) <= 5e-3                           # bf16 trunk vs fp32 oracle (patch level)
+    maps = engine.get_similarity_maps_from_tensor((x[:, :1] * 255).round().to(torch.uint8).cuda(), te, sigma=1.5)
+    assert maps.shape == (1, 3, 3, 1) and float((maps[0, :, :, 0].cpu() - ref_map).abs().max()) <= 5e-3
