@@ -2,9 +2,15 @@
 (``chexpert-get-embedding.py:7``, ``test_first_emb.py:14``, ``trash/lower_bound_mcs.py:13``: ``from
 health_multimodal.image import get_biovil_resnet``) run unchanged with this repository on ``PYTHONPATH``.  The image side and the image/text similarity arithmetic (``health_multimodal.vlp``) are provided: the text encoder (CXR-BERT) is outside the hot path and is consumed through its ``[P,128]`` outputs."""
 import importlib
+import pkgutil
 import sys
 
 __version__ = "0.1.3+b200"
+
+# Everything that is NOT replaced here (``health_multimodal.text`` with CXR-BERT, ``health_multimodal.common``) keeps
+# coming from the reference checkout further down ``sys.path``: its ``health_multimodal`` directory is appended to this
+# package's search path, while ``.image`` and ``.vlp`` are pinned to the B200 implementation in ``sys.modules`` below.
+__path__ = pkgutil.extend_path(__path__, __name__)
 
 _IMPL = "incremental_multimodal_medical_learning_ii_b200.image"
 _SUBMODULES = ("", ".model", ".model.model", ".model.resnet", ".model.modules", ".inference_engine", ".utils",

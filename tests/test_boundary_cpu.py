@@ -121,3 +121,26 @@ def test_bn_fold_and_stem_packing_match_conv_bn():
     full = F.conv2d((k / 255).repeat(1, 3, 1, 1), w, b, stride=2, padding=3)
     folded = F.conv2d(k, w.sum(1, keepdim=True) / 255, b, stride=2, padding=3)
     assert torch.allclose(full, folded, atol=1e-10)
+
+
+def test_alias_package_leaves_the_reference_text_side_reachable():
+    """The reference's scripts import ``health_multimodal.text`` next to ``health_multimodal.image``
+    (Trainer.py, ZERO_JOINT_BOUNDS.py ...).  With this repository ahead of the reference on sys.path the image side must
+    be ours and the text side must still resolve to the reference's package (skipped where no checkout is present)."""
+    import importlib
+    import os
+    import subprocess
+    import sys
+    ref = "/root/reference"
+    if not os.path.isdir(os.path.join(ref, "health_multimodal", "text")):
+        pytest.skip("no reference checkout on this machine")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = ("import health_multimodal, health_multimodal.image as i, importlib.util as u; "
+            "s = u.find_spec('health_multimodal.text'); "
+            "print(i.__name__); print(s.origin if s else None)")
+    env = dict(os.environ, PYTHONPATH=os.pathsep.join([root, ref]))
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = out.stdout.strip().splitlines()
+    assert lines[0] == "incremental_multimodal_medical_learning_ii_b200.image"
+    assert lines[1].startswith(os.path.join(ref, "health_multimodal", "text"))
