@@ -172,6 +172,13 @@ int32_t bv_l1_block_nhwc(const void* t1, int32_t batch, int32_t height, int32_t 
  *   out[M,N] (fp32) = a[M,K] (bf16) x w[N,K]^T (bf16);  N multiple of 32 in [32,256], K multiple of 64. */
 int32_t bv_pair_gemm_test(const void* a, const void* w, int32_t m, int32_t n, int32_t k, float* out, bv_stream stream);
 
+/* The stem alone on 8-bit frames (conv1 7x7/2 -> bn1 -> relu -> maxpool, health_multimodal/image/model/resnet.py:34-37):
+ *   frames u8 [B][H][W] (H, W multiples of 32), w8 = bv_weights.stem_u8_k8, out bf16 NHWC [B][H/4][W/4][64].
+ *   variant 0 = row-streaming kernel (csrc/stem_rows.cuh, what bv_forward uses), 1 = tile kernel (csrc/stem_fused.cuh).
+ * Kernel-level parity tests call this; bv_forward runs the same launches. */
+int32_t bv_stem_u8_nhwc(const void* frames, int32_t batch, int32_t height, int32_t width, const bv_conv* host_w8,
+                        void* out, int32_t variant, bv_stream stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -24,6 +24,7 @@
 #include "pair_gemm.cuh"
 #include "resize.cuh"
 #include "stem_fused.cuh"
+#include "stem_rows.cuh"
 
 namespace {
 
@@ -212,6 +213,8 @@ int device_setup() {
         BV_CUDA(cudaFuncSetAttribute(bv::head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
         BV_CUDA(cudaFuncSetAttribute(bv::stem_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      bv::kStemSmemRequest));
+        BV_CUDA(cudaFuncSetAttribute(bv::stem_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     bv::kSrSmemBytes));
         g_attr_set = true;
     }
     g_num_sms = prop.multiProcessorCount;
@@ -633,6 +636,8 @@ struct bv_handle {
     std::vector<PlanStep> steps;    // in execution order (stem GEMM first)
     bv::StemParams stem{};          // fused 8-bit stem (valid when use_fused_stem)
     bool use_fused_stem = false;
+    bv::StemRowsParams stem_rows{}; // row-streaming 8-bit stem (valid when use_stem_rows)
+    bool use_stem_rows = false;
     const void* trunk = nullptr;    // final [B,h,w,2048] bf16
     int last_launches = 0;
     // optional per-launch timing (cudaEvents on the launch stream)
@@ -921,6 +926,17 @@ static int build_plan(bv_handle* h, const void* frames, int dtype, int B, int C,
         h->stem.tiles_x = (W / 4) / bv::kStemPool;
         h->stem.tiles_y = (H / 4) / bv::kStemPool;
     }
+    // Row-streaming stem (stem_rows.cuh): default for 8-bit frames; BV_STEM_V1 keeps the tile kernel above.
+    h->use_stem_rows = h->use_fused_stem && !env_flag("BV_STEM_V1");
+    if (h->use_stem_rows) {
+        memset(&h->stem_rows, 0, sizeof(h->stem_rows));
+        h->stem_rows.w = reinterpret_cast<const __nv_bfloat16*>(h->w.stem_u8_k8.w);
+        h->stem_rows.out = reinterpret_cast<__nv_bfloat16*>(buf_a);
+        h->stem_rows.B = B;
+        h->stem_rows.H = H;
+        h->stem_rows.W = W;
+        h->stem_rows.strips_x = (W / 4 + bv::kSrStripPx - 1) / bv::kSrStripPx;
+    }
     (void)frames;
     return BV_OK;
 }
@@ -959,7 +975,18 @@ int32_t bv_forward(bv_handle* h, const void* frames, int32_t dtype, int32_t B, i
     double pflops = 0, pbytes = 0;
     const int H2 = H / 2, W2 = W / 2, H4 = H / 4, W4 = W / 4;
     __nv_bfloat16* patches = reinterpret_cast<__nv_bfloat16*>(ws + lay.buf_a);
-    if (h->use_fused_stem) {
+    if (h->use_fused_stem && (reinterpret_cast<uintptr_t>(frames) & 7u))
+        return fail(BV_ERR_INVALID, "8-bit frames must be 8-byte aligned");
+    if (h->use_stem_rows) {
+        h->stem_rows.frames = reinterpret_cast<const uint8_t*>(frames);
+        const int strips = B * h->stem_rows.strips_x;
+        const int grid = std::min(strips, g_num_sms);
+        bv::stem_rows_kernel<<<grid, bv::kSrThreads, bv::kSrSmemBytes, st>>>(h->stem_rows);
+        BV_CUDA(cudaGetLastError());
+        ++launches;
+        prof_mark(h, st, "stem_rows conv7x7+bn+relu+maxpool", 2.0 * B * H2 * W2 * 64 * 49,
+                  (double)B * H * W + (double)B * H4 * W4 * 64 * 2);
+    } else if (h->use_fused_stem) {
         // 1-3 fused: conv7x7/2 + BN + ReLU + max-pool in one kernel, frame bytes in, layer1 input out
         h->stem.frames = reinterpret_cast<const uint8_t*>(frames);
         const int tiles = B * h->stem.tiles_x * h->stem.tiles_y;
@@ -1320,6 +1347,46 @@ int32_t bv_l1_block_nhwc(const void* t1, int32_t B, int32_t H, int32_t W, const 
     L1Launch L;
     if ((rc = build_l1_block(&L, B, H, W, t1, *c2, *c3, residual, out1, *next, out2))) return rc;
     return launch_l1_block(L, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int32_t bv_stem_u8_nhwc(const void* frames, int32_t B, int32_t H, int32_t W, const bv_conv* w8, void* out,
+                        int32_t variant, bv_stream stream) {
+    if (!frames || !w8 || !w8->w || !w8->bias || !out) return fail(BV_ERR_INVALID, "null argument");
+    if (B <= 0 || H <= 0 || W <= 0 || H % 32 || W % 32) return fail(BV_ERR_INVALID, "H, W must be multiples of 32");
+    int rc = device_setup();
+    if (rc) return rc;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (variant == 0) {
+        if (reinterpret_cast<uintptr_t>(frames) & 7u) return fail(BV_ERR_INVALID, "frames must be 8-byte aligned");
+        bv::StemRowsParams p{};
+        p.frames = reinterpret_cast<const uint8_t*>(frames);
+        p.w = reinterpret_cast<const __nv_bfloat16*>(w8->w);
+        p.out = reinterpret_cast<__nv_bfloat16*>(out);
+        p.B = B;
+        p.H = H;
+        p.W = W;
+        p.strips_x = (W / 4 + bv::kSrStripPx - 1) / bv::kSrStripPx;
+        if (const char* d = getenv("BV_SR_DEBUG")) p.debug = atoi(d);
+        const int grid = std::min(B * p.strips_x, g_num_sms);
+        bv::stem_rows_kernel<<<grid, bv::kSrThreads, bv::kSrSmemBytes, st>>>(p);
+    } else if (variant == 1) {
+        bv::StemParams p{};
+        if ((rc = make_tmap_2d(&p.tmW, w8->w, 64, 64, 64, 64))) return rc;
+        p.frames = reinterpret_cast<const uint8_t*>(frames);
+        p.bias = w8->bias;
+        p.out = reinterpret_cast<__nv_bfloat16*>(out);
+        p.B = B;
+        p.H = H;
+        p.W = W;
+        p.tiles_x = (W / 4) / bv::kStemPool;
+        p.tiles_y = (H / 4) / bv::kStemPool;
+        const int grid = std::min(B * p.tiles_x * p.tiles_y, 2 * g_num_sms);
+        bv::stem_fused_kernel<<<grid, bv::kStemThreads, bv::kStemSmemRequest, st>>>(p);
+    } else {
+        return fail(BV_ERR_INVALID, "unknown stem variant %d", variant);
+    }
+    BV_CUDA(cudaGetLastError());
+    return BV_OK;
 }
 
 int32_t bv_pair_gemm_test(const void* a, const void* w, int32_t M, int32_t N, int32_t K, float* out, bv_stream stream) {

@@ -1,0 +1,315 @@
+// Row-streaming BioViL stem for 8-bit frames: conv 7x7 stride 2 pad 3 (1 folded input channel -> 64) + BatchNorm +
+// ReLU + max-pool 3x3 stride 2 pad 1 -> NHWC bf16 input of layer1, as a warp-specialised pipeline that walks down a
+// strip of the frame and never materialises a 2-D im2col tile.
+//
+// Replaces (reference): ResNetHIML.forward conv1 -> bn1 -> relu -> maxpool,
+// health_multimodal/image/model/resnet.py:34-37, on frames made by ToTensor + ExpandChannels
+// (health_multimodal/image/data/transforms.py:12-38).  Same arithmetic and rounding points as stem_fused.cuh
+// (bf16 operands, fp32 accumulate incl. the BatchNorm bias, one bf16 rounding, max-pool, ReLU).
+//
+// Idea: with a NON-swizzled K-major shared-memory descriptor the two 16-byte K chunks of one tcgen05.mma K step may
+// sit anywhere (their distance is the descriptor's LBO field).  Expand every input row ONCE horizontally,
+//     E[y][m] = the 8 pixels under the filter for conv column cx(m)            (16 bytes, 128 GEMM rows -> 2 KB),
+// and the im2col operand of conv row c is simply rows 2c-3 .. 2c+3 of E: chunk r of GEMM row m = E[2c-3+r][m].
+// Vertical reuse costs nothing - each input row is expanded once (2 x 16 B per conv pixel instead of 7 x 16 B) -
+// and two conv rows share one N = 128 MMA: A = [ones | E rows 4g-3 .. 4g+5] (10 chunks = 5 K steps),
+// B rows 0..63 = filter rows against chunks 1..7, B rows 64..127 = the same filter rows against chunks 3..9,
+// chunk 0 = BatchNorm bias (hi + mid + lo bf16 terms against 1.0).  One pooled output row therefore is
+// 5 MMAs (128 x 128 x 16), 4 new E rows, and an epilogue that pools IN REGISTERS: vertical max against the conv row
+// carried from the previous step, horizontal max with two warp shuffles.
+//
+// GEMM row m <-> conv column: lane quarter q = m / 32 covers local conv columns 30 q + (m % 32), i.e. quarters overlap
+// by two columns so that every 3-wide pooling window lies inside one warp (TMEM lane quarters cannot be crossed).
+// One strip = 60 pooled columns (4 quarters x 15) x the whole frame height; W = 480 is exactly two strips.
+//
+// Warps: 0 cp.async producer (raw bytes, 4 input rows per stage, zero fill outside the frame), 1-4 expand + u8 -> bf16,
+// 5 MMA issue, 6-13 epilogue (lane quarter x channel half).  Rings: raw boxes (4), E groups of 4 rows (5),
+// TMEM accumulators (4 x 128 columns).
+#pragma once
+#include "ptx.cuh"
+#include "stem_fused.cuh"   // cp_async_8_zfill
+
+namespace bv {
+
+constexpr int kSrStripPx = 60;                    // pooled columns per strip
+constexpr int kSrNG = 5;                          // E ring: groups of 4 expanded input rows
+constexpr int kSrRowBytes = 128 * 16;             // one expanded input row
+constexpr int kSrGroupBytes = 4 * kSrRowBytes;
+constexpr int kSrRawStages = 4;
+constexpr int kSrRawPitch = 256;                  // bytes per raw input row in a box
+constexpr int kSrRawBytes = 4 * kSrRawPitch;
+constexpr int kSrTmemStages = 4;                  // x 128 columns (two conv rows x 64 channels)
+constexpr int kSrChunks = 10;                     // K chunks of 8: ones + 9 input rows
+constexpr int kSrWBytes = kSrChunks * 128 * 16;   // B operand: chunk-major, 128 rows x 16 B per chunk
+constexpr int kSrThreads = 14 * 32;
+constexpr int kSrOnesBytes = 128 * 16;
+constexpr int kSrSmemBytes =
+    kSrOnesBytes + kSrNG * kSrGroupBytes + kSrWBytes + kSrRawStages * kSrRawBytes + 256 + 1024 /* alignment slack */;
+
+struct StemRowsParams {
+    const uint8_t* frames;        // u8 [B][H][W], 8-byte aligned
+    const __nv_bfloat16* w;       // [64][64], k = r*8 + s, chunk 7 = BatchNorm bias hi/mid/lo (bv_weights.stem_u8_k8)
+    __nv_bfloat16* out;           // [B][H/4][W/4][64]
+    int B, H, W;
+    int strips_x;                 // ceil((W/4) / 60)
+    int debug;                    // BV_SR_DEBUG bisect bits (1 no loads, 2 no MMA, 8 no tcgen05.ld)
+};
+
+// K-major descriptor WITHOUT swizzle (cute::UMMA LayoutType::SWIZZLE_NONE, canonical layout
+// ((8,m),(8,2)):((16 B, SBO),(2 B, LBO))): rows 16 bytes apart inside an 8-row core matrix, 8-row groups SBO apart,
+// the two K chunks of a K step LBO apart.
+__device__ __forceinline__ uint64_t umma_desc_k_none(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+    d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFFu) << 16;
+    d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFFu) << 32;
+    d |= static_cast<uint64_t>(1) << 46;
+    return d;
+}
+
+// four 8-bit pixels -> four bf16 (exact): 0x4B0000pp is the float 8388608 + pp
+__device__ __forceinline__ void u8x4_to_bf16x4(uint32_t w, uint32_t& lo, uint32_t& hi) {
+    const float f0 = __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7440)) - 8388608.0f;
+    const float f1 = __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7441)) - 8388608.0f;
+    const float f2 = __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7442)) - 8388608.0f;
+    const float f3 = __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7443)) - 8388608.0f;
+    const __nv_bfloat162 a = __floats2bfloat162_rn(f0, f1), b = __floats2bfloat162_rn(f2, f3);
+    lo = *reinterpret_cast<const uint32_t*>(&a);
+    hi = *reinterpret_cast<const uint32_t*>(&b);
+}
+
+__device__ __forceinline__ uint32_t bf16x2_max(uint32_t a, uint32_t b) {
+    const __nv_bfloat162 r = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&a), *reinterpret_cast<const __nv_bfloat162*>(&b));
+    return *reinterpret_cast<const uint32_t*>(&r);
+}
+
+__global__ void __launch_bounds__(kSrThreads, 1) stem_rows_kernel(const __grid_constant__ StemRowsParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+    uint8_t* ones = smem;                                   // 128 x [1,1,1,0,0,0,0,0]: sits BELOW the ring (LBO > 0)
+    uint8_t* ring = ones + kSrOnesBytes;                    // kSrNG groups x 4 expanded rows
+    uint8_t* wsm = ring + kSrNG * kSrGroupBytes;            // B operand
+    uint8_t* raw = wsm + kSrWBytes;                         // raw byte boxes
+    uint64_t* bars = reinterpret_cast<uint64_t*>(raw + kSrRawStages * kSrRawBytes);
+    uint64_t* raw_full = bars;
+    uint64_t* raw_empty = raw_full + kSrRawStages;
+    uint64_t* e_full = raw_empty + kSrRawStages;
+    uint64_t* e_empty = e_full + kSrNG;
+    uint64_t* t_full = e_empty + kSrNG;
+    uint64_t* t_empty = t_full + kSrTmemStages;
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(t_empty + kSrTmemStages);
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5;
+    const int lane = tid & 31;
+    const int Hp = p.H / 4, Wp = p.W / 4;
+    const int nstrips = p.B * p.strips_x;
+    const uint32_t groups_per_strip = static_cast<uint32_t>(Hp + 2);
+
+    if (tid == 0) {
+        for (int i = 0; i < kSrRawStages; ++i) {
+            mbar_init(raw_full + i, 32);
+            mbar_init(raw_empty + i, 128);
+        }
+        for (int i = 0; i < kSrNG; ++i) {
+            mbar_init(e_full + i, 128);
+            mbar_init(e_empty + i, 1);
+        }
+        for (int i = 0; i < kSrTmemStages; ++i) {
+            mbar_init(t_full + i, 1);
+            mbar_init(t_empty + i, 8);
+        }
+        fence_barrier_init();
+    }
+    // constant operands, written once through the generic proxy
+    if (tid < 128) *reinterpret_cast<uint4*>(ones + tid * 16) = make_uint4(0x3F803F80u, 0x00003F80u, 0u, 0u);
+    for (int i = tid; i < kSrChunks * 128; i += kSrThreads) {
+        const int c = i >> 7, n = i & 127;
+        // rows 0..63: conv row 2g (filter row r against chunk 1 + r); rows 64..127: conv row 2g+1 (chunk 3 + r)
+        const int r = (n < 64) ? c - 1 : c - 3;
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (c == 0) v = *reinterpret_cast<const uint4*>(p.w + (n & 63) * 64 + 56);
+        else if (r >= 0 && r < 7) v = *reinterpret_cast<const uint4*>(p.w + (n & 63) * 64 + r * 8);
+        *reinterpret_cast<uint4*>(wsm + c * 2048 + n * 16) = v;
+    }
+    fence_proxy_async_smem();
+    if (warp == 5) {
+        tmem_alloc(tmem_ptr, 512);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp == 0) {
+        // ---------------- raw byte producer ----------------
+        // 4 input rows x 256 bytes per group as 8-byte cp.async pieces (TMA needs a 16-byte aligned box start; the
+        // strip origin 240 s - 8 is only 8-byte aligned), zero fill outside the frame; the mbarrier arrival of each
+        // lane fires when its copies have landed.  smem byte i of a row <-> input column 240 s - 8 + i.
+        uint32_t n = 0;
+        for (int strip = blockIdx.x; strip < nstrips; strip += gridDim.x) {
+            const int b = strip / p.strips_x, s = strip - b * p.strips_x;
+            const int x = 4 * kSrStripPx * s - 8 + 8 * lane;
+            const bool x_ok = x >= 0 && x < p.W;
+            const uint8_t* fb = p.frames + static_cast<size_t>(b) * p.H * p.W + (x_ok ? x : 0);
+            for (int j = -2; j < Hp; ++j, ++n) {
+                const uint32_t st = n % kSrRawStages;
+                mbar_wait(raw_empty + st, ((n / kSrRawStages) & 1u) ^ 1u);
+                if (!(p.debug & 1)) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const int y = 4 * j + 2 + k;
+                        const bool ok = x_ok && y >= 0 && y < p.H;
+                        cp_async_8_zfill(raw + st * kSrRawBytes + k * kSrRawPitch + lane * 8,
+                                         fb + static_cast<size_t>(ok ? y : 0) * p.W, ok);
+                    }
+                }
+                asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];\n" ::"r"(smem_u32(raw_full + st)) : "memory");
+            }
+        }
+    } else if (warp <= 4) {
+        // ---------------- horizontal expansion + u8 -> bf16 ----------------
+        const int m = tid - 32;
+        const int lcx = 30 * (m >> 5) + (m & 31);
+        const uint32_t woff = static_cast<uint32_t>((2 * lcx + 3) >> 2) * 4u;   // the 8 pixels start at byte 2*lcx + 3
+        const uint32_t shift = static_cast<uint32_t>((2 * lcx + 3) & 3) * 8u;
+        uint32_t n = 0;
+        for (int strip = blockIdx.x; strip < nstrips; strip += gridDim.x) {
+            for (int j = -2; j < Hp; ++j, ++n) {
+                const uint32_t rs = n % kSrRawStages, es = n % kSrNG;
+                mbar_wait(raw_full + rs, (n / kSrRawStages) & 1u);
+                mbar_wait(e_empty + es, ((n / kSrNG) & 1u) ^ 1u);
+                const uint8_t* src = raw + rs * kSrRawBytes + woff;
+                uint8_t* dst = ring + es * kSrGroupBytes + m * 16;
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    const uint32_t* s32 = reinterpret_cast<const uint32_t*>(src + r * kSrRawPitch);
+                    const uint32_t w0 = s32[0], w1 = s32[1], w2 = s32[2];
+                    const uint32_t lo = __funnelshift_r(w0, w1, shift), hi = __funnelshift_r(w1, w2, shift);
+                    uint4 v;
+                    u8x4_to_bf16x4(lo, v.x, v.y);
+                    u8x4_to_bf16x4(hi, v.z, v.w);
+                    *reinterpret_cast<uint4*>(dst + r * kSrRowBytes) = v;
+                }
+                fence_proxy_async_smem();
+                mbar_arrive(e_full + es);
+                mbar_arrive(raw_empty + rs);
+            }
+        }
+    } else if (warp == 5) {
+        // ---------------- MMA issue ----------------
+        if (elect_one()) {
+            constexpr uint32_t idesc = umma_idesc_bf16_f32(128, 128);
+            const uint32_t ones_a = smem_u32(ones), ring_a = smem_u32(ring), w_a = smem_u32(wsm);
+            uint32_t gbase = 0, sc = 0;
+            for (int strip = blockIdx.x; strip < nstrips; strip += gridDim.x, gbase += groups_per_strip) {
+                for (int g = 0; g < Hp; ++g, ++sc) {
+                    // group G = gbase + j + 2 holds input rows 4j+2 .. 4j+5; this step reads j = g-2 (last row), g-1, g
+                    const uint32_t G0 = gbase + g, G1 = G0 + 1, G2 = G0 + 2;
+                    if (g == 0) {
+                        mbar_wait(e_full + G0 % kSrNG, (G0 / kSrNG) & 1u);
+                        mbar_wait(e_full + G1 % kSrNG, (G1 / kSrNG) & 1u);
+                    }
+                    mbar_wait(e_full + G2 % kSrNG, (G2 / kSrNG) & 1u);
+                    const uint32_t ts = sc % kSrTmemStages;
+                    mbar_wait(t_empty + ts, ((sc / kSrTmemStages) & 1u) ^ 1u);
+                    tc_fence_after();
+                    const uint32_t a0 = ring_a + (G0 % kSrNG) * kSrGroupBytes;
+                    const uint32_t a1 = ring_a + (G1 % kSrNG) * kSrGroupBytes;
+                    const uint32_t a2 = ring_a + (G2 % kSrNG) * kSrGroupBytes;
+                    const uint32_t d = tmem_base + ts * 128u;
+                    // K step 0: [ones | input row 4g-3 (last row of group g-2)]
+                    const uint32_t row0 = a0 + 3 * kSrRowBytes;
+                    if (!(p.debug & 2)) {
+                    umma_bf16_ss(d, umma_desc_k_none(ones_a, row0 - ones_a, 128), umma_desc_k_none(w_a, 2048, 128), idesc, 0u);
+                    // K steps 1..4: row pairs (4g-2, 4g-1), (4g, 4g+1), (4g+2, 4g+3), (4g+4, 4g+5)
+                    umma_bf16_ss(d, umma_desc_k_none(a1, kSrRowBytes, 128), umma_desc_k_none(w_a + 2 * 2048, 2048, 128), idesc, 1u);
+                    umma_bf16_ss(d, umma_desc_k_none(a1 + 2 * kSrRowBytes, kSrRowBytes, 128),
+                                 umma_desc_k_none(w_a + 4 * 2048, 2048, 128), idesc, 1u);
+                    umma_bf16_ss(d, umma_desc_k_none(a2, kSrRowBytes, 128), umma_desc_k_none(w_a + 6 * 2048, 2048, 128), idesc, 1u);
+                    umma_bf16_ss(d, umma_desc_k_none(a2 + 2 * kSrRowBytes, kSrRowBytes, 128),
+                                 umma_desc_k_none(w_a + 8 * 2048, 2048, 128), idesc, 1u);
+                    }
+                    umma_commit(t_full + ts);
+                    umma_commit(e_empty + G0 % kSrNG);
+                    if (g == Hp - 1) {
+                        umma_commit(e_empty + G1 % kSrNG);
+                        umma_commit(e_empty + G2 % kSrNG);
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    } else {
+        // ---------------- epilogue: TMEM -> bf16 -> 3x3/2 max-pool in registers -> ReLU -> global ----------------
+        const int q = warp & 3;            // TMEM lane quarter
+        const int hf = (warp - 6) >> 2;    // channel half
+        uint32_t sc = 0;
+        for (int strip = blockIdx.x; strip < nstrips; strip += gridDim.x) {
+            const int b = strip / p.strips_x, s = strip - b * p.strips_x;
+            // local conv column 0 of strip 0 is conv column -1: max-pool padding, never wins
+            const bool pad_left = (s == 0 && q == 0 && lane == 0);
+            const int px = kSrStripPx * s + 15 * q + (lane >> 1);
+            const bool store_ok = (lane >> 1) < 15 && px < Wp;
+            uint32_t carry[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) carry[i] = 0xFF80FF80u;   // conv row -1: padding
+            for (int g = 0; g < Hp; ++g, ++sc) {
+                const uint32_t ts = sc % kSrTmemStages;
+                mbar_wait(t_full + ts, (sc / kSrTmemStages) & 1u);
+                tc_fence_after();
+                uint32_t ra[32], rb[32];
+                const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + ts * 128u + static_cast<uint32_t>(hf * 32);
+                if (!(p.debug & 8)) {
+                    tmem_ld_32x32(taddr, ra);
+                    tmem_ld_32x32(taddr + 64u, rb);
+                    tmem_ld_wait();
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) ra[i] = rb[i] = 0u;
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(t_empty + ts);
+                uint32_t v[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const __nv_bfloat162 ha = __floats2bfloat162_rn(__uint_as_float(ra[2 * i]), __uint_as_float(ra[2 * i + 1]));
+                    const __nv_bfloat162 hb = __floats2bfloat162_rn(__uint_as_float(rb[2 * i]), __uint_as_float(rb[2 * i + 1]));
+                    const uint32_t ua = pad_left ? 0xFF80FF80u : *reinterpret_cast<const uint32_t*>(&ha);
+                    const uint32_t ub = pad_left ? 0xFF80FF80u : *reinterpret_cast<const uint32_t*>(&hb);
+                    uint32_t x = bf16x2_max(bf16x2_max(carry[i], ua), ub);   // conv rows 2g-1, 2g, 2g+1
+                    carry[i] = ub;
+                    const uint32_t x1 = __shfl_down_sync(0xffffffffu, x, 1);
+                    const uint32_t x2 = __shfl_down_sync(0xffffffffu, x, 2);
+                    x = bf16x2_max(bf16x2_max(x, x1), x2);                   // conv columns 2j, 2j+1, 2j+2 (lane 2j)
+                    v[i] = bf16x2_max(x, 0u);                                // ReLU after the pool
+                }
+                // even lane 2j holds pooled pixel j (64 B = 4 chunks of this channel half); the odd neighbour takes
+                // chunks 1 and 3 so that every store instruction writes whole 32-byte sectors
+                __nv_bfloat16* dst = p.out + ((static_cast<size_t>(b) * Hp + g) * Wp + px) * 64 + hf * 32 + (lane & 1) * 8;
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    uint4 o;
+                    uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const uint32_t t = __shfl_sync(0xffffffffu, v[(2 * i + 1) * 4 + e], lane & ~1);
+                        ow[e] = (lane & 1) ? t : v[2 * i * 4 + e];
+                    }
+                    if (store_ok) *reinterpret_cast<uint4*>(dst + i * 16) = o;
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 5) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+}  // namespace bv

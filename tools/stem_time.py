@@ -1,0 +1,32 @@
+"""Time the two 8-bit stem kernels alone (bv_stem_u8_nhwc) at the bench shape: 512 frames of 480x480."""
+import ctypes
+import sys
+
+import torch
+
+sys.path.insert(0, ".")
+sys.path.insert(0, "tests")
+import test_stem_gpu as T  # noqa: E402
+from incremental_multimodal_medical_learning_ii_b200 import _native as N  # noqa: E402
+
+B, H, W = 512, 480, 480
+g = torch.Generator().manual_seed(0)
+frames = [torch.randint(0, 256, (B, H, W), generator=g, dtype=torch.uint8).to(T.DEV) for _ in range(2)]
+w = (torch.randn(64, 7, 7, generator=g) / 7 / 255).to(torch.bfloat16)
+conv, keep, _ = T._pack_w8(w.float(), torch.randn(64, generator=g), T.DEV)
+out = torch.empty((B, H // 4, W // 4, 64), device=T.DEV, dtype=torch.bfloat16)
+lib = N.lib()
+st = N.current_stream_handle(torch.device(T.DEV))
+for variant, name in ((1, "tile (stem_fused)"), (0, "rows (stem_rows)"), (1, "tile (stem_fused)"), (0, "rows (stem_rows)")):
+    for i in range(3):
+        N.check(lib.bv_stem_u8_nhwc(N.ptr(frames[i & 1]), B, H, W, ctypes.byref(conv), N.ptr(out), variant, st))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    n = 20
+    for i in range(n):
+        N.check(lib.bv_stem_u8_nhwc(N.ptr(frames[i & 1]), B, H, W, ctypes.byref(conv), N.ptr(out), variant, st))
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / n
+    gb = (B * H * W + out.numel() * 2) / 1e9
+    print(f"{name}: {ms:.3f} ms per launch, {gb / ms * 1e3:.0f} GB/s algorithmic")
