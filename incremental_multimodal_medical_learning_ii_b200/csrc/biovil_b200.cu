@@ -124,6 +124,14 @@ bool env_flag(const char* name) {
     return v && v[0] && v[0] != '0';
 }
 
+// Row-streaming stem: 16 epilogue warps of 16 channels by default, BV_SR_CG2 = 8 warps of 32 channels.
+void launch_stem_rows(const bv::StemRowsParams& p, int grid, cudaStream_t st) {
+    if (env_flag("BV_SR_CG2"))
+        bv::stem_rows_kernel<2><<<grid, bv::sr_threads(2), bv::kSrSmemBytes, st>>>(p);
+    else
+        bv::stem_rows_kernel<4><<<grid, bv::sr_threads(4), bv::kSrSmemBytes, st>>>(p);
+}
+
 struct ConvOperand {
     const void* x;  // NHWC bf16 [B][H][W][cin]
     int H, W;
@@ -213,7 +221,9 @@ int device_setup() {
         BV_CUDA(cudaFuncSetAttribute(bv::head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
         BV_CUDA(cudaFuncSetAttribute(bv::stem_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      bv::kStemSmemRequest));
-        BV_CUDA(cudaFuncSetAttribute(bv::stem_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        BV_CUDA(cudaFuncSetAttribute(bv::stem_rows_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     bv::kSrSmemBytes));
+        BV_CUDA(cudaFuncSetAttribute(bv::stem_rows_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      bv::kSrSmemBytes));
         g_attr_set = true;
     }
@@ -981,7 +991,7 @@ int32_t bv_forward(bv_handle* h, const void* frames, int32_t dtype, int32_t B, i
         h->stem_rows.frames = reinterpret_cast<const uint8_t*>(frames);
         const int strips = B * h->stem_rows.strips_x;
         const int grid = std::min(strips, g_num_sms);
-        bv::stem_rows_kernel<<<grid, bv::kSrThreads, bv::kSrSmemBytes, st>>>(h->stem_rows);
+        launch_stem_rows(h->stem_rows, grid, st);
         BV_CUDA(cudaGetLastError());
         ++launches;
         prof_mark(h, st, "stem_rows conv7x7+bn+relu+maxpool", 2.0 * B * H2 * W2 * 64 * 49,
@@ -1368,7 +1378,7 @@ int32_t bv_stem_u8_nhwc(const void* frames, int32_t B, int32_t H, int32_t W, con
         p.strips_x = (W / 4 + bv::kSrStripPx - 1) / bv::kSrStripPx;
         if (const char* d = getenv("BV_SR_DEBUG")) p.debug = atoi(d);
         const int grid = std::min(B * p.strips_x, g_num_sms);
-        bv::stem_rows_kernel<<<grid, bv::kSrThreads, bv::kSrSmemBytes, st>>>(p);
+        launch_stem_rows(p, grid, st);
     } else if (variant == 1) {
         bv::StemParams p{};
         if ((rc = make_tmap_2d(&p.tmW, w8->w, 64, 64, 64, 64))) return rc;

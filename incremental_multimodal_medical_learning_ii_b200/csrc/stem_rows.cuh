@@ -23,7 +23,7 @@
 // One strip = 60 pooled columns (4 quarters x 15) x the whole frame height; W = 480 is exactly two strips.
 //
 // Warps: 0 cp.async producer (raw bytes, 4 input rows per stage, zero fill outside the frame), 1-4 expand + u8 -> bf16,
-// 5 MMA issue, 6-13 epilogue (lane quarter x channel half).  Rings: raw boxes (4), E groups of 4 rows (5),
+// 5 MMA issue, 6.. epilogue (lane quarter x channel group, 4 x CG warps).  Rings: raw boxes (4), E groups of 4 rows (5),
 // TMEM accumulators (4 x 128 columns).
 #pragma once
 #include "ptx.cuh"
@@ -35,16 +35,16 @@ constexpr int kSrStripPx = 60;                    // pooled columns per strip
 constexpr int kSrNG = 5;                          // E ring: groups of 4 expanded input rows
 constexpr int kSrRowBytes = 128 * 16;             // one expanded input row
 constexpr int kSrGroupBytes = 4 * kSrRowBytes;
-constexpr int kSrRawStages = 4;
+constexpr int kSrRawStages = 8;                   // 1 KB each (4 / 8 / 16 stages measured equal)
 constexpr int kSrRawPitch = 256;                  // bytes per raw input row in a box
 constexpr int kSrRawBytes = 4 * kSrRawPitch;
 constexpr int kSrTmemStages = 4;                  // x 128 columns (two conv rows x 64 channels)
 constexpr int kSrChunks = 10;                     // K chunks of 8: ones + 9 input rows
 constexpr int kSrWBytes = kSrChunks * 128 * 16;   // B operand: chunk-major, 128 rows x 16 B per chunk
-constexpr int kSrThreads = 14 * 32;
+__host__ __device__ constexpr int sr_threads(int cg) { return (6 + 4 * cg) * 32; }   // CG = channel groups of the epilogue (64 / CG channels per warp)
 constexpr int kSrOnesBytes = 128 * 16;
 constexpr int kSrSmemBytes =
-    kSrOnesBytes + kSrNG * kSrGroupBytes + kSrWBytes + kSrRawStages * kSrRawBytes + 256 + 1024 /* alignment slack */;
+    kSrOnesBytes + kSrNG * kSrGroupBytes + kSrWBytes + kSrRawStages * kSrRawBytes + 512;
 
 struct StemRowsParams {
     const uint8_t* frames;        // u8 [B][H][W], 8-byte aligned
@@ -52,7 +52,7 @@ struct StemRowsParams {
     __nv_bfloat16* out;           // [B][H/4][W/4][64]
     int B, H, W;
     int strips_x;                 // ceil((W/4) / 60)
-    int debug;                    // BV_SR_DEBUG bisect bits (1 no loads, 2 no MMA, 8 no tcgen05.ld)
+    int debug;                    // BV_SR_DEBUG bisect bits (1 no loads, 2 no MMA)
 };
 
 // K-major descriptor WITHOUT swizzle (cute::UMMA LayoutType::SWIZZLE_NONE, canonical layout
@@ -83,9 +83,29 @@ __device__ __forceinline__ uint32_t bf16x2_max(uint32_t a, uint32_t b) {
     return *reinterpret_cast<const uint32_t*>(&r);
 }
 
-__global__ void __launch_bounds__(kSrThreads, 1) stem_rows_kernel(const __grid_constant__ StemRowsParams p) {
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+template <int N>
+__device__ __forceinline__ void sr_tmem_ld(uint32_t taddr, uint32_t (&r)[N]) {
+    static_assert(N == 16 || N == 32, "16 or 32 columns");
+    if constexpr (N == 32) {
+        tmem_ld_32x32(taddr, r);
+    } else {
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+              "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+            : "r"(taddr)
+            : "memory");
+    }
+}
+
+template <int CG>
+__global__ void __launch_bounds__(sr_threads(CG), 1) stem_rows_kernel(const __grid_constant__ StemRowsParams p) {
+    constexpr int kThreads = sr_threads(CG);
+    constexpr int kCh = 64 / CG;        // channels per epilogue warp
+    constexpr int kPk = kCh / 2;        // packed bf16x2 registers per conv row
+    extern __shared__ __align__(1024) uint8_t smem[];   // keep the shared address space visible (LDS/STS, not LD.E)
+    if ((smem_u32(smem) & 127u) != 0u) __trap();
     uint8_t* ones = smem;                                   // 128 x [1,1,1,0,0,0,0,0]: sits BELOW the ring (LBO > 0)
     uint8_t* ring = ones + kSrOnesBytes;                    // kSrNG groups x 4 expanded rows
     uint8_t* wsm = ring + kSrNG * kSrGroupBytes;            // B operand
@@ -104,6 +124,7 @@ __global__ void __launch_bounds__(kSrThreads, 1) stem_rows_kernel(const __grid_c
     const int lane = tid & 31;
     const int Hp = p.H / 4, Wp = p.W / 4;
     const int nstrips = p.B * p.strips_x;
+    constexpr uint32_t nraw = kSrRawStages;
     const uint32_t groups_per_strip = static_cast<uint32_t>(Hp + 2);
 
     if (tid == 0) {
@@ -117,13 +138,13 @@ __global__ void __launch_bounds__(kSrThreads, 1) stem_rows_kernel(const __grid_c
         }
         for (int i = 0; i < kSrTmemStages; ++i) {
             mbar_init(t_full + i, 1);
-            mbar_init(t_empty + i, 8);
+            mbar_init(t_empty + i, 4 * CG);
         }
         fence_barrier_init();
     }
     // constant operands, written once through the generic proxy
     if (tid < 128) *reinterpret_cast<uint4*>(ones + tid * 16) = make_uint4(0x3F803F80u, 0x00003F80u, 0u, 0u);
-    for (int i = tid; i < kSrChunks * 128; i += kSrThreads) {
+    for (int i = tid; i < kSrChunks * 128; i += kThreads) {
         const int c = i >> 7, n = i & 127;
         // rows 0..63: conv row 2g (filter row r against chunk 1 + r); rows 64..127: conv row 2g+1 (chunk 3 + r)
         const int r = (n < 64) ? c - 1 : c - 3;
@@ -154,8 +175,8 @@ __global__ void __launch_bounds__(kSrThreads, 1) stem_rows_kernel(const __grid_c
             const bool x_ok = x >= 0 && x < p.W;
             const uint8_t* fb = p.frames + static_cast<size_t>(b) * p.H * p.W + (x_ok ? x : 0);
             for (int j = -2; j < Hp; ++j, ++n) {
-                const uint32_t st = n % kSrRawStages;
-                mbar_wait(raw_empty + st, ((n / kSrRawStages) & 1u) ^ 1u);
+                const uint32_t st = n % nraw;
+                mbar_wait(raw_empty + st, ((n / nraw) & 1u) ^ 1u);
                 if (!(p.debug & 1)) {
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
@@ -177,8 +198,8 @@ __global__ void __launch_bounds__(kSrThreads, 1) stem_rows_kernel(const __grid_c
         uint32_t n = 0;
         for (int strip = blockIdx.x; strip < nstrips; strip += gridDim.x) {
             for (int j = -2; j < Hp; ++j, ++n) {
-                const uint32_t rs = n % kSrRawStages, es = n % kSrNG;
-                mbar_wait(raw_full + rs, (n / kSrRawStages) & 1u);
+                const uint32_t rs = n % nraw, es = n % kSrNG;
+                mbar_wait(raw_full + rs, (n / nraw) & 1u);
                 mbar_wait(e_empty + es, ((n / kSrNG) & 1u) ^ 1u);
                 const uint8_t* src = raw + rs * kSrRawBytes + woff;
                 uint8_t* dst = ring + es * kSrGroupBytes + m * 16;
@@ -244,41 +265,43 @@ __global__ void __launch_bounds__(kSrThreads, 1) stem_rows_kernel(const __grid_c
     } else {
         // ---------------- epilogue: TMEM -> bf16 -> 3x3/2 max-pool in registers -> ReLU -> global ----------------
         const int q = warp & 3;            // TMEM lane quarter
-        const int hf = (warp - 6) >> 2;    // channel half
+        const int cg = (warp - 6) >> 2;    // channel group
         uint32_t sc = 0;
         for (int strip = blockIdx.x; strip < nstrips; strip += gridDim.x) {
             const int b = strip / p.strips_x, s = strip - b * p.strips_x;
             // local conv column 0 of strip 0 is conv column -1: max-pool padding, never wins
-            const bool pad_left = (s == 0 && q == 0 && lane == 0);
+            const bool pad_warp = (s == 0 && q == 0);
             const int px = kSrStripPx * s + 15 * q + (lane >> 1);
             const bool store_ok = (lane >> 1) < 15 && px < Wp;
-            uint32_t carry[16];
+            uint32_t carry[kPk];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) carry[i] = 0xFF80FF80u;   // conv row -1: padding
+            for (int i = 0; i < kPk; ++i) carry[i] = 0xFF80FF80u;   // conv row -1: padding
             for (int g = 0; g < Hp; ++g, ++sc) {
                 const uint32_t ts = sc % kSrTmemStages;
                 mbar_wait(t_full + ts, (sc / kSrTmemStages) & 1u);
                 tc_fence_after();
-                uint32_t ra[32], rb[32];
-                const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + ts * 128u + static_cast<uint32_t>(hf * 32);
-                if (!(p.debug & 8)) {
-                    tmem_ld_32x32(taddr, ra);
-                    tmem_ld_32x32(taddr + 64u, rb);
-                    tmem_ld_wait();
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) ra[i] = rb[i] = 0u;
-                }
+                uint32_t ra[kCh], rb[kCh];
+                const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + ts * 128u + static_cast<uint32_t>(cg * kCh);
+                sr_tmem_ld<kCh>(taddr, ra);
+                sr_tmem_ld<kCh>(taddr + 64u, rb);
+                tmem_ld_wait();
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(t_empty + ts);
-                uint32_t v[16];
+                uint32_t v[kPk];
+                if (pad_warp) {   // warp-uniform: only the first quarter of strip 0 holds the padding column
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
+                    for (int i = 0; i < kCh; ++i) {
+                        ra[i] = lane == 0 ? 0xFF800000u : ra[i];   // -inf
+                        rb[i] = lane == 0 ? 0xFF800000u : rb[i];
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < kPk; ++i) {
                     const __nv_bfloat162 ha = __floats2bfloat162_rn(__uint_as_float(ra[2 * i]), __uint_as_float(ra[2 * i + 1]));
                     const __nv_bfloat162 hb = __floats2bfloat162_rn(__uint_as_float(rb[2 * i]), __uint_as_float(rb[2 * i + 1]));
-                    const uint32_t ua = pad_left ? 0xFF80FF80u : *reinterpret_cast<const uint32_t*>(&ha);
-                    const uint32_t ub = pad_left ? 0xFF80FF80u : *reinterpret_cast<const uint32_t*>(&hb);
+                    const uint32_t ua = *reinterpret_cast<const uint32_t*>(&ha);
+                    const uint32_t ub = *reinterpret_cast<const uint32_t*>(&hb);
                     uint32_t x = bf16x2_max(bf16x2_max(carry[i], ua), ub);   // conv rows 2g-1, 2g, 2g+1
                     carry[i] = ub;
                     const uint32_t x1 = __shfl_down_sync(0xffffffffu, x, 1);
@@ -286,11 +309,11 @@ __global__ void __launch_bounds__(kSrThreads, 1) stem_rows_kernel(const __grid_c
                     x = bf16x2_max(bf16x2_max(x, x1), x2);                   // conv columns 2j, 2j+1, 2j+2 (lane 2j)
                     v[i] = bf16x2_max(x, 0u);                                // ReLU after the pool
                 }
-                // even lane 2j holds pooled pixel j (64 B = 4 chunks of this channel half); the odd neighbour takes
-                // chunks 1 and 3 so that every store instruction writes whole 32-byte sectors
-                __nv_bfloat16* dst = p.out + ((static_cast<size_t>(b) * Hp + g) * Wp + px) * 64 + hf * 32 + (lane & 1) * 8;
+                // even lane 2j holds pooled pixel j (kCh channels = kCh / 8 chunks of 16 bytes); the odd neighbour takes
+                // the odd chunks so that every store instruction writes whole 32-byte sectors
+                __nv_bfloat16* dst = p.out + ((static_cast<size_t>(b) * Hp + g) * Wp + px) * 64 + cg * kCh + (lane & 1) * 8;
 #pragma unroll
-                for (int i = 0; i < 2; ++i) {
+                for (int i = 0; i < kCh / 16; ++i) {
                     uint4 o;
                     uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
 #pragma unroll

@@ -17,7 +17,14 @@ conv, keep, _ = T._pack_w8(w.float(), torch.randn(64, generator=g), T.DEV)
 out = torch.empty((B, H // 4, W // 4, 64), device=T.DEV, dtype=torch.bfloat16)
 lib = N.lib()
 st = N.current_stream_handle(torch.device(T.DEV))
-for variant, name in ((1, "tile (stem_fused)"), (0, "rows (stem_rows)"), (1, "tile (stem_fused)"), (0, "rows (stem_rows)")):
+import os
+CASES = [(1, "", "", "", "tile (stem_fused)"), (0, "1", "", "", "rows, 8 epilogue warps"), (0, "", "", "", "rows, 16 epilogue warps"),
+         (0, "1", "", "", "rows, 8 epilogue warps"), (0, "", "", "", "rows, 16 epilogue warps"),
+         (0, "1", "", "2", "rows, 8 epilogue warps, no MMA"), (0, "1", "", "3", "rows, 8 epilogue warps, no loads, no MMA")]
+for variant, cg2, raw, dbg, name in CASES:
+    os.environ["BV_SR_CG2"] = cg2
+    os.environ["BV_SR_RAW"] = raw
+    os.environ["BV_SR_DEBUG"] = dbg or "0"
     for i in range(3):
         N.check(lib.bv_stem_u8_nhwc(N.ptr(frames[i & 1]), B, H, W, ctypes.byref(conv), N.ptr(out), variant, st))
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
