@@ -1,5 +1,5 @@
 """One warm-up forward + one forward of configs[1] (batch 512, 1x480x480 u8) for use under ncu:
-    ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum -k regex:'conv_gemm|stem_fused|head' ...
+    ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum -k regex:'conv_gemm|chain_gemm|conv3x3_tap3|l1_block|stem_|head' -s 44 -c 44 ...
 Usage: python tools/ncu_step.py [batch] [forwards]"""
 import os
 import sys
