@@ -124,12 +124,13 @@ bool env_flag(const char* name) {
     return v && v[0] && v[0] != '0';
 }
 
-// Row-streaming stem: 16 epilogue warps of 16 channels by default, BV_SR_CG2 = 8 warps of 32 channels.
+// Row-streaming stem: 8 epilogue warps of 32 channels (0.566 ms per 512 frames alone); BV_SR_CG4 = 16 warps of 16
+// channels (0.594 ms: the kernel is bound by instruction throughput, not latency, and more warps add per-warp overhead).
 void launch_stem_rows(const bv::StemRowsParams& p, int grid, cudaStream_t st) {
-    if (env_flag("BV_SR_CG2"))
-        bv::stem_rows_kernel<2><<<grid, bv::sr_threads(2), bv::kSrSmemBytes, st>>>(p);
-    else
+    if (env_flag("BV_SR_CG4"))
         bv::stem_rows_kernel<4><<<grid, bv::sr_threads(4), bv::kSrSmemBytes, st>>>(p);
+    else
+        bv::stem_rows_kernel<2><<<grid, bv::sr_threads(2), bv::kSrSmemBytes, st>>>(p);
 }
 
 struct ConvOperand {

@@ -55,12 +55,12 @@ def _run(frames, conv, variant):
 SHAPES = [(1, 32, 32), (2, 64, 96), (3, 96, 160), (2, 480, 480), (1, 512, 512), (3, 480, 256), (80, 480, 480)]
 
 
-@pytest.mark.parametrize("variant", [0, 2, 1], ids=["rows", "rows8", "tile"])
+@pytest.mark.parametrize("variant", [0, 2, 1], ids=["rows", "rows16", "tile"])
 @pytest.mark.parametrize("shape", SHAPES, ids=lambda s: "x".join(map(str, s)))
 def test_stem_integer_bit_exact(shape, variant, monkeypatch):
     B, H, W = shape
-    if variant == 2:        # row-streaming kernel with 8 epilogue warps of 32 channels instead of 16 of 16
-        monkeypatch.setenv("BV_SR_CG2", "1")
+    if variant == 2:        # row-streaming kernel with 16 epilogue warps of 16 channels instead of 8 of 32
+        monkeypatch.setenv("BV_SR_CG4", "1")
         variant = 0
     g = torch.Generator().manual_seed(B * 7 + H + W)
     frames = torch.randint(0, 256, (B, H, W), generator=g, dtype=torch.uint8)

@@ -22,7 +22,7 @@ CASES = [(1, "", "", "", "tile (stem_fused)"), (0, "1", "", "", "rows, 8 epilogu
          (0, "1", "", "", "rows, 8 epilogue warps"), (0, "", "", "", "rows, 16 epilogue warps"),
          (0, "1", "", "2", "rows, 8 epilogue warps, no MMA"), (0, "1", "", "3", "rows, 8 epilogue warps, no loads, no MMA")]
 for variant, cg2, raw, dbg, name in CASES:
-    os.environ["BV_SR_CG2"] = cg2
+    os.environ["BV_SR_CG4"] = "" if cg2 else "1"
     os.environ["BV_SR_RAW"] = raw
     os.environ["BV_SR_DEBUG"] = dbg or "0"
     for i in range(3):
