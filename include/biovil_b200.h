@@ -179,6 +179,12 @@ int32_t bv_pair_gemm_test(const void* a, const void* w, int32_t m, int32_t n, in
 int32_t bv_stem_u8_nhwc(const void* frames, int32_t batch, int32_t height, int32_t width, const bv_conv* host_w8,
                         void* out, int32_t variant, bv_stream stream);
 
+/* The row-streaming stem with layer1.0's conv1 fused in (torchvision Bottleneck.forward conv1 -> bn1 -> relu on the
+ * max-pool output, resnet.py:38-39): out = max-pool output as above, out1 = relu(conv1x1(out) + bias) bf16 NHWC
+ * [B][H/4][W/4][64]; host_c1 is a 64 -> 64 1x1 bv_conv.  What bv_forward launches for 8-bit frames. */
+int32_t bv_stem_conv1_u8_nhwc(const void* frames, int32_t batch, int32_t height, int32_t width, const bv_conv* host_w8,
+                              const bv_conv* host_c1, void* out, void* out1, bv_stream stream);
+
 #ifdef __cplusplus
 }
 #endif

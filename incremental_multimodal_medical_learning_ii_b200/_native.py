@@ -67,7 +67,7 @@ EXPORTED_SYMBOLS = (
     "bv_set_prompts", "bv_forward", "bv_score", "bv_last_forward_launches", "bv_set_profile", "bv_get_profile",
     "bv_conv2d_nhwc", "bv_conv_chain_nhwc", "bv_smooth_heatmaps",
     "bv_resize_workspace_bytes", "bv_resize_center_crop_u8", "bv_pair_gemm_test", "bv_l1_block_nhwc",
-    "bv_stem_u8_nhwc",
+    "bv_stem_u8_nhwc", "bv_stem_conv1_u8_nhwc",
 )
 
 _lib = None
@@ -143,6 +143,9 @@ def lib() -> ctypes.CDLL:
                                    POINTER(BvConv), c_void_p, c_void_p]
     l.bv_stem_u8_nhwc.restype = c_int32
     l.bv_stem_u8_nhwc.argtypes = [c_void_p, c_int32, c_int32, c_int32, POINTER(BvConv), c_void_p, c_int32, c_void_p]
+    l.bv_stem_conv1_u8_nhwc.restype = c_int32
+    l.bv_stem_conv1_u8_nhwc.argtypes = [c_void_p, c_int32, c_int32, c_int32, POINTER(BvConv), POINTER(BvConv), c_void_p,
+                                        c_void_p, c_void_p]
     l.bv_pair_gemm_test.restype = c_int32
     l.bv_pair_gemm_test.argtypes = [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p]
     l.bv_smooth_heatmaps.restype = c_int32

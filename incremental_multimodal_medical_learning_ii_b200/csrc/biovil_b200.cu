@@ -126,11 +126,16 @@ bool env_flag(const char* name) {
 
 // Row-streaming stem: 8 epilogue warps of 32 channels (0.566 ms per 512 frames alone); BV_SR_CG4 = 16 warps of 16
 // channels (0.594 ms: the kernel is bound by instruction throughput, not latency, and more warps add per-warp overhead).
+// With p.out1 set the kernel also applies layer1.0's conv1 (1x1, 64 -> 64, + bn1 + ReLU) to every pooled pixel.
 void launch_stem_rows(const bv::StemRowsParams& p, int grid, cudaStream_t st) {
-    if (env_flag("BV_SR_CG4"))
-        bv::stem_rows_kernel<4><<<grid, bv::sr_threads(4), bv::kSrSmemBytes, st>>>(p);
-    else
-        bv::stem_rows_kernel<2><<<grid, bv::sr_threads(2), bv::kSrSmemBytes, st>>>(p);
+    const bool c1 = p.out1 != nullptr;
+    if (env_flag("BV_SR_CG4")) {
+        if (c1) bv::stem_rows_kernel<4, true><<<grid, bv::sr_threads(4), bv::sr_smem_bytes(true), st>>>(p);
+        else bv::stem_rows_kernel<4, false><<<grid, bv::sr_threads(4), bv::sr_smem_bytes(false), st>>>(p);
+    } else {
+        if (c1) bv::stem_rows_kernel<2, true><<<grid, bv::sr_threads(2), bv::sr_smem_bytes(true), st>>>(p);
+        else bv::stem_rows_kernel<2, false><<<grid, bv::sr_threads(2), bv::sr_smem_bytes(false), st>>>(p);
+    }
 }
 
 struct ConvOperand {
@@ -222,10 +227,14 @@ int device_setup() {
         BV_CUDA(cudaFuncSetAttribute(bv::head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
         BV_CUDA(cudaFuncSetAttribute(bv::stem_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      bv::kStemSmemRequest));
-        BV_CUDA(cudaFuncSetAttribute(bv::stem_rows_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     bv::kSrSmemBytes));
-        BV_CUDA(cudaFuncSetAttribute(bv::stem_rows_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     bv::kSrSmemBytes));
+        BV_CUDA(cudaFuncSetAttribute(bv::stem_rows_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     bv::sr_smem_bytes(false)));
+        BV_CUDA(cudaFuncSetAttribute(bv::stem_rows_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     bv::sr_smem_bytes(false)));
+        BV_CUDA(cudaFuncSetAttribute(bv::stem_rows_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     bv::sr_smem_bytes(true)));
+        BV_CUDA(cudaFuncSetAttribute(bv::stem_rows_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     bv::sr_smem_bytes(true)));
         g_attr_set = true;
     }
     g_num_sms = prop.multiProcessorCount;
@@ -854,7 +863,16 @@ static int build_plan(bv_handle* h, const void* frames, int dtype, int B, int C,
     uint8_t* nxt = buf_b;
     int ch = H / 4, cw = W / 4;
     int blk = 0;
-    bool t1_ready = false;  // this block's conv1 output was already produced by the previous block's chained kernel
+    // 8-bit frames: the row-streaming stem kernel can also produce layer1.0's conv1 output (BV_STEM_C1).  Off by default:
+    // measured 0.91 ms against 0.565 + 0.30 ms for the two kernels (the fused form gives up one of four TMEM stages,
+    // and its second epilogue competes with the first for the instruction slots that bound the kernel)
+    const bool stem_rows = (dtype == BV_DTYPE_U8) && h->w.stem_u8_k8.w != nullptr && !env_flag("BV_NO_FUSED_STEM") &&
+                           !env_flag("BV_STEM_V1");
+    const bv_conv& l1c1 = h->w.conv1[0];
+    const bool stem_c1 = stem_rows && env_flag("BV_STEM_C1") && l1c1.cin == 64 && l1c1.cout == 64 && l1c1.r == 1 &&
+                         l1c1.s == 1 && l1c1.stride == 1 && l1c1.pad == 0 && (H / 4) % 2 == 0;
+    uint8_t* stem_t1 = t1;
+    bool t1_ready = stem_c1;  // this block's conv1 output was already produced by the previous kernel (chain / stem)
     for (int li = 0; li < 4; ++li) {
         for (int bi = 0; bi < kLayerBlocks[li]; ++bi, ++blk) {
             const bv_conv& c1 = h->w.conv1[blk];
@@ -947,6 +965,11 @@ static int build_plan(bv_handle* h, const void* frames, int dtype, int B, int C,
         h->stem_rows.H = H;
         h->stem_rows.W = W;
         h->stem_rows.strips_x = (W / 4 + bv::kSrStripPx - 1) / bv::kSrStripPx;
+        if (stem_c1) {
+            h->stem_rows.w1 = reinterpret_cast<const __nv_bfloat16*>(l1c1.w);
+            h->stem_rows.b1 = l1c1.bias;
+            h->stem_rows.out1 = reinterpret_cast<__nv_bfloat16*>(stem_t1);
+        }
     }
     (void)frames;
     return BV_OK;
@@ -995,8 +1018,10 @@ int32_t bv_forward(bv_handle* h, const void* frames, int32_t dtype, int32_t B, i
         launch_stem_rows(h->stem_rows, grid, st);
         BV_CUDA(cudaGetLastError());
         ++launches;
-        prof_mark(h, st, "stem_rows conv7x7+bn+relu+maxpool", 2.0 * B * H2 * W2 * 64 * 49,
-                  (double)B * H * W + (double)B * H4 * W4 * 64 * 2);
+        const bool c1 = h->stem_rows.out1 != nullptr;
+        prof_mark(h, st, c1 ? "stem_rows conv7x7+bn+relu+maxpool+conv1x1(64)" : "stem_rows conv7x7+bn+relu+maxpool",
+                  2.0 * B * H2 * W2 * 64 * 49 + (c1 ? 2.0 * B * H4 * W4 * 64 * 64 : 0.0),
+                  (double)B * H * W + (double)B * H4 * W4 * 64 * 2 * (c1 ? 2 : 1));
     } else if (h->use_fused_stem) {
         // 1-3 fused: conv7x7/2 + BN + ReLU + max-pool in one kernel, frame bytes in, layer1 input out
         h->stem.frames = reinterpret_cast<const uint8_t*>(frames);
@@ -1396,6 +1421,32 @@ int32_t bv_stem_u8_nhwc(const void* frames, int32_t B, int32_t H, int32_t W, con
     } else {
         return fail(BV_ERR_INVALID, "unknown stem variant %d", variant);
     }
+    BV_CUDA(cudaGetLastError());
+    return BV_OK;
+}
+
+int32_t bv_stem_conv1_u8_nhwc(const void* frames, int32_t B, int32_t H, int32_t W, const bv_conv* w8, const bv_conv* c1,
+                              void* out, void* out1, bv_stream stream) {
+    if (!frames || !w8 || !w8->w || !c1 || !c1->w || !c1->bias || !out || !out1) return fail(BV_ERR_INVALID, "null argument");
+    if (B <= 0 || H <= 0 || W <= 0 || H % 32 || W % 32) return fail(BV_ERR_INVALID, "H, W must be multiples of 32");
+    if (c1->cin != 64 || c1->cout != 64 || c1->r != 1 || c1->s != 1 || c1->stride != 1 || c1->pad != 0)
+        return fail(BV_ERR_INVALID, "the fused conv1 must be 1x1, 64 -> 64, stride 1");
+    if (reinterpret_cast<uintptr_t>(frames) & 7u) return fail(BV_ERR_INVALID, "frames must be 8-byte aligned");
+    int rc = device_setup();
+    if (rc) return rc;
+    bv::StemRowsParams p{};
+    p.frames = reinterpret_cast<const uint8_t*>(frames);
+    p.w = reinterpret_cast<const __nv_bfloat16*>(w8->w);
+    p.out = reinterpret_cast<__nv_bfloat16*>(out);
+    p.B = B;
+    p.H = H;
+    p.W = W;
+    p.strips_x = (W / 4 + bv::kSrStripPx - 1) / bv::kSrStripPx;
+    p.w1 = reinterpret_cast<const __nv_bfloat16*>(c1->w);
+    p.b1 = c1->bias;
+    p.out1 = reinterpret_cast<__nv_bfloat16*>(out1);
+    if (const char* d = getenv("BV_SR_DEBUG")) p.debug = atoi(d);
+    launch_stem_rows(p, std::min(B * p.strips_x, g_num_sms), reinterpret_cast<cudaStream_t>(stream));
     BV_CUDA(cudaGetLastError());
     return BV_OK;
 }

@@ -38,13 +38,18 @@ constexpr int kSrGroupBytes = 4 * kSrRowBytes;
 constexpr int kSrRawStages = 8;                   // 1 KB each (4 / 8 / 16 stages measured equal)
 constexpr int kSrRawPitch = 256;                  // bytes per raw input row in a box
 constexpr int kSrRawBytes = 4 * kSrRawPitch;
-constexpr int kSrTmemStages = 4;                  // x 128 columns (two conv rows x 64 channels)
+constexpr int sr_tmem_stages(bool c1) { return c1 ? 3 : 4; }   // x 128 columns (two conv rows x 64 channels); the fused
+                                                               // conv1 takes the last 128 columns (2 x 64)
+constexpr int kSrALbo = 2048 + 64;                // pooled-pixel A operand of the fused conv1: chunk stride (the 64 skews
+                                                  // the banks of the even / odd lanes that store chunk pairs)
+constexpr int kSrABufBytes = 8 * kSrALbo;         // 128 pooled pixels x 64 channels, chunk-major
+constexpr int kSrW1Bytes = 64 * 64 * 2;
 constexpr int kSrChunks = 10;                     // K chunks of 8: ones + 9 input rows
 constexpr int kSrWBytes = kSrChunks * 128 * 16;   // B operand: chunk-major, 128 rows x 16 B per chunk
 __host__ __device__ constexpr int sr_threads(int cg) { return (6 + 4 * cg) * 32; }   // CG = channel groups of the epilogue (64 / CG channels per warp)
 constexpr int kSrOnesBytes = 128 * 16;
-constexpr int kSrSmemBytes =
-    kSrOnesBytes + kSrNG * kSrGroupBytes + kSrWBytes + kSrRawStages * kSrRawBytes + 512;
+constexpr int kSrBaseBytes = kSrOnesBytes + kSrNG * kSrGroupBytes + kSrWBytes + kSrRawStages * kSrRawBytes + 512;
+constexpr int sr_smem_bytes(bool c1) { return kSrBaseBytes + (c1 ? 2 * kSrABufBytes + kSrW1Bytes + 256 : 0); }
 
 struct StemRowsParams {
     const uint8_t* frames;        // u8 [B][H][W], 8-byte aligned
@@ -52,7 +57,11 @@ struct StemRowsParams {
     __nv_bfloat16* out;           // [B][H/4][W/4][64]
     int B, H, W;
     int strips_x;                 // ceil((W/4) / 60)
-    int debug;                    // BV_SR_DEBUG bisect bits (1 no loads, 2 no MMA)
+    // fused layer1.0 conv1 (1x1, 64 -> 64, + folded bn1 + ReLU; resnet.py:39 / torchvision Bottleneck.forward): C1 kernels only
+    const __nv_bfloat16* w1;      // [64 out][64 in] bf16
+    const float* b1;              // [64]
+    __nv_bfloat16* out1;          // [B][H/4][W/4][64]
+    int debug;                    // BV_SR_DEBUG bisect bits (1 no loads, 2 no MMA; fused conv1: 4 no conv1 stores, 8 no conv1 epilogue, 16 no A-buffer stores)
 };
 
 // K-major descriptor WITHOUT swizzle (cute::UMMA LayoutType::SWIZZLE_NONE, canonical layout
@@ -99,9 +108,10 @@ __device__ __forceinline__ void sr_tmem_ld(uint32_t taddr, uint32_t (&r)[N]) {
     }
 }
 
-template <int CG>
+template <int CG, bool C1>
 __global__ void __launch_bounds__(sr_threads(CG), 1) stem_rows_kernel(const __grid_constant__ StemRowsParams p) {
     constexpr int kThreads = sr_threads(CG);
+    constexpr int kSrTmemStages = C1 ? 3 : 4;
     constexpr int kCh = 64 / CG;        // channels per epilogue warp
     constexpr int kPk = kCh / 2;        // packed bf16x2 registers per conv row
     extern __shared__ __align__(1024) uint8_t smem[];   // keep the shared address space visible (LDS/STS, not LD.E)
@@ -117,7 +127,14 @@ __global__ void __launch_bounds__(sr_threads(CG), 1) stem_rows_kernel(const __gr
     uint64_t* e_empty = e_full + kSrNG;
     uint64_t* t_full = e_empty + kSrNG;
     uint64_t* t_empty = t_full + kSrTmemStages;
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(t_empty + kSrTmemStages);
+    uint64_t* a_full = t_empty + 4;          // fused conv1: pooled-pixel A buffers (2), conv1 accumulators (2)
+    uint64_t* a_empty = a_full + 2;
+    uint64_t* c1_full = a_empty + 2;
+    uint64_t* c1_empty = c1_full + 2;
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(c1_empty + 2);
+    uint8_t* abuf = smem + kSrBaseBytes;     // C1 only
+    uint8_t* w1sm = abuf + 2 * kSrABufBytes;
+    float* b1sm = reinterpret_cast<float*>(w1sm + kSrW1Bytes);
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5;
@@ -140,6 +157,14 @@ __global__ void __launch_bounds__(sr_threads(CG), 1) stem_rows_kernel(const __gr
             mbar_init(t_full + i, 1);
             mbar_init(t_empty + i, 4 * CG);
         }
+        if (C1) {
+            for (int i = 0; i < 2; ++i) {
+                mbar_init(a_full + i, 4 * CG * 32);
+                mbar_init(a_empty + i, 1);
+                mbar_init(c1_full + i, 1);
+                mbar_init(c1_empty + i, 4 * CG);
+            }
+        }
         fence_barrier_init();
     }
     // constant operands, written once through the generic proxy
@@ -152,6 +177,13 @@ __global__ void __launch_bounds__(sr_threads(CG), 1) stem_rows_kernel(const __gr
         if (c == 0) v = *reinterpret_cast<const uint4*>(p.w + (n & 63) * 64 + 56);
         else if (r >= 0 && r < 7) v = *reinterpret_cast<const uint4*>(p.w + (n & 63) * 64 + r * 8);
         *reinterpret_cast<uint4*>(wsm + c * 2048 + n * 16) = v;
+    }
+    if (C1) {
+        for (int i = tid; i < 8 * 64; i += kThreads) {   // conv1 weights, chunk-major: 64 rows x 16 B per chunk
+            const int c = i >> 6, n = i & 63;
+            *reinterpret_cast<uint4*>(w1sm + c * 1024 + n * 16) = *reinterpret_cast<const uint4*>(p.w1 + n * 64 + c * 8);
+        }
+        if (tid < 64) b1sm[tid] = p.b1[tid];
     }
     fence_proxy_async_smem();
     if (warp == 5) {
@@ -223,7 +255,23 @@ __global__ void __launch_bounds__(sr_threads(CG), 1) stem_rows_kernel(const __gr
         if (elect_one()) {
             constexpr uint32_t idesc = umma_idesc_bf16_f32(128, 128);
             const uint32_t ones_a = smem_u32(ones), ring_a = smem_u32(ring), w_a = smem_u32(wsm);
-            uint32_t gbase = 0, sc = 0;
+            uint32_t gbase = 0, sc = 0, su = 0;   // su: pairs of pooled rows ("super-steps"), counted across strips
+            uint32_t next_c1 = 0;                 // first super-step whose conv1 has not been issued yet
+            // conv1 of super-step x: [128 pooled pixels x 64] x W1^T, A operand written by the epilogue warps
+            auto issue_c1 = [&](uint32_t x) {
+                const uint32_t ab = x & 1u, ph = (x >> 1) & 1u;
+                mbar_wait(a_full + ab, ph);
+                mbar_wait(c1_empty + ab, ph ^ 1u);
+                tc_fence_after();
+                const uint32_t a_a = smem_u32(abuf) + ab * kSrABufBytes, w1_a = smem_u32(w1sm);
+                const uint32_t d1 = tmem_base + 384u + ab * 64u;
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    umma_bf16_ss(d1, umma_desc_k_none(a_a + 2 * k * kSrALbo, kSrALbo, 128),
+                                 umma_desc_k_none(w1_a + 2 * k * 1024, 1024, 128), umma_idesc_bf16_f32(128, 64), k ? 1u : 0u);
+                umma_commit(c1_full + ab);
+                umma_commit(a_empty + ab);
+            };
             for (int strip = blockIdx.x; strip < nstrips; strip += gridDim.x, gbase += groups_per_strip) {
                 for (int g = 0; g < Hp; ++g, ++sc) {
                     // group G = gbase + j + 2 holds input rows 4j+2 .. 4j+5; this step reads j = g-2 (last row), g-1, g
@@ -258,15 +306,56 @@ __global__ void __launch_bounds__(sr_threads(CG), 1) stem_rows_kernel(const __gr
                         umma_commit(e_empty + G1 % kSrNG);
                         umma_commit(e_empty + G2 % kSrNG);
                     }
+                    if (C1) {
+                        // conv1 of a finished super-step is issued as soon as the epilogue has written its A buffer; the
+                        // main MMAs never wait for it (they run up to three pooled rows ahead of the epilogue)
+                        su += static_cast<uint32_t>(g & 1);
+                        if (next_c1 < su && mbar_try_wait(a_full + (next_c1 & 1u), (next_c1 >> 1) & 1u)) issue_c1(next_c1++);
+                    }
                 }
             }
+            if (C1)
+                while (next_c1 < su) issue_c1(next_c1++);
         }
         __syncwarp();
     } else {
         // ---------------- epilogue: TMEM -> bf16 -> 3x3/2 max-pool in registers -> ReLU -> global ----------------
         const int q = warp & 3;            // TMEM lane quarter
         const int cg = (warp - 6) >> 2;    // channel group
-        uint32_t sc = 0;
+        uint32_t sc = 0, su = 0;
+        int pb = 0, ps = 0, pg0 = 0;       // frame, strip column and first pooled row of the previous super-step
+        // second epilogue (fused conv1): accumulator lane m <-> pooled pixel (row pg0 + m / 64, strip column m % 64)
+        auto conv1_out = [&](uint32_t x) {
+            const uint32_t cb = x & 1u;
+            mbar_wait(c1_full + cb, (x >> 1) & 1u);
+            tc_fence_after();
+            uint32_t r[kCh];
+            sr_tmem_ld<kCh>(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + 384u + cb * 64u + static_cast<uint32_t>(cg * kCh), r);
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(c1_empty + cb);
+            if (p.debug & 8) return;
+            const int m = 32 * q + lane, lpx = m & 63;
+            const int pxx = kSrStripPx * ps + lpx;
+            const bool ok = lpx < kSrStripPx && pxx < Wp;
+            __nv_bfloat16* dst = p.out1 + ((static_cast<size_t>(pb) * Hp + pg0 + (m >> 6)) * Wp + pxx) * 64 + cg * kCh;
+#pragma unroll
+            for (int c = 0; c < kCh / 8; ++c) {
+                const float4 ba = *reinterpret_cast<const float4*>(b1sm + cg * kCh + c * 8);
+                const float4 bb = *reinterpret_cast<const float4*>(b1sm + cg * kCh + c * 8 + 4);
+                const float bias[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
+                uint4 o;
+                uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const __nv_bfloat162 h = __floats2bfloat162_rn(__uint_as_float(r[c * 8 + 2 * e]) + bias[2 * e],
+                                                                   __uint_as_float(r[c * 8 + 2 * e + 1]) + bias[2 * e + 1]);
+                    ow[e] = bf16x2_max(*reinterpret_cast<const uint32_t*>(&h), 0u);
+                }
+                if (ok && !(p.debug & 4)) *reinterpret_cast<uint4*>(dst + c * 8) = o;
+            }
+        };
         for (int strip = blockIdx.x; strip < nstrips; strip += gridDim.x) {
             const int b = strip / p.strips_x, s = strip - b * p.strips_x;
             // local conv column 0 of strip 0 is conv column -1: max-pool padding, never wins
@@ -312,6 +401,12 @@ __global__ void __launch_bounds__(sr_threads(CG), 1) stem_rows_kernel(const __gr
                 // even lane 2j holds pooled pixel j (kCh channels = kCh / 8 chunks of 16 bytes); the odd neighbour takes
                 // the odd chunks so that every store instruction writes whole 32-byte sectors
                 __nv_bfloat16* dst = p.out + ((static_cast<size_t>(b) * Hp + g) * Wp + px) * 64 + cg * kCh + (lane & 1) * 8;
+                uint8_t* arow = nullptr;
+                if (C1) {
+                    if (!(g & 1)) mbar_wait(a_empty + (su & 1u), ((su >> 1) & 1u) ^ 1u);   // conv1 of super-step su-2 has read it
+                    arow = abuf + (su & 1u) * kSrABufBytes + (cg * (kCh / 8) + (lane & 1)) * kSrALbo +
+                           (64 * (g & 1) + 15 * q + (lane >> 1)) * 16;
+                }
 #pragma unroll
                 for (int i = 0; i < kCh / 16; ++i) {
                     uint4 o;
@@ -322,9 +417,20 @@ __global__ void __launch_bounds__(sr_threads(CG), 1) stem_rows_kernel(const __gr
                         ow[e] = (lane & 1) ? t : v[2 * i * 4 + e];
                     }
                     if (store_ok) *reinterpret_cast<uint4*>(dst + i * 16) = o;
+                    if (C1 && (lane >> 1) < 15 && !(p.debug & 16)) *reinterpret_cast<uint4*>(arow + 2 * i * kSrALbo) = o;
+                }
+                if (C1 && (g & 1)) {
+                    fence_proxy_async_smem();
+                    mbar_arrive(a_full + (su & 1u));
+                    if (su >= 1) conv1_out(su - 1);
+                    pb = b;
+                    ps = s;
+                    pg0 = g - 1;
+                    ++su;
                 }
             }
         }
+        if (C1 && su >= 1) conv1_out(su - 1);
     }
 
     tc_fence_before();

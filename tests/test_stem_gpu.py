@@ -90,3 +90,53 @@ def test_stem_gaussian_one_ulp_and_variants_agree(shape):
     mism = (outs[0] != outs[1]).float().mean().item()
     print(f"rows vs tile kernel {shape}: {mism:.2e} of the outputs differ (by one bf16 ulp)")
     assert mism < 1e-2
+
+
+@pytest.mark.parametrize("cg4", [False, True], ids=["epi8", "epi16"])
+@pytest.mark.parametrize("integer", [True, False], ids=["int", "gauss"])
+@pytest.mark.parametrize("shape", [(1, 32, 32), (3, 96, 160), (2, 480, 480), (1, 512, 512), (80, 480, 480)],
+                         ids=lambda s: "x".join(map(str, s)))
+def test_stem_with_fused_conv1(shape, integer, cg4, monkeypatch):
+    """Row-streaming stem + layer1.0 conv1 (1x1 64->64, +bias, ReLU) in one kernel: the max-pool output must equal the
+    un-fused kernel's bit for bit, and the conv1 output must equal fp32 conv + bias + ReLU + bf16 rounding of it
+    (integer operands: exact; Gaussian: one bf16 ulp)."""
+    from incremental_multimodal_medical_learning_ii_b200 import _native as N
+    from incremental_multimodal_medical_learning_ii_b200 import packing
+    if cg4:
+        monkeypatch.setenv("BV_SR_CG4", "1")
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    B, H, W = shape
+    g = torch.Generator().manual_seed(B + H * 5 + W)
+    frames = torch.randint(0, 16 if integer else 256, (B, H, W), generator=g, dtype=torch.uint8)
+    if integer:
+        w = torch.randint(-1, 2, (64, 7, 7), generator=g).float() * (torch.rand(64, 7, 7, generator=g) < 0.1)
+        bias = torch.randint(-60, 60, (64,), generator=g).float()
+        w1 = (torch.randint(-1, 2, (64, 64, 1, 1), generator=g).float() * (torch.rand(64, 64, 1, 1, generator=g) < 0.2))
+        b1 = torch.randint(-3, 4, (64,), generator=g).float()
+    else:
+        w = (torch.randn(64, 7, 7, generator=g) * (49 ** -0.5) / 255.0)
+        bias = torch.randn(64, generator=g) * 0.3
+        w1 = torch.randn(64, 64, 1, 1, generator=g) * 64 ** -0.5
+        b1 = torch.randn(64, generator=g) * 0.3
+    w, w1 = w.to(torch.bfloat16), w1.to(torch.bfloat16)
+    conv, keep, b_eff = _pack_w8(w.float(), bias, DEV)
+    c1 = packing.pack_single_conv(w1, b1, 1, 0, torch.device(DEV))
+    plain = _run(frames, conv, 0)
+    lib = N.lib()
+    out = torch.full((B, H // 4, W // 4, 64), float("nan"), device=DEV, dtype=torch.bfloat16)
+    out1 = torch.full((B, H // 4, W // 4, 64), float("nan"), device=DEV, dtype=torch.bfloat16)
+    fr = frames.to(DEV).contiguous()
+    N.check(lib.bv_stem_conv1_u8_nhwc(N.ptr(fr), B, H, W, ctypes.byref(conv), ctypes.byref(c1[0]), N.ptr(out), N.ptr(out1),
+                                      N.current_stream_handle(torch.device(DEV))))
+    torch.cuda.synchronize()
+    assert torch.equal(out, plain)
+    if integer:   # pooled values must be exact bf16 integers for the second conv to be exact
+        assert out.float().abs().max() <= 256
+    ref1 = torch.relu(F.conv2d(out.double().permute(0, 3, 1, 2), w1.double().to(DEV), b1.double().to(DEV)))
+    ref1 = ref1.permute(0, 2, 3, 1).float()
+    assert not torch.isnan(out1.float()).any()
+    if integer:
+        assert torch.equal(out1, ref1.to(torch.bfloat16)), (out1.float() - ref1).abs().max().item()
+    else:
+        assert ((out1.float() - ref1).abs() <= ref1.abs() * 2.0 ** -7 + 1e-3).all(), (out1.float() - ref1).abs().max().item()

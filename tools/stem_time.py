@@ -37,3 +37,28 @@ for variant, cg2, raw, dbg, name in CASES:
     ms = e0.elapsed_time(e1) / n
     gb = (B * H * W + out.numel() * 2) / 1e9
     print(f"{name}: {ms:.3f} ms per launch, {gb / ms * 1e3:.0f} GB/s algorithmic")
+
+# fused conv1 variant (bv_stem_conv1_u8_nhwc): max-pool output + layer1.0 conv1 output from one kernel
+from incremental_multimodal_medical_learning_ii_b200 import packing  # noqa: E402
+os.environ["BV_SR_DEBUG"] = "0"
+c1 = packing.pack_single_conv((torch.randn(64, 64, 1, 1, generator=g) / 8).to(torch.bfloat16), torch.randn(64, generator=g), 1, 0,
+                              torch.device(T.DEV))
+out1 = torch.empty_like(out)
+for cg4, dbg, name in (("", "0", "rows + conv1, 8 epilogue warps"), ("1", "0", "rows + conv1, 16 epilogue warps"),
+                       ("", "4", "rows + conv1, 8 warps, no conv1 stores"), ("", "8", "rows + conv1, 8 warps, no conv1 epilogue math/stores"),
+                       ("", "16", "rows + conv1, 8 warps, no A-buffer stores"), ("", "28", "rows + conv1, 8 warps, none of the three")):
+    os.environ["BV_SR_CG4"] = cg4
+    os.environ["BV_SR_DEBUG"] = dbg
+    for i in range(3):
+        N.check(lib.bv_stem_conv1_u8_nhwc(N.ptr(frames[i & 1]), B, H, W, ctypes.byref(conv), ctypes.byref(c1[0]), N.ptr(out),
+                                          N.ptr(out1), st))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(20):
+        N.check(lib.bv_stem_conv1_u8_nhwc(N.ptr(frames[i & 1]), B, H, W, ctypes.byref(conv), ctypes.byref(c1[0]), N.ptr(out),
+                                          N.ptr(out1), st))
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 20
+    gb = (B * H * W + 2 * out.numel() * 2) / 1e9
+    print(f"{name}: {ms:.3f} ms per launch, {gb / ms * 1e3:.0f} GB/s algorithmic")
