@@ -1,5 +1,5 @@
 """One warm-up forward + one forward of configs[1] (batch 512, 1x480x480 u8) for use under ncu:
-    ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum -k regex:'conv_gemm|chain_gemm|conv3x3_tap3|l1_block|stem_|head' -s 44 -c 44 ...
+    ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum -k regex:'conv_gemm|chain_gemm|conv3x3_tap3|l1_block|stem_|head' -s 45 -c 45 ... (one forward = 45 launches: stem, 43 conv kernels, head)
 Usage: python tools/ncu_step.py [batch] [forwards]"""
 import os
 import sys
