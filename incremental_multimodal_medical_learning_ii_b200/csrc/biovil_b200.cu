@@ -145,14 +145,16 @@ struct ConvOperand {
 };
 
 // Kernel configurations <BN, STAGES, NBUF> (see ConvGemmCfg): picked per layer by arithmetic intensity.
-enum ConvCfg { kCfg256Deep = 0, kCfg256Res, kCfg128Res, kCfg128Deep, kCfg64, kCfg64BRes, kCfg64Wide, kCfg64Tap3, kCfg128M2, kNumCfg };
+enum ConvCfg { kCfg256Deep = 0, kCfg256Res, kCfg128Res, kCfg128Deep, kCfg64, kCfg64BRes, kCfg64Wide, kCfg64Tap3, kCfg128M2, kCfg128TR, kNumCfg };
 // kCfg64Tap3 is a different kernel (conv3x3_tap3.cuh): the three horizontal taps of a filter row in one N = 192 MMA
 #define BV_FOR_EACH_CFG(X)                                                                                        \
-    X(kCfg256Deep, 256, 4, 2, false, false, 1, 8) X(kCfg256Res, 256, 3, 5, false, false, 1, 16)                               \
-    X(kCfg128Res, 128, 3, 7, false, false, 1, 16) X(kCfg128Deep, 128, 6, 2, false, false, 1, 16) X(kCfg64, 64, 8, 2, false, false, 1, 16) \
-    X(kCfg64BRes, 64, 6, 2, true, false, 1, 16) X(kCfg64Wide, 64, 6, 2, true, true, 1, 16) X(kCfg128M2, 128, 4, 2, false, false, 2, 16)
-const int kCfgBN[kNumCfg] = {256, 256, 128, 128, 64, 64, 64, 64, 128};
-const int kCfgMT[kNumCfg] = {1, 1, 1, 1, 1, 1, 1, 1, 2};
+    X(kCfg256Deep, 256, 4, 2, false, false, 1, 8, false) X(kCfg256Res, 256, 3, 5, false, false, 1, 16, false)                 \
+    X(kCfg128Res, 128, 3, 7, false, false, 1, 16, false) X(kCfg128Deep, 128, 6, 2, false, false, 1, 16, false)                \
+    X(kCfg64, 64, 8, 2, false, false, 1, 16, false) X(kCfg64BRes, 64, 6, 2, true, false, 1, 16, false)                        \
+    X(kCfg64Wide, 64, 6, 2, true, true, 1, 16, false) X(kCfg128M2, 128, 4, 2, false, false, 2, 16, false)                     \
+    X(kCfg128TR, 128, 4, 2, false, false, 2, 16, true)
+const int kCfgBN[kNumCfg] = {256, 256, 128, 128, 64, 64, 64, 64, 128, 128};
+const int kCfgMT[kNumCfg] = {1, 1, 1, 1, 1, 1, 1, 1, 2, 2};
 
 struct ConvLaunch {
     bv::ConvGemmParams p;
@@ -208,10 +210,10 @@ int device_setup() {
     int rc = resolve_driver();
     if (rc) return rc;
     if (!g_attr_set) {
-#define BV_SET_ATTR(id, BN, ST, NB, BR, WD, MT, EP)                                                 \
-    BV_CUDA(cudaFuncSetAttribute(bv::conv_gemm_kernel<BN, ST, NB, BR, WD, MT, EP>,                  \
+#define BV_SET_ATTR(id, BN, ST, NB, BR, WD, MT, EP, TR)                                             \
+    BV_CUDA(cudaFuncSetAttribute(bv::conv_gemm_kernel<BN, ST, NB, BR, WD, MT, EP, TR>,              \
                                  cudaFuncAttributeMaxDynamicSharedMemorySize,                       \
-                                 bv::ConvGemmCfg<BN, ST, NB, BR, WD, MT, EP>::kSmemBytes));
+                                 bv::ConvGemmCfg<BN, ST, NB, BR, WD, MT, EP, TR>::kSmemBytes));
         BV_FOR_EACH_CFG(BV_SET_ATTR)
 #undef BV_SET_ATTR
 #define BV_SET_CHAIN_ATTR(id, N2, ST, NB)                                                              \
@@ -272,12 +274,15 @@ int build_conv(ConvLaunch* L, int B, const ConvOperand* ops, int nops, const voi
     if (cfg == kCfg64BRes && wide_ok && !env_flag("BV_NO_WIDE")) cfg = kCfg64Wide;
     // long-K 128-wide layers without residual (layer2's 3x3): two m-tiles share every weight stage
     if (cfg == kCfg128Deep && total_kblocks >= 8 && !residual && !out_fp32 && !env_flag("BV_NO_M2")) cfg = kCfg128M2;
+    // ... and when the layer is exactly 128 wide the tile is computed transposed (weights as the A operand, N = 256 pixels)
+    const bool tr_ok = N == 128 && nops == 1 && !residual && !out_fp32;
+    if (cfg == kCfg128M2 && tr_ok && !env_flag("BV_NO_TR")) cfg = kCfg128TR;
     const bool tap3_ok = wide_ok && c0.cin == 64;
     if (cfg == kCfg64Wide && tap3_ok && !env_flag("BV_NO_TAP3")) cfg = kCfg64Tap3;
     if (const char* force = getenv("BV_FORCE_CFG")) {
         const int f = atoi(force);
         if (f >= 0 && f < kNumCfg && N % kCfgBN[f] == 0 &&
-            (f != kCfg64BRes || (N == 64 && total_kblocks <= bv::kMaxResidentKB)) && (f != kCfg128M2 || (!residual && !out_fp32)))
+            (f != kCfg64BRes || (N == 64 && total_kblocks <= bv::kMaxResidentKB)) && (f != kCfg128M2 || (!residual && !out_fp32)) && (f != kCfg128TR || tr_ok))
             cfg = f;
     }
     if (cfg == kCfg64Wide && !wide_ok) cfg = kCfg64;
@@ -359,11 +364,11 @@ int launch_conv(const ConvLaunch& L0, cudaStream_t st) {
         L.p.dbg = g_dbg;
     }
     switch (L.cfg) {
-#define BV_LAUNCH(id, BN, ST, NB, BR, WD, MT, EP)                                                         \
+#define BV_LAUNCH(id, BN, ST, NB, BR, WD, MT, EP, TR)                                                     \
     case id:                                                                                              \
-        bv::conv_gemm_kernel<BN, ST, NB, BR, WD, MT, EP>                                                  \
-            <<<L.grid, bv::ConvGemmCfg<BN, ST, NB, BR, WD, MT, EP>::kThreads,                             \
-               bv::ConvGemmCfg<BN, ST, NB, BR, WD, MT, EP>::kSmemBytes, st>>>(L.p);                       \
+        bv::conv_gemm_kernel<BN, ST, NB, BR, WD, MT, EP, TR>                                              \
+            <<<L.grid, bv::ConvGemmCfg<BN, ST, NB, BR, WD, MT, EP, TR>::kThreads,                         \
+               bv::ConvGemmCfg<BN, ST, NB, BR, WD, MT, EP, TR>::kSmemBytes, st>>>(L.p);                   \
         break;
         BV_FOR_EACH_CFG(BV_LAUNCH)
 #undef BV_LAUNCH

@@ -93,9 +93,16 @@ constexpr int kMaxResidentKB = 9;
 // EPI = epilogue warps (8: two per TMEM lane quarter, 32 columns of a sub-tile each; 16: four per quarter, 16 columns each).
 // The epilogue is a chain of latencies, so memory-bound configurations gain from 16 warps (layer2/3 conv3 + identity:
 // -5..-11 %); the compute-bound 256-wide long-K configuration loses 3-9 % to the extra resident threads and keeps 8.
-template <int BN, int STAGES, int NBUF, bool BRES = false, bool WIDE = false, int MT = 1, int EPI = 16>
+// TR = "transposed" tile for 128-wide layers: the WEIGHTS are the A operand (M = 128 output channels) and the 256 pixels
+// of the stage's two m-tiles the B operand (N = 256).  A 128x128x16 MMA is bound by the 64 B/cycle A-operand read
+// (78 cycles), a 128x256x16 one runs at the math rate (128 cycles for twice the work): -18 % tensor time.  The
+// accumulator is then channel-major (TMEM lane = channel, column = pixel); the epilogue transposes it on the way into
+// the swizzled staging tiles with 2-byte stores (32 per thread and sub-tile, conflict-free: the 32 lanes of a store
+// cover 64 contiguous bytes of one pixel row).
+template <int BN, int STAGES, int NBUF, bool BRES = false, bool WIDE = false, int MT = 1, int EPI = 16, bool TR = false>
 struct ConvGemmCfg {
     static_assert(EPI == 8 || EPI == 16, "epilogue warps");
+    static_assert(!TR || (MT == 2 && BN == 128 && EPI == 16 && NBUF == 2), "transposed tiles: 128 channels x 2 m-tiles");
     static constexpr int kEpiWarps = EPI;
     static constexpr int kThreads = gemm_threads(EPI);
     static_assert(!WIDE || BRES, "the wide 3x3 mode keeps the weights resident");
@@ -128,9 +135,9 @@ __device__ __forceinline__ void tmem_ld_32x16b(uint32_t taddr, uint32_t (&r)[16]
         : "memory");
 }
 
-template <int BN, int STAGES, int NBUF, bool BRES = false, bool WIDE = false, int MT = 1, int EPI = 16>
+template <int BN, int STAGES, int NBUF, bool BRES = false, bool WIDE = false, int MT = 1, int EPI = 16, bool TR = false>
 __global__ void __launch_bounds__(gemm_threads(EPI), 1) conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
-    using Cfg = ConvGemmCfg<BN, STAGES, NBUF, BRES, WIDE, MT, EPI>;
+    using Cfg = ConvGemmCfg<BN, STAGES, NBUF, BRES, WIDE, MT, EPI, TR>;
     constexpr int kEpiWarps = EPI;
     constexpr int kDmaWarp = 2 + EPI;
     constexpr int kWarpCols = kChunkCols / (EPI / 4);   // columns of a 64-column sub-tile per epilogue warp
@@ -345,6 +352,19 @@ __global__ void __launch_bounds__(gemm_threads(EPI), 1) conv_gemm_kernel(const _
                         umma_commit(&empty_bar[stage]);
                         if (kb == total_kb - 1) umma_commit(&tmem_full[acc]);
                     }
+                } else if constexpr (TR) {
+                    if (elect_one()) {
+                        // D[channel, pixel] += W[128 x 16] * X[256 x 16]^T: the two m-tiles of the stage are one contiguous
+                        // 256-row swizzled tile
+                        const uint64_t wdesc = umma_desc_k_sw128(b_base + static_cast<uint32_t>(stage * Cfg::kBBytes));
+                        const uint64_t xdesc = umma_desc_k_sw128(a_base + static_cast<uint32_t>(stage * kAStage));
+#pragma unroll
+                        for (int k = 0; k < kBlockK / 16; ++k)
+                            umma_bf16_ss(d_tmem, wdesc + static_cast<uint64_t>(2 * k), xdesc + static_cast<uint64_t>(2 * k),
+                                         umma_idesc_bf16_f32(128, 256), (kb != 0 || k != 0) ? 1u : 0u);
+                        umma_commit(&empty_bar[stage]);
+                        if (kb == total_kb - 1) umma_commit(&tmem_full[acc]);
+                    }
                 } else if (elect_one()) {
                     const uint64_t bdesc =
                         umma_desc_k_sw128(b_base + static_cast<uint32_t>((BRES ? kb : stage) * Cfg::kBBytes));
@@ -439,6 +459,42 @@ __global__ void __launch_bounds__(gemm_threads(EPI), 1) conv_gemm_kernel(const _
             tc_fence_after();
             const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
                                    static_cast<uint32_t>(acc * Cfg::kAccStageCols);
+            if constexpr (TR) {
+                // lane = output channel (quarters 0,1 -> channel chunk 0, quarters 2,3 -> chunk 1), column = pixel; the
+                // four warps of a quarter take 32 pixels each.  Both channel chunks of an m-tile are written at once.
+                const int cch = quarter >> 1;
+                const int ch_local = (quarter & 1) * 32 + lane;
+                const int pxg = cg;
+                float bias_v = __ldg(p.bias[0] + n_blk * BN + cch * kChunkCols + ch_local);
+                const uint32_t grp = static_cast<uint32_t>(ch_local >> 3), sub = static_cast<uint32_t>(ch_local & 7) * 2u;
+#pragma unroll 1
+                for (int u = 0; u < MT; ++u, g += kChunks) {
+                    const int b0 = g % kBufs, b1 = (g + 1) % kBufs;
+                    mbar_wait(&buf_ready[b0], (g / kBufs) & 1u);
+                    mbar_wait(&buf_ready[b1], ((g + 1) / kBufs) & 1u);
+                    uint32_t v[32];
+                    tmem_ld_32x32(t_row + static_cast<uint32_t>(u * BN + pxg * 32), v);
+                    tmem_ld_wait();
+                    uint8_t* tile = staging + (cch ? b1 : b0) * kStagingBytes + pxg * 32 * 128;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        float f = __uint_as_float(v[j]) + bias_v;
+                        if (p.relu) f = fmaxf(f, 0.0f);
+                        const __nv_bfloat16 h = __float2bfloat16_rn(f);
+                        *reinterpret_cast<__nv_bfloat16*>(tile + j * 128 + ((grp ^ static_cast<uint32_t>(j & 7)) << 4) + sub) = h;
+                    }
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) {
+                        mbar_arrive(&buf_written[b0]);
+                        mbar_arrive(&buf_written[b1]);
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+                continue;
+            }
 #pragma unroll 1
             for (int cu = 0; cu < MT * kChunks; ++cu, ++g) {   // m-tile u of the stage, 64-column sub-tile c
                 const int u = cu / kChunks, c = cu - u * kChunks;

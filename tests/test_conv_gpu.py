@@ -238,3 +238,11 @@ def test_two_m_tiles_per_stage(env, case, monkeypatch):
     assert torch.equal(out, ref), f"max abs diff {(out.float() - ref.float()).abs().max().item()}"
     monkeypatch.setenv("BV_FORCE_CFG", "3")
     assert torch.equal(_conv_native(lib, N, x, conv, relu=True, out_fp32=False), ref)
+    # kCfg128TR: the same stage computed transposed (weights as the A operand, N = 256 pixels, channel-major accumulator
+    # transposed by the epilogue's 2-byte stores); also without ReLU (negative outputs survive)
+    monkeypatch.setenv("BV_FORCE_CFG", "9")
+    out = _conv_native(lib, N, x, conv, relu=True, out_fp32=False)
+    assert not torch.isnan(out.float()).any(), "unwritten rows"
+    assert torch.equal(out, ref), f"transposed tile: max abs diff {(out.float() - ref.float()).abs().max().item()}"
+    ref_lin = ref64.permute(0, 2, 3, 1).float().to(torch.bfloat16)
+    assert torch.equal(_conv_native(lib, N, x, conv, relu=False, out_fp32=False), ref_lin)
