@@ -48,7 +48,8 @@ constexpr int kSrChunks = 10;                     // K chunks of 8: ones + 9 inp
 constexpr int kSrWBytes = kSrChunks * 128 * 16;   // B operand: chunk-major, 128 rows x 16 B per chunk
 __host__ __device__ constexpr int sr_threads(int cg) { return (6 + 4 * cg) * 32; }   // CG = channel groups of the epilogue (64 / CG channels per warp)
 constexpr int kSrOnesBytes = 128 * 16;
-constexpr int kSrBaseBytes = kSrOnesBytes + kSrNG * kSrGroupBytes + kSrWBytes + kSrRawStages * kSrRawBytes + 512;
+constexpr int kSrRowBufBytes = 4 * 512;            // 4 rows x 256 bf16 pixels, double-buffered
+constexpr int kSrBaseBytes = kSrOnesBytes + kSrNG * kSrGroupBytes + kSrWBytes + kSrRawStages * kSrRawBytes + 512 + 2 * kSrRowBufBytes;
 constexpr int sr_smem_bytes(bool c1) { return kSrBaseBytes + (c1 ? 2 * kSrABufBytes + kSrW1Bytes + 256 : 0); }
 
 struct StemRowsParams {
@@ -82,9 +83,16 @@ __device__ __forceinline__ void u8x4_to_bf16x4(uint32_t w, uint32_t& lo, uint32_
     const float f1 = __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7441)) - 8388608.0f;
     const float f2 = __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7442)) - 8388608.0f;
     const float f3 = __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7443)) - 8388608.0f;
-    const __nv_bfloat162 a = __floats2bfloat162_rn(f0, f1), b = __floats2bfloat162_rn(f2, f3);
-    lo = *reinterpret_cast<const uint32_t*>(&a);
-    hi = *reinterpret_cast<const uint32_t*>(&b);
+    // integers below 256 are exact in bf16: the pack is the two high halves
+    lo = __byte_perm(__float_as_uint(f0), __float_as_uint(f1), 0x7632);
+    hi = __byte_perm(__float_as_uint(f2), __float_as_uint(f3), 0x7632);
+}
+
+// two fp32 -> packed bf16x2 (lo in the low half), round to nearest even, ReLU folded into the conversion
+__device__ __forceinline__ uint32_t pack_bf16x2_relu(uint32_t lo_f32, uint32_t hi_f32) {
+    uint32_t d;
+    asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;\n" : "=r"(d) : "f"(__uint_as_float(hi_f32)), "f"(__uint_as_float(lo_f32)));
+    return d;
 }
 
 __device__ __forceinline__ uint32_t bf16x2_max(uint32_t a, uint32_t b) {
@@ -132,6 +140,7 @@ __global__ void __launch_bounds__(sr_threads(CG), 1) stem_rows_kernel(const __gr
     uint64_t* c1_full = a_empty + 2;
     uint64_t* c1_empty = c1_full + 2;
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(c1_empty + 2);
+    uint8_t* rowbf = raw + kSrRawStages * kSrRawBytes + 512;   // bf16 row buffers of the expanders
     uint8_t* abuf = smem + kSrBaseBytes;     // C1 only
     uint8_t* w1sm = abuf + 2 * kSrABufBytes;
     float* b1sm = reinterpret_cast<float*>(w1sm + kSrW1Bytes);
@@ -175,7 +184,12 @@ __global__ void __launch_bounds__(sr_threads(CG), 1) stem_rows_kernel(const __gr
         const int r = (n < 64) ? c - 1 : c - 3;
         uint4 v = make_uint4(0u, 0u, 0u, 0u);
         if (c == 0) v = *reinterpret_cast<const uint4*>(p.w + (n & 63) * 64 + 56);
-        else if (r >= 0 && r < 7) v = *reinterpret_cast<const uint4*>(p.w + (n & 63) * 64 + r * 8);
+        else if (r >= 0 && r < 7) {
+            // the expanded chunks start ONE pixel left of the filter window (4-byte aligned in the bf16 row buffer):
+            // filter column s sits at chunk position s + 1, position 0 carries a zero weight
+            const uint4 w = *reinterpret_cast<const uint4*>(p.w + (n & 63) * 64 + r * 8);
+            v = make_uint4(w.x << 16, __funnelshift_l(w.x, w.y, 16), __funnelshift_l(w.y, w.z, 16), __funnelshift_l(w.z, w.w, 16));
+        }
         *reinterpret_cast<uint4*>(wsm + c * 2048 + n * 16) = v;
     }
     if (C1) {
@@ -223,31 +237,37 @@ __global__ void __launch_bounds__(sr_threads(CG), 1) stem_rows_kernel(const __gr
         }
     } else if (warp <= 4) {
         // ---------------- horizontal expansion + u8 -> bf16 ----------------
+        // phase 1: every pixel of the 4 raw rows is converted ONCE into a bf16 row buffer (thread t: row t / 32, 8 pixels);
+        // phase 2: thread m copies the 8 pixels under conv column lcx(m) (element 2 lcx + 2 onwards: 4-byte aligned) of
+        // each row into E.  The row buffer is double-buffered, so one named barrier per group orders both hazards.
         const int m = tid - 32;
         const int lcx = 30 * (m >> 5) + (m & 31);
-        const uint32_t woff = static_cast<uint32_t>((2 * lcx + 3) >> 2) * 4u;   // the 8 pixels start at byte 2*lcx + 3
-        const uint32_t shift = static_cast<uint32_t>((2 * lcx + 3) & 3) * 8u;
+        const int prow = m >> 5, pcol = m & 31;
         uint32_t n = 0;
         for (int strip = blockIdx.x; strip < nstrips; strip += gridDim.x) {
             for (int j = -2; j < Hp; ++j, ++n) {
                 const uint32_t rs = n % nraw, es = n % kSrNG;
+                uint8_t* rb = rowbf + (n & 1u) * kSrRowBufBytes;
                 mbar_wait(raw_full + rs, (n / nraw) & 1u);
+                {
+                    const uint2 px = *reinterpret_cast<const uint2*>(raw + rs * kSrRawBytes + prow * kSrRawPitch + pcol * 8);
+                    uint4 v;
+                    u8x4_to_bf16x4(px.x, v.x, v.y);
+                    u8x4_to_bf16x4(px.y, v.z, v.w);
+                    *reinterpret_cast<uint4*>(rb + prow * 512 + pcol * 16) = v;
+                }
+                mbar_arrive(raw_empty + rs);
+                asm volatile("bar.sync 1, 128;\n" ::: "memory");
                 mbar_wait(e_empty + es, ((n / kSrNG) & 1u) ^ 1u);
-                const uint8_t* src = raw + rs * kSrRawBytes + woff;
+                const uint8_t* src = rb + 4 * lcx + 4;
                 uint8_t* dst = ring + es * kSrGroupBytes + m * 16;
 #pragma unroll
                 for (int r = 0; r < 4; ++r) {
-                    const uint32_t* s32 = reinterpret_cast<const uint32_t*>(src + r * kSrRawPitch);
-                    const uint32_t w0 = s32[0], w1 = s32[1], w2 = s32[2];
-                    const uint32_t lo = __funnelshift_r(w0, w1, shift), hi = __funnelshift_r(w1, w2, shift);
-                    uint4 v;
-                    u8x4_to_bf16x4(lo, v.x, v.y);
-                    u8x4_to_bf16x4(hi, v.z, v.w);
-                    *reinterpret_cast<uint4*>(dst + r * kSrRowBytes) = v;
+                    const uint32_t* s32 = reinterpret_cast<const uint32_t*>(src + r * 512);
+                    *reinterpret_cast<uint4*>(dst + r * kSrRowBytes) = make_uint4(s32[0], s32[1], s32[2], s32[3]);
                 }
                 fence_proxy_async_smem();
                 mbar_arrive(e_full + es);
-                mbar_arrive(raw_empty + rs);
             }
         }
     } else if (warp == 5) {
@@ -364,7 +384,7 @@ __global__ void __launch_bounds__(sr_threads(CG), 1) stem_rows_kernel(const __gr
             const bool store_ok = (lane >> 1) < 15 && px < Wp;
             uint32_t carry[kPk];
 #pragma unroll
-            for (int i = 0; i < kPk; ++i) carry[i] = 0xFF80FF80u;   // conv row -1: padding
+            for (int i = 0; i < kPk; ++i) carry[i] = 0u;   // conv row -1: padding (values are ReLU'd, 0 never wins wrongly)
             for (int g = 0; g < Hp; ++g, ++sc) {
                 const uint32_t ts = sc % kSrTmemStages;
                 mbar_wait(t_full + ts, (sc / kSrTmemStages) & 1u);
@@ -387,16 +407,14 @@ __global__ void __launch_bounds__(sr_threads(CG), 1) stem_rows_kernel(const __gr
                 }
 #pragma unroll
                 for (int i = 0; i < kPk; ++i) {
-                    const __nv_bfloat162 ha = __floats2bfloat162_rn(__uint_as_float(ra[2 * i]), __uint_as_float(ra[2 * i + 1]));
-                    const __nv_bfloat162 hb = __floats2bfloat162_rn(__uint_as_float(rb[2 * i]), __uint_as_float(rb[2 * i + 1]));
-                    const uint32_t ua = *reinterpret_cast<const uint32_t*>(&ha);
-                    const uint32_t ub = *reinterpret_cast<const uint32_t*>(&hb);
+                    // ReLU rides on the conversion (relu and max commute, so this is the reference's relu -> maxpool order)
+                    const uint32_t ua = pack_bf16x2_relu(ra[2 * i], ra[2 * i + 1]);
+                    const uint32_t ub = pack_bf16x2_relu(rb[2 * i], rb[2 * i + 1]);
                     uint32_t x = bf16x2_max(bf16x2_max(carry[i], ua), ub);   // conv rows 2g-1, 2g, 2g+1
                     carry[i] = ub;
                     const uint32_t x1 = __shfl_down_sync(0xffffffffu, x, 1);
                     const uint32_t x2 = __shfl_down_sync(0xffffffffu, x, 2);
-                    x = bf16x2_max(bf16x2_max(x, x1), x2);                   // conv columns 2j, 2j+1, 2j+2 (lane 2j)
-                    v[i] = bf16x2_max(x, 0u);                                // ReLU after the pool
+                    v[i] = bf16x2_max(bf16x2_max(x, x1), x2);                // conv columns 2j, 2j+1, 2j+2 (lane 2j)
                 }
                 // even lane 2j holds pooled pixel j (kCh channels = kCh / 8 chunks of 16 bytes); the odd neighbour takes
                 // the odd chunks so that every store instruction writes whole 32-byte sectors
