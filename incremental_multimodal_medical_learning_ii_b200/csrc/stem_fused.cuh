@@ -1,3 +1,5 @@
+// TILE variant of the fused 8-bit stem (superseded as the default by the row-streaming kernel in stem_rows.cuh, which is
+// 2x faster; kept behind BV_STEM_V1 and bv_stem_u8_nhwc(variant 1) as the second implementation the tests compare with).
 // Fused BioViL stem for 8-bit frames: conv 7x7 stride 2 pad 3 (1 folded input channel -> 64) + BatchNorm + ReLU +
 // max-pool 3x3 stride 2 pad 1, written straight as the NHWC bf16 input of layer1.  The 240x240x64 conv output
 // (7.4 MB per frame in bf16, the largest tensor of the network) never reaches HBM.
