@@ -140,6 +140,28 @@ def test_small_sizes_and_float_paths_vs_oracle(setup):
         assert cos >= 0.999 and rel <= 3e-2
 
 
+def test_512_crop_8bit_frames_vs_oracle(setup):
+    """The reference's other crop size (512x512: 16x16 patch grid, 128 pooled columns = two full stem strips + a ragged
+    one, layer1 width not a multiple of 30 so the CTA-pair block kernel is not eligible) on 8-bit frames, plus a
+    non-square 8-bit case, against the CPU oracle."""
+    import biovil_oracle as O
+    from incremental_multimodal_medical_learning_ii_b200 import frames as FR
+    variant, m, sd, golden = setup
+    prompts = FR.synthetic_prompt_embeddings(14, 1, 128, seed=29)
+    m.set_prompts(prompts, reduce="mean")
+    for (B, H, W) in ((2, 512, 512), (3, 160, 352)):
+        fr = FR.synthetic_frames_u8(11, B, max(H, W), kind="structured", seed=4)[:, :, :H, :W].contiguous()
+        ref = O.image_model_forward(sd, FR.frames_as_reference_input(fr))
+        res = m.embed_and_score(fr.to(DEV))
+        cos, rel, _ = _metrics(res["global"], ref["projected_global_embedding"])
+        sc = O.zero_shot_score(ref["projected_global_embedding"], prompts, "mean")
+        dprob = (res["prob"].cpu() - sc["prob"]).abs().max().item()
+        print(f"[{variant}] u8 {B}x{H}x{W}: cosine {cos:.6f} rel {rel:.3e} max|dprob| {dprob:.2e}")
+        assert cos >= 0.999 and rel <= 3e-2 and dprob <= 1e-3
+        grid = m(fr.to(DEV)).projected_patch_embeddings
+        assert grid.shape == (B, 128, H // 32, W // 32)
+
+
 def test_guards(setup):
     variant, m, sd, golden = setup
     with pytest.raises(ValueError):
