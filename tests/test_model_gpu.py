@@ -140,6 +140,24 @@ def test_small_sizes_and_float_paths_vs_oracle(setup):
         assert cos >= 0.999 and rel <= 3e-2
 
 
+def test_full_bench_batch_matches_chunks(setup):
+    """BASELINE.json configs[1] at full size (512 frames of 480x480): every kernel runs its full persistent schedule
+    (all 148 CTAs, hundreds of tiles each).  Size-independent property: the results equal, bit for bit, those of the
+    same frames sent through in chunks of 64."""
+    from incremental_multimodal_medical_learning_ii_b200 import frames as FR
+    variant, m, sd, golden = setup
+    m.set_prompts(FR.synthetic_prompt_embeddings(14, 5, 128, seed=31), reduce="mean")
+    fr = torch.cat([FR.synthetic_frames_u8(o, 64, 480, kind="structured", seed=5, device=DEV) for o in range(0, 512, 64)])
+    full = m.embed_and_score(fr)
+    full = {k: full[k].clone() for k in ("global", "prob", "pred", "sim")}
+    assert not torch.isnan(full["global"]).any()
+    assert full["global"].shape == (512, 128) and full["prob"].shape == (512, 14)
+    for o in range(0, 512, 64):
+        part = m.embed_and_score(fr[o:o + 64].contiguous())
+        for k in full:
+            assert torch.equal(part[k], full[k][o:o + 64]), f"[{variant}] chunk at {o} differs in {k}"
+
+
 def test_512_crop_8bit_frames_vs_oracle(setup):
     """The reference's other crop size (512x512: 16x16 patch grid, 128 pooled columns = two full stem strips + a ragged
     one, layer1 width not a multiple of 30 so the CTA-pair block kernel is not eligible) on 8-bit frames, plus a
