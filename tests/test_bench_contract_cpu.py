@@ -38,3 +38,27 @@ def test_traffic_file_matches_the_committed_launch_list():
     # algorithmic bytes of the conv path are ~237 MB per image; measured DRAM traffic must be in that range
     per_image = t["conv_dram_bytes_per_step"] / 512
     assert 120e6 < per_image < 260e6
+
+
+def test_traffic_json_is_what_the_committed_ncu_launch_list_says(tmp_path):
+    """``roofline.traffic`` comes from ``profiles/traffic.json``; that file must be reproducible from the committed ncu
+    launch list it names (one forward = the stem, 43 further convolution launches and the head)."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    with open(os.path.join(root, "profiles", "traffic.json")) as f:
+        committed = json.load(f)
+    src = os.path.join(root, committed["source"])
+    assert os.path.exists(src), f"{committed['source']} is not committed"
+    dst = tmp_path / "copy.csv"
+    subprocess.run([sys.executable, os.path.join(root, "tools", "summarise_ncu_launches.py"), src, str(dst),
+                    str(committed["batch"])], check=True, capture_output=True)
+    with open(tmp_path / "traffic.json") as f:
+        again = json.load(f)
+    for key in ("conv_launches", "all_launches", "conv_dram_bytes_per_step", "all_dram_bytes_per_step"):
+        assert again[key] == committed[key], key
+    assert committed["conv_launches"] == 44 and committed["all_launches"] == 45
+    # every launch moves at least its algorithmic bytes; the whole step within 10 % of the 237 MB per image of SURVEY 8(d)
+    per_image = committed["conv_dram_bytes_per_step"] / committed["batch"]
+    assert 150e6 < per_image < 1.1 * 237e6
