@@ -97,8 +97,8 @@ constexpr int kMaxResidentKB = 9;
 // of the stage's two m-tiles the B operand (N = 256).  A 128x128x16 MMA is bound by the 64 B/cycle A-operand read
 // (78 cycles), a 128x256x16 one runs at the math rate (128 cycles for twice the work): -18 % tensor time.  The
 // accumulator is then channel-major (TMEM lane = channel, column = pixel); the epilogue transposes it on the way into
-// the swizzled staging tiles with 2-byte stores (32 per thread and sub-tile, conflict-free: the 32 lanes of a store
-// cover 64 contiguous bytes of one pixel row).
+// the swizzled staging tiles with 2-byte stores (32 per thread and sub-tile: the 32 lanes of a store cover 64 contiguous
+// bytes of one pixel row; two lanes share each bank word = one extra wavefront, far off the critical path).
 template <int BN, int STAGES, int NBUF, bool BRES = false, bool WIDE = false, int MT = 1, int EPI = 16, bool TR = false>
 struct ConvGemmCfg {
     static_assert(EPI == 8 || EPI == 16, "epilogue warps");
