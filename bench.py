@@ -122,7 +122,7 @@ def cpu_reference_run(n_frames: int, batch: int = 16):
     """The reference's CPU path (oracle port, proven bit-equal to the reference in oracle/make_golden.py):
     fp32 ImageModel forward + restated scorer on `n_frames` synthetic frames with all host cores."""
     import biovil_oracle as O
-    import weights as Wt
+    from incremental_multimodal_medical_learning_ii_b200 import synthetic_weights as Wt
     from incremental_multimodal_medical_learning_ii_b200 import frames as FR
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
@@ -168,7 +168,7 @@ def run_reference(args):
 
 def run_ours(args):
     import torch.distributed as dist
-    import weights as Wt
+    from incremental_multimodal_medical_learning_ii_b200 import synthetic_weights as Wt
     from incremental_multimodal_medical_learning_ii_b200 import frames as FR
     from incremental_multimodal_medical_learning_ii_b200.image import get_biovil_resnet
 

@@ -12,8 +12,13 @@
  *                     MLP.forward (projector)                    health_multimodal/image/model/modules.py:43-55
  *                     get_patchwise_projected_embeddings         health_multimodal/image/model/model.py:161-175
  *                     patch x prompt similarity map              health_multimodal/vlp/inference_engine.py:93-108
+ *   bv_forward_graph  the same forward, captured once per argument set as a CUDA graph and replayed (the reference's
+ *                     extraction loop calls the model with batch size 1: chexpert-get-embedding.py:47-49, 68-80)
+ *   bv_quantize_frames_f32  undoes ToTensor + ExpandChannels on 8-bit data   health_multimodal/image/data/transforms.py:12-38
  *   bv_set_prompts    Trainer.bert_forward_mean (prompt side)    Trainer.py:1657-1680
  *   bv_score          Trainer.myCosineSimilarity + label loop    Trainer.py:1682-1704, 805-837, 1019-1047
+ *   bv_pairwise_cosine  Trainer.myCosineSimilarity alone (one call, no state)   Trainer.py:1682-1704
+ *   bv_jpeg_info / bv_jpeg_decode_gray_u8   read_image of a grey JPEG (nvJPEG)   DataRetrieval.py:70-96
  *   bv_resize_center_crop_u8  transforms.Resize + CenterCrop on 8-bit frames (Pillow 8bpc bilinear, bit-exact)
  *                     DataRetrieval.py:175-180; health_multimodal/image/data/transforms.py:30-41
  *   bv_smooth_heatmaps  gaussian_filter(sigma) of the similarity maps health_multimodal/vlp/inference_engine.py:107-109
@@ -110,9 +115,36 @@ int32_t bv_forward(bv_handle* h, const void* frames, int32_t dtype, int32_t batc
                    int32_t width, void* workspace, size_t workspace_bytes, const bv_outputs* host_out,
                    bv_stream stream);
 
+/* bv_forward recorded once into a CUDA graph per distinct argument set (frame / workspace / output pointers, shape,
+ * installed prompt buffers) and replayed with ONE cudaGraphLaunch afterwards: same arguments, same results.  For the
+ * launch-bound regime (the reference's batch-size-1 loop); callers must pass the SAME buffers again to hit the cache
+ * (8 entries, oldest dropped).  Falls back to direct launches while profiling is on. */
+int32_t bv_forward_graph(bv_handle* h, const void* frames, int32_t dtype, int32_t batch, int32_t channels, int32_t height,
+                         int32_t width, void* workspace, size_t workspace_bytes, const bv_outputs* host_out,
+                         bv_stream stream);
+
+/* Float frames x [B,C,H,W] (C = 1 or 3) -> out u8 [B,1,H,W] = round(255 x) of channel 0; *bad (device int32, zeroed
+ * here) becomes non-zero when some pixel is NOT 8-bit data (|255 x - k| > 1e-3, k outside 0..255, NaN) or the channels
+ * differ: the caller then feeds the float frames to bv_forward instead.  H*W multiple of 4, x 16-byte aligned. */
+int32_t bv_quantize_frames_f32(const float* x, int32_t batch, int32_t channels, int32_t height, int32_t width,
+                               uint8_t* out, int32_t* bad, bv_stream stream);
+
 /* Score cached embeddings emb [B,128] (un-normalised) against the installed prompts. */
 int32_t bv_score(bv_handle* h, const float* emb, int32_t batch, float* sim, float* prob, uint8_t* pred, float* score,
                  bv_stream stream);
+
+/* out[b][p] = cosine(x[b], y[p]) for x [B,128], y [P,128] (both un-normalised; rows divided by their L2 norm, no eps:
+ * torchmetrics.pairwise_cosine_similarity as Trainer.myCosineSimilarity calls it); reduce_max != 0 -> out [B] = max over p
+ * (the MAX_EMB branch, Trainer.py:1691-1694).  Stateless: no handle, no allocation, asynchronous on `stream`. */
+int32_t bv_pairwise_cosine(const float* x, const float* y, int32_t batch, int32_t num_prompts, int32_t reduce_max,
+                           float* out, bv_stream stream);
+
+/* JPEG decode in front of the resize kernel (nvJPEG, resolved with dlopen at first use).  bv_jpeg_info parses the
+ * header of a HOST buffer; bv_jpeg_decode_gray_u8 decodes it into the DEVICE buffer out [height][pitch] (luma plane =
+ * the grey values of a single-component JPEG).  Not bit-exact against libjpeg (IDCT rounding): within +-2 grey levels. */
+int32_t bv_jpeg_info(const uint8_t* host_data, size_t length, int32_t* width, int32_t* height, int32_t* components);
+int32_t bv_jpeg_decode_gray_u8(const uint8_t* host_data, size_t length, uint8_t* out, int32_t width, int32_t height,
+                               int32_t pitch, bv_stream stream);
 
 /* Resize(size) -> CenterCrop(crop) of n same-sized 8-bit grayscale frames src [n,h,w] -> out [n,crop,crop] with the
  * integer arithmetic of Pillow's 8bpc bilinear resampler (short side -> size, long side int(size*long/short), centre
@@ -181,7 +213,8 @@ int32_t bv_stem_u8_nhwc(const void* frames, int32_t batch, int32_t height, int32
 
 /* The row-streaming stem with layer1.0's conv1 fused in (torchvision Bottleneck.forward conv1 -> bn1 -> relu on the
  * max-pool output, resnet.py:38-39): out = max-pool output as above, out1 = relu(conv1x1(out) + bias) bf16 NHWC
- * [B][H/4][W/4][64]; host_c1 is a 64 -> 64 1x1 bv_conv.  What bv_forward launches for 8-bit frames. */
+ * [B][H/4][W/4][64]; host_c1 is a 64 -> 64 1x1 bv_conv.  Experiment entry: bv_forward launches this form only with
+ * BV_STEM_C1=1 (measured slower than stem + separate conv1, DESIGN.md switches table); the default is bv_stem_u8_nhwc. */
 int32_t bv_stem_conv1_u8_nhwc(const void* frames, int32_t batch, int32_t height, int32_t width, const bv_conv* host_w8,
                               const bv_conv* host_c1, void* out, void* out1, bv_stream stream);
 

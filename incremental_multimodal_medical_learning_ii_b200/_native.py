@@ -67,7 +67,8 @@ EXPORTED_SYMBOLS = (
     "bv_set_prompts", "bv_forward", "bv_score", "bv_last_forward_launches", "bv_set_profile", "bv_get_profile",
     "bv_conv2d_nhwc", "bv_conv_chain_nhwc", "bv_smooth_heatmaps",
     "bv_resize_workspace_bytes", "bv_resize_center_crop_u8", "bv_pair_gemm_test", "bv_l1_block_nhwc",
-    "bv_stem_u8_nhwc", "bv_stem_conv1_u8_nhwc",
+    "bv_stem_u8_nhwc", "bv_stem_conv1_u8_nhwc", "bv_forward_graph", "bv_pairwise_cosine", "bv_quantize_frames_f32",
+    "bv_jpeg_info", "bv_jpeg_decode_gray_u8",
 )
 
 _lib = None
@@ -79,13 +80,15 @@ def sources():
 
 def build(force: bool = False, verbose: bool = False) -> Path:
     """Compile ``libbiovil_b200.so`` for sm_100a next to this file (no-op when up to date)."""
-    deps = list(CSRC.glob("*.cu")) + list(CSRC.glob("*.cuh")) + [INCLUDE / "biovil_b200.h"]
+    deps = list(CSRC.glob("*.cu")) + list(CSRC.glob("*.cuh")) + list(CSRC.glob("*.h")) + [INCLUDE / "biovil_b200.h"]
     if LIB_PATH.exists() and not force:
         newest = max(p.stat().st_mtime for p in deps)
         if LIB_PATH.stat().st_mtime >= newest:
             return LIB_PATH
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc, *NVCC_FLAGS, "-o", str(LIB_PATH), *map(str, sources())]
+    cmd = [nvcc, *NVCC_FLAGS, "-o", str(LIB_PATH), *map(str, sources()), "-ldl"]
+    if os.environ.get("BV_BUILD_TIMING"):          # profiling build: wait-cycle counters compiled in (BV_TIMING=1 reports)
+        cmd.insert(1, "-DBV_ENABLE_TIMING=1")
     if verbose:
         cmd.insert(1, "-Xptxas")
         cmd.insert(2, "-v")
@@ -153,6 +156,16 @@ def lib() -> ctypes.CDLL:
     l.bv_conv_chain_nhwc.restype = c_int32
     l.bv_conv_chain_nhwc.argtypes = [c_void_p, c_int32, c_int32, c_int32, POINTER(BvConv), c_void_p, c_int32, c_int32,
                                      POINTER(BvConv), c_void_p, c_void_p, POINTER(BvConv), c_void_p, c_void_p]
+    l.bv_forward_graph.restype = c_int32
+    l.bv_forward_graph.argtypes = l.bv_forward.argtypes
+    l.bv_pairwise_cosine.restype = c_int32
+    l.bv_pairwise_cosine.argtypes = [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p]
+    l.bv_quantize_frames_f32.restype = c_int32
+    l.bv_quantize_frames_f32.argtypes = [c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p]
+    l.bv_jpeg_info.restype = c_int32
+    l.bv_jpeg_info.argtypes = [c_void_p, c_size_t, POINTER(c_int32), POINTER(c_int32), POINTER(c_int32)]
+    l.bv_jpeg_decode_gray_u8.restype = c_int32
+    l.bv_jpeg_decode_gray_u8.argtypes = [c_void_p, c_size_t, c_void_p, c_int32, c_int32, c_int32, c_void_p]
     _lib = l
     return l
 

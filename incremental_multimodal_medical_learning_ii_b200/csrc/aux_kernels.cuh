@@ -217,6 +217,77 @@ __global__ void __launch_bounds__(256) score_kernel(const float* __restrict__ em
     }
 }
 
+// Trainer.myCosineSimilarity(x, y) as one launch (Trainer.py:1682-1704): out[b, p] = cos(x[b], y[p]) for x [B,128],
+// y [P,128], both un-normalised (rows divided by their L2 norm, plain division - torchmetrics semantics); with
+// `reduce_max` the max over the P prompts (the MAX_EMB branch, :1691-1694) -> out [B,1].  One warp per image row; the
+// prompt norms are recomputed per warp (P is 1..8: cheaper than a second launch or a device allocation).
+__global__ void __launch_bounds__(256) pairwise_cosine_kernel(const float* __restrict__ x, const float* __restrict__ y, int B,
+                                                             int P, int reduce_max, float* __restrict__ out) {
+    const int warps = (gridDim.x * blockDim.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    for (int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; b < B; b += warps) {
+        float4 xv = reinterpret_cast<const float4*>(x + static_cast<size_t>(b) * kEmbDim)[lane];
+        float ss = xv.x * xv.x + xv.y * xv.y + xv.z * xv.z + xv.w * xv.w;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, off);
+        const float nx = sqrtf(ss);
+        xv = make_float4(xv.x / nx, xv.y / nx, xv.z / nx, xv.w / nx);
+        float best = -INFINITY;
+        bool any_nan = false;
+        for (int pp = 0; pp < P; ++pp) {
+            float4 yv = reinterpret_cast<const float4*>(y + static_cast<size_t>(pp) * kEmbDim)[lane];
+            float sy = yv.x * yv.x + yv.y * yv.y + yv.z * yv.z + yv.w * yv.w;
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) sy += __shfl_xor_sync(0xffffffffu, sy, off);
+            const float ny = sqrtf(sy);
+            yv = make_float4(yv.x / ny, yv.y / ny, yv.z / ny, yv.w / ny);
+            float d = xv.x * yv.x + xv.y * yv.y + xv.z * yv.z + xv.w * yv.w;
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) d += __shfl_xor_sync(0xffffffffu, d, off);
+            if (!reduce_max) {
+                if (lane == 0) out[static_cast<size_t>(b) * P + pp] = d;
+            } else {
+                any_nan |= (d != d);
+                best = fmaxf(best, d);
+            }
+        }
+        if (reduce_max && lane == 0) out[b] = any_nan ? __int_as_float(0x7fc00000) : best;
+    }
+}
+
+// ----------------------------------------------------------------------------------------------
+// Float frames -> 8-bit frames when they ARE 8-bit data: ToTensor + ExpandChannels (transforms.py:12-38) hand the
+// model k/255 with k a byte and three identical channels.  One pass reads the fp32 frames [B,C,H,W] (C = 1 or 3),
+// writes k as uint8 [B,1,H,W] and raises *bad (zeroed by the caller) when any pixel is not within 1e-3 grey levels of an integer in 0..255 or
+// the channels differ - the caller then takes the general float stem instead.  Replaces five torch reductions with
+// three host synchronisations by one launch and one flag read.  4 pixels per thread (16-byte loads, 4-byte stores).
+// ----------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) quantize_frames_kernel(const float* __restrict__ x, uint8_t* __restrict__ out, int C,
+                                                             long long hw4, long long total4, int* __restrict__ bad) {
+    bool good = true;
+    for (long long t = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; t < total4;
+         t += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const long long b = t / hw4, r = t - b * hw4;
+        const float4* src = reinterpret_cast<const float4*>(x) + b * C * hw4 + r;
+        const float4 v = __ldg(src);
+        const float f[4] = {v.x, v.y, v.z, v.w};
+        for (int c = 1; c < C; ++c) {
+            const float4 w = __ldg(src + c * hw4);
+            good = good && (w.x == v.x) && (w.y == v.y) && (w.z == v.z) && (w.w == v.w);
+        }
+        uint32_t packed = 0;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float k255 = f[e] * 255.0f;
+            const float k = rintf(k255);
+            good = good && (fabsf(k255 - k) <= 1e-3f) && (k >= 0.0f) && (k <= 255.0f);   // NaN fails the first test
+            packed |= (static_cast<uint32_t>(fminf(fmaxf(k, 0.0f), 255.0f)) & 0xFFu) << (8 * e);
+        }
+        reinterpret_cast<uint32_t*>(out)[t] = packed;
+    }
+    if (!__all_sync(0xffffffffu, good) && (threadIdx.x & 31) == 0) atomicOr(bad, 1);
+}
+
 // ----------------------------------------------------------------------------------------------
 // Projector tail + embeddings + scoring, one CTA (256 threads) per image.
 //   hid [B*P, 128] fp32  = ReLU(BN(conv1x1_2048->128(x4)))   (written by the tcgen05 GEMM, modules.py:43-46)
@@ -251,6 +322,8 @@ __global__ void __launch_bounds__(128) head_global_kernel(const HeadParams hp) {
     const int b = blockIdx.x;
     const int d = threadIdx.x;
     const int lane = d & 31;
+    asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");   // programmatic dependent launch, see ptx.cuh
+    asm volatile("griddepcontrol.wait;\n" ::: "memory");
     const float* hp_b = hp.hid + static_cast<size_t>(b) * hp.P * kEmbDim + d;
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
     int pidx = 0;
@@ -294,6 +367,8 @@ __global__ void __launch_bounds__(256) head_kernel(const HeadParams hp) {
     for (int i = tid; i < kEmbDim * kEmbDim; i += 256) w2t[i] = __ldg(hp.w2t + i);
     const float bias = __ldg(hp.b2 + d);
     float gacc = 0.0f;
+    asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");   // programmatic dependent launch, see ptx.cuh
+    asm volatile("griddepcontrol.wait;\n" ::: "memory");                 // weights above are constants; hid is not
     __syncthreads();
     for (int p0 = 0; p0 < hp.P; p0 += 2) {
         const int pidx = p0 + half;

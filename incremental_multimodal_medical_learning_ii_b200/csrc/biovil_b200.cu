@@ -13,6 +13,7 @@
 #include <map>
 #include <mutex>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/biovil_b200.h"
@@ -20,6 +21,7 @@
 #include "chain_gemm.cuh"
 #include "conv3x3_tap3.cuh"
 #include "conv_gemm.cuh"
+#include "jpeg_stage.h"
 #include "l1_block.cuh"
 #include "pair_gemm.cuh"
 #include "resize.cuh"
@@ -124,17 +126,51 @@ bool env_flag(const char* name) {
     return v && v[0] && v[0] != '0';
 }
 
+// Every kernel of the forward goes through here: optional thread-block cluster, and programmatic dependent launch
+// (ptx.cuh: pdl_launch_dependents / pdl_wait) so that the next kernel's prologue overlaps this kernel's tail.
+// BV_NO_PDL=1 launches with plain stream serialisation (A/B switch).
+bool pdl_enabled() {
+    static const bool on = !env_flag("BV_NO_PDL");
+    return on;
+}
+template <typename... KArgs, typename... Args>
+cudaError_t launch_ex(void (*kernel)(KArgs...), int grid, int block, size_t smem, cudaStream_t st, int cluster,
+                      Args&&... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid, 1, 1);
+    cfg.blockDim = dim3(block, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[2];
+    int n = 0;
+    if (cluster > 1) {
+        at[n].id = cudaLaunchAttributeClusterDimension;
+        at[n].val.clusterDim.x = cluster;
+        at[n].val.clusterDim.y = 1;
+        at[n].val.clusterDim.z = 1;
+        ++n;
+    }
+    if (pdl_enabled()) {
+        at[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[n].val.programmaticStreamSerializationAllowed = 1;
+        ++n;
+    }
+    cfg.attrs = at;
+    cfg.numAttrs = n;
+    return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+
 // Row-streaming stem: 8 epilogue warps of 32 channels (0.566 ms per 512 frames alone); BV_SR_CG4 = 16 warps of 16
 // channels (0.594 ms: the kernel is bound by instruction throughput, not latency, and more warps add per-warp overhead).
 // With p.out1 set the kernel also applies layer1.0's conv1 (1x1, 64 -> 64, + bn1 + ReLU) to every pooled pixel.
 void launch_stem_rows(const bv::StemRowsParams& p, int grid, cudaStream_t st) {
     const bool c1 = p.out1 != nullptr;
     if (env_flag("BV_SR_CG4")) {
-        if (c1) bv::stem_rows_kernel<4, true><<<grid, bv::sr_threads(4), bv::sr_smem_bytes(true), st>>>(p);
-        else bv::stem_rows_kernel<4, false><<<grid, bv::sr_threads(4), bv::sr_smem_bytes(false), st>>>(p);
+        if (c1) launch_ex(bv::stem_rows_kernel<4, true>, grid, bv::sr_threads(4), bv::sr_smem_bytes(true), st, 1, p);
+        else launch_ex(bv::stem_rows_kernel<4, false>, grid, bv::sr_threads(4), bv::sr_smem_bytes(false), st, 1, p);
     } else {
-        if (c1) bv::stem_rows_kernel<2, true><<<grid, bv::sr_threads(2), bv::sr_smem_bytes(true), st>>>(p);
-        else bv::stem_rows_kernel<2, false><<<grid, bv::sr_threads(2), bv::sr_smem_bytes(false), st>>>(p);
+        if (c1) launch_ex(bv::stem_rows_kernel<2, true>, grid, bv::sr_threads(2), bv::sr_smem_bytes(true), st, 1, p);
+        else launch_ex(bv::stem_rows_kernel<2, false>, grid, bv::sr_threads(2), bv::sr_smem_bytes(false), st, 1, p);
     }
 }
 
@@ -191,55 +227,79 @@ struct PlanStep {
     L1Launch l1b;
 };
 
-int g_num_sms = 0;
-bool g_attr_set = false;
-long long* g_dbg = nullptr;  // BV_TIMING=1: per-CTA wait-cycle counters of the most recent conv launch
+// Per-device state: the dynamic-shared-memory opt-ins (cudaFuncSetAttribute) apply to the device that is current when
+// they are made, the SM count and the cluster-launch capability differ per device, and one process may drive several
+// devices (an ImageModel on cuda:0 and a ZeroShotScorer on cuda:1).  Every entry point calls device_setup(), which
+// (re)binds the calling thread to the state of ITS current device.
+constexpr int kMaxDevices = 64;
+struct DeviceState {
+    bool ready = false;
+    int num_sms = 0;
+    int l1_launchable = -1;        // -1 = not probed yet
+    long long* dbg = nullptr;      // BV_TIMING builds: per-CTA wait-cycle counters of the most recent launch
+};
+DeviceState g_dev[kMaxDevices];
+std::mutex g_dev_mutex;
+thread_local DeviceState* t_dev = nullptr;   // state of the calling thread's current device (set by device_setup)
+thread_local int g_num_sms = 0;              // == t_dev->num_sms
+
+int set_kernel_attributes() {
+#define BV_SET_ATTR(id, BN, ST, NB, BR, WD, MT, EP, TR)                                             \
+    BV_CUDA(cudaFuncSetAttribute(bv::conv_gemm_kernel<BN, ST, NB, BR, WD, MT, EP, TR>,              \
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize,                       \
+                                 bv::ConvGemmCfg<BN, ST, NB, BR, WD, MT, EP, TR>::kSmemBytes));
+    BV_FOR_EACH_CFG(BV_SET_ATTR)
+#undef BV_SET_ATTR
+#define BV_SET_CHAIN_ATTR(id, N2, ST, NB)                                                           \
+    BV_CUDA(cudaFuncSetAttribute(bv::chain_gemm_kernel<N2, ST, NB>,                                 \
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize,                       \
+                                 bv::ChainCfg<N2, ST, NB>::kSmemBytes));
+    BV_FOR_EACH_CHAIN(BV_SET_CHAIN_ATTR)
+#undef BV_SET_CHAIN_ATTR
+    BV_CUDA(cudaFuncSetAttribute(bv::conv3x3_tap3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 bv::kTap3SmemBytes));
+    BV_CUDA(cudaFuncSetAttribute(bv::l1_block_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 bv::L1Cfg<64>::kSmemBytes));
+    BV_CUDA(cudaFuncSetAttribute(bv::head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
+    BV_CUDA(cudaFuncSetAttribute(bv::stem_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 bv::kStemSmemRequest));
+    BV_CUDA(cudaFuncSetAttribute(bv::stem_rows_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 bv::sr_smem_bytes(false)));
+    BV_CUDA(cudaFuncSetAttribute(bv::stem_rows_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 bv::sr_smem_bytes(false)));
+    BV_CUDA(cudaFuncSetAttribute(bv::stem_rows_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 bv::sr_smem_bytes(true)));
+    BV_CUDA(cudaFuncSetAttribute(bv::stem_rows_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 bv::sr_smem_bytes(true)));
+    BV_CUDA(cudaFuncSetAttribute(bv::pair_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bv::kPairSmemBytes));
+    return BV_OK;
+}
 
 int device_setup() {
-    if (g_num_sms > 0) return BV_OK;
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) {
         cudaGetLastError();
         return fail(BV_ERR_NO_DEVICE, "no CUDA device available (this library has no CPU fallback)");
     }
-    cudaDeviceProp prop;
-    BV_CUDA(cudaGetDeviceProperties(&prop, dev));
-    if (prop.major != 10)
-        return fail(BV_ERR_NO_DEVICE, "device %s is sm_%d%d; this library is built for sm_100a only", prop.name,
-                    prop.major, prop.minor);
-    int rc = resolve_driver();
-    if (rc) return rc;
-    if (!g_attr_set) {
-#define BV_SET_ATTR(id, BN, ST, NB, BR, WD, MT, EP, TR)                                             \
-    BV_CUDA(cudaFuncSetAttribute(bv::conv_gemm_kernel<BN, ST, NB, BR, WD, MT, EP, TR>,              \
-                                 cudaFuncAttributeMaxDynamicSharedMemorySize,                       \
-                                 bv::ConvGemmCfg<BN, ST, NB, BR, WD, MT, EP, TR>::kSmemBytes));
-        BV_FOR_EACH_CFG(BV_SET_ATTR)
-#undef BV_SET_ATTR
-#define BV_SET_CHAIN_ATTR(id, N2, ST, NB)                                                              \
-    BV_CUDA(cudaFuncSetAttribute(bv::chain_gemm_kernel<N2, ST, NB>,                                 \
-                                 cudaFuncAttributeMaxDynamicSharedMemorySize,                       \
-                                 bv::ChainCfg<N2, ST, NB>::kSmemBytes));
-        BV_FOR_EACH_CHAIN(BV_SET_CHAIN_ATTR)
-#undef BV_SET_CHAIN_ATTR
-        BV_CUDA(cudaFuncSetAttribute(bv::conv3x3_tap3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     bv::kTap3SmemBytes));
-        BV_CUDA(cudaFuncSetAttribute(bv::l1_block_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     bv::L1Cfg<64>::kSmemBytes));
-        BV_CUDA(cudaFuncSetAttribute(bv::head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
-        BV_CUDA(cudaFuncSetAttribute(bv::stem_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     bv::kStemSmemRequest));
-        BV_CUDA(cudaFuncSetAttribute(bv::stem_rows_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     bv::sr_smem_bytes(false)));
-        BV_CUDA(cudaFuncSetAttribute(bv::stem_rows_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     bv::sr_smem_bytes(false)));
-        BV_CUDA(cudaFuncSetAttribute(bv::stem_rows_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     bv::sr_smem_bytes(true)));
-        BV_CUDA(cudaFuncSetAttribute(bv::stem_rows_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     bv::sr_smem_bytes(true)));
-        g_attr_set = true;
+    if (dev < 0 || dev >= kMaxDevices) return fail(BV_ERR_INVALID, "device index %d out of range", dev);
+    DeviceState* d = &g_dev[dev];
+    if (!d->ready) {
+        std::lock_guard<std::mutex> lock(g_dev_mutex);
+        if (!d->ready) {
+            cudaDeviceProp prop;
+            BV_CUDA(cudaGetDeviceProperties(&prop, dev));
+            if (prop.major != 10)
+                return fail(BV_ERR_NO_DEVICE, "device %d (%s) is sm_%d%d; this library is built for sm_100a only", dev,
+                            prop.name, prop.major, prop.minor);
+            int rc = resolve_driver();
+            if (rc) return rc;
+            if ((rc = set_kernel_attributes())) return rc;
+            d->num_sms = prop.multiProcessorCount;
+            d->ready = true;
+        }
     }
-    g_num_sms = prop.multiProcessorCount;
+    t_dev = d;
+    g_num_sms = d->num_sms;
     return BV_OK;
 }
 
@@ -358,7 +418,8 @@ int build_conv(ConvLaunch* L, int B, const ConvOperand* ops, int nops, const voi
 
 int launch_conv(const ConvLaunch& L0, cudaStream_t st) {
     ConvLaunch L = L0;
-    if (env_flag("BV_TIMING")) {
+    if (bv::kTimingBuild && env_flag("BV_TIMING")) {
+        long long*& g_dbg = t_dev->dbg;
         if (!g_dbg) cudaMalloc(&g_dbg, 4 * 8 * 1024);
         cudaMemsetAsync(g_dbg, 0, 4 * 8 * 1024, st);
         L.p.dbg = g_dbg;
@@ -366,14 +427,14 @@ int launch_conv(const ConvLaunch& L0, cudaStream_t st) {
     switch (L.cfg) {
 #define BV_LAUNCH(id, BN, ST, NB, BR, WD, MT, EP, TR)                                                     \
     case id:                                                                                              \
-        bv::conv_gemm_kernel<BN, ST, NB, BR, WD, MT, EP, TR>                                              \
-            <<<L.grid, bv::ConvGemmCfg<BN, ST, NB, BR, WD, MT, EP, TR>::kThreads,                         \
-               bv::ConvGemmCfg<BN, ST, NB, BR, WD, MT, EP, TR>::kSmemBytes, st>>>(L.p);                   \
+        launch_ex(bv::conv_gemm_kernel<BN, ST, NB, BR, WD, MT, EP, TR>, L.grid,                           \
+                  bv::ConvGemmCfg<BN, ST, NB, BR, WD, MT, EP, TR>::kThreads,                              \
+                  bv::ConvGemmCfg<BN, ST, NB, BR, WD, MT, EP, TR>::kSmemBytes, st, 1, L.p);               \
         break;
         BV_FOR_EACH_CFG(BV_LAUNCH)
 #undef BV_LAUNCH
         case kCfg64Tap3:
-            bv::conv3x3_tap3_kernel<<<L.grid, bv::kTap3Threads, bv::kTap3SmemBytes, st>>>(L.p);
+            launch_ex(bv::conv3x3_tap3_kernel, L.grid, bv::kTap3Threads, bv::kTap3SmemBytes, st, 1, L.p);
             break;
         default:
             return fail(BV_ERR_INVALID, "unknown conv configuration %d", L.cfg);
@@ -382,7 +443,7 @@ int launch_conv(const ConvLaunch& L0, cudaStream_t st) {
     if (L.p.dbg) {
         static long long host[4 * 1024];
         cudaStreamSynchronize(st);
-        cudaMemcpy(host, g_dbg, sizeof(long long) * 4 * L.grid, cudaMemcpyDeviceToHost);
+        cudaMemcpy(host, t_dev->dbg, sizeof(long long) * 4 * L.grid, cudaMemcpyDeviceToHost);
         double a[4] = {0, 0, 0, 0};
         for (int i = 0; i < L.grid; ++i)
             for (int j = 0; j < 4; ++j) a[j] += (double)host[i * 4 + j] / L.grid;
@@ -508,7 +569,8 @@ int build_l1_block(L1Launch* L, int B, int H, int W, const void* t1, const bv_co
 // Can the device co-schedule CTA pairs of the fused layer1 kernel at all (cluster launch, 224 KB of smem per CTA)?
 // Queried once; when it cannot (MIG slice, odd SM count per TPC) the plan keeps the two-kernel path for that block.
 bool l1_block_launchable() {
-    static int cached = -1;
+    if (!t_dev) return false;
+    int& cached = t_dev->l1_launchable;
     if (cached >= 0) return cached == 1;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(2, 1, 1);
@@ -529,32 +591,21 @@ bool l1_block_launchable() {
 }
 
 int launch_l1_block(const L1Launch& L, cudaStream_t st) {
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(L.grid, 1, 1);
-    cfg.blockDim = dim3(bv::kL1Threads, 1, 1);
-    cfg.dynamicSmemBytes = bv::L1Cfg<64>::kSmemBytes;
-    cfg.stream = st;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = 2;
-    at[0].val.clusterDim.y = 1;
-    at[0].val.clusterDim.z = 1;
-    cfg.attrs = at;
-    cfg.numAttrs = 1;
     bv::L1BlockParams prm = L.p;
     // measured (ncu): the L2 prefetch adds 0.6 GB of DRAM reads per launch and does not change the duration
     prm.l2_prefetch = env_flag("BV_L1_PREFETCH") ? 1 : 0;
-    if (env_flag("BV_TIMING")) {
+    if (bv::kTimingBuild && env_flag("BV_TIMING")) {
+        long long*& g_dbg = t_dev->dbg;
         if (!g_dbg) cudaMalloc(&g_dbg, 4 * 8 * 1024);
         cudaMemsetAsync(g_dbg, 0, 4 * 8 * 1024, st);
         prm.dbg = g_dbg;
     }
-    BV_CUDA(cudaLaunchKernelEx(&cfg, bv::l1_block_kernel<64>, prm));
+    BV_CUDA(launch_ex(bv::l1_block_kernel<64>, L.grid, bv::kL1Threads, bv::L1Cfg<64>::kSmemBytes, st, 2, prm));
     if (prm.dbg) {
         static long long host[8 * 128];
         const int pairs = L.grid / 2;
         cudaStreamSynchronize(st);
-        cudaMemcpy(host, g_dbg, sizeof(long long) * 8 * pairs, cudaMemcpyDeviceToHost);
+        cudaMemcpy(host, t_dev->dbg, sizeof(long long) * 8 * pairs, cudaMemcpyDeviceToHost);
         double a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         for (int i = 0; i < pairs; ++i)
             for (int j = 0; j < 8; ++j) a[j] += (double)host[i * 8 + j] / pairs;
@@ -563,7 +614,7 @@ int launch_l1_block(const L1Launch& L, cudaStream_t st) {
                 a[0], 100 * a[1] / a[0], 100 * a[2] / a[0], 100 * a[3] / a[0], 100 * a[4] / a[0], 100 * a[5] / a[0],
                 100 * a[6] / a[0]);
         static long long h2[74 * 13];
-        cudaMemcpy(h2, g_dbg + 1024, sizeof(h2), cudaMemcpyDeviceToHost);
+        cudaMemcpy(h2, t_dev->dbg + 1024, sizeof(h2), cudaMemcpyDeviceToHost);
         double e[12] = {0}, tot = 0;
         for (int i = 0; i < pairs; ++i) {
             for (int j = 0; j < 12; ++j) e[j] += (double)h2[i * 12 + j] / pairs;
@@ -572,7 +623,7 @@ int launch_l1_block(const L1Launch& L, cudaStream_t st) {
         const char* nm[12] = {"wait d0_full", "e0 compute+write", "wait t2_free", "wait d1_full", "wait res_ready", "e1 compute",
                               "e1 group barrier", "e1 copy-out", "wait d2_full", "e2 compute+copy", "e2 barrier", "between"};
         static long long tr[64];
-        cudaMemcpy(tr, g_dbg + 2048, sizeof(tr), cudaMemcpyDeviceToHost);
+        cudaMemcpy(tr, t_dev->dbg + 2048, sizeof(tr), cudaMemcpyDeviceToHost);
         const char* en[13] = {"G0 issued", "t2_ready seen", "G1 issued", "sub_written0", "sub_written1", "sub_written2", "sub_written3",
                               "G2 issued", "E0: d0_full seen", "E0: t2_ready arrived", "E1: d1_full seen", "E1: res_ready seen", "E1 done"};
         const long long base = tr[1];
@@ -593,8 +644,8 @@ int launch_chain(const ChainLaunch& L, cudaStream_t st) {
     switch (L.cfg) {
 #define BV_LAUNCH_CHAIN(id, N2, ST, NB)                                                                    \
     case id:                                                                                               \
-        bv::chain_gemm_kernel<N2, ST, NB>                                                                  \
-            <<<L.grid, bv::kChainThreads, bv::ChainCfg<N2, ST, NB>::kSmemBytes, st>>>(L.p);                \
+        launch_ex(bv::chain_gemm_kernel<N2, ST, NB>, L.grid, bv::kChainThreads,                            \
+                  bv::ChainCfg<N2, ST, NB>::kSmemBytes, st, 1, L.p);                                       \
         break;
         BV_FOR_EACH_CHAIN(BV_LAUNCH_CHAIN)
 #undef BV_LAUNCH_CHAIN
@@ -647,6 +698,7 @@ struct bv_handle {
     // prompts
     float* yn = nullptr;      // [L][2][P][128] unit vectors
     float* heat_t = nullptr;  // [L][128]
+    size_t yn_cap = 0, heat_cap = 0;   // capacities in 128-float rows
     int L = 0, P = 0;
     // cached plan
     struct Key {
@@ -670,6 +722,13 @@ struct bv_handle {
     std::vector<cudaEvent_t> events;
     std::vector<bv_launch_info> infos;
     int n_events = 0;
+    // bv_forward_graph: instantiated CUDA graphs of whole forwards, keyed by every argument that is baked into the nodes
+    struct GraphEntry {
+        std::vector<uintptr_t> key;
+        cudaGraphExec_t exec;
+        int launches;
+    };
+    std::vector<GraphEntry> graphs;
 };
 
 namespace {
@@ -769,19 +828,37 @@ void bv_destroy(bv_handle* h) {
     if (!h) return;
     if (h->yn) cudaFree(h->yn);
     if (h->heat_t) cudaFree(h->heat_t);
+    for (cudaEvent_t e : h->events) cudaEventDestroy(e);
+    for (auto& g : h->graphs) cudaGraphExecDestroy(g.exec);
     delete h;
 }
 
 int32_t bv_set_prompts(bv_handle* h, const float* prompts, int32_t L, int32_t P, const float* heat_text,
                        bv_stream stream) {
     if (!h || !prompts || L <= 0 || P <= 0) return fail(BV_ERR_INVALID, "bad prompt arguments");
+    int rc = device_setup();
+    if (rc) return rc;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    if (h->yn) cudaFree(h->yn);
-    if (h->heat_t) cudaFree(h->heat_t);
-    h->yn = h->heat_t = nullptr;
     const int NP = L * 2 * P;
-    BV_CUDA(cudaMalloc(&h->yn, (size_t)NP * bv::kEmbDim * sizeof(float)));
-    BV_CUDA(cudaMalloc(&h->heat_t, (size_t)L * bv::kEmbDim * sizeof(float)));
+    // The prompt buffers are reused while they are large enough: cudaFree synchronises the whole device, and callers such
+    // as Trainer.myCosineSimilarity's drop-in install prompts 2 x L times per batch.  Growing allocates the new buffers
+    // first, so a failed allocation leaves the handle's previous prompt set intact.
+    if ((size_t)NP > h->yn_cap || (size_t)L > h->heat_cap) {
+        float *yn = nullptr, *ht = nullptr;
+        const size_t yn_cap = std::max<size_t>(NP, 2 * h->yn_cap), heat_cap = std::max<size_t>(L, 2 * h->heat_cap);
+        BV_CUDA(cudaMalloc(&yn, yn_cap * bv::kEmbDim * sizeof(float)));
+        cudaError_t e = cudaMalloc(&ht, heat_cap * bv::kEmbDim * sizeof(float));
+        if (e != cudaSuccess) {
+            cudaFree(yn);
+            return fail(BV_ERR_CUDA, "cudaMalloc of the heat-map text buffer failed: %s", cudaGetErrorString(e));
+        }
+        if (h->yn) cudaFree(h->yn);          // (synchronises: kernels still reading the old set finish first)
+        if (h->heat_t) cudaFree(h->heat_t);
+        h->yn = yn;
+        h->heat_t = ht;
+        h->yn_cap = yn_cap;
+        h->heat_cap = heat_cap;
+    }
     bv::prompt_normalize_kernel<<<(NP + 3) / 4, 128, 0, st>>>(prompts, h->yn, NP);
     BV_CUDA(cudaGetLastError());
     if (heat_text) {
@@ -798,13 +875,26 @@ int32_t bv_set_prompts(bv_handle* h, const float* prompts, int32_t L, int32_t P,
     return BV_OK;
 }
 
+int32_t bv_pairwise_cosine(const float* x, const float* y, int32_t B, int32_t P, int32_t reduce_max, float* out,
+                           bv_stream stream) {
+    if (!x || !y || !out || B <= 0 || P <= 0) return fail(BV_ERR_INVALID, "bad cosine arguments");
+    int rc = device_setup();
+    if (rc) return rc;
+    const int blocks = std::min((B + 7) / 8, g_num_sms * 8);
+    bv::pairwise_cosine_kernel<<<blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, y, B, P, reduce_max, out);
+    BV_CUDA(cudaGetLastError());
+    return BV_OK;
+}
+
 int32_t bv_score(bv_handle* h, const float* emb, int32_t B, float* sim, float* prob, uint8_t* pred, float* score,
                  bv_stream stream) {
     if (!h || !emb || B <= 0) return fail(BV_ERR_INVALID, "bad score arguments");
     if (!h->yn) return fail(BV_ERR_INVALID, "bv_set_prompts has not been called");
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     bv::ScoreOut o{sim, prob, pred, score};
-    const int blocks = std::min((B + 7) / 8, 148 * 8);
+    int rc = device_setup();
+    if (rc) return rc;
+    const int blocks = std::min((B + 7) / 8, g_num_sms * 8);
     bv::score_kernel<<<blocks, 256, 0, st>>>(emb, h->yn, B, h->L, h->P, o);
     BV_CUDA(cudaGetLastError());
     return BV_OK;
@@ -980,8 +1070,11 @@ static int build_plan(bv_handle* h, const void* frames, int dtype, int B, int C,
     return BV_OK;
 }
 
-int32_t bv_forward(bv_handle* h, const void* frames, int32_t dtype, int32_t B, int32_t C, int32_t H, int32_t W,
-                   void* workspace, size_t workspace_bytes, const bv_outputs* out, bv_stream stream) {
+}  // extern "C"
+
+namespace {
+int forward_impl(bv_handle* h, const void* frames, int32_t dtype, int32_t B, int32_t C, int32_t H, int32_t W,
+                 void* workspace, size_t workspace_bytes, const bv_outputs* out, bv_stream stream) {
     if (!h || !frames || !workspace || !out) return fail(BV_ERR_INVALID, "null argument");
     if (!h->w.proj3_wt || !h->w.proj0.w || !h->w.stem_u8.w)
         return fail(BV_ERR_INVALID, "this handle was created without image-model weights (scoring only)");
@@ -1115,14 +1208,138 @@ int32_t bv_forward(bv_handle* h, const void* frames, int32_t dtype, int32_t B, i
         hp.heat_t = h->heat_t;
         const size_t smem = (size_t)(bv::kEmbDim * bv::kEmbDim + 2 * bv::kEmbDim + 8 + 4 * bv::kEmbDim) * sizeof(float);
         if (!out->patch_emb && !out->heat)
-            bv::head_global_kernel<<<B, 128, 0, st>>>(hp);
+            launch_ex(bv::head_global_kernel, B, 128, 0, st, 1, hp);
         else
-            bv::head_kernel<<<B, 256, smem, st>>>(hp);
+            launch_ex(bv::head_kernel, B, 256, smem, st, 1, hp);
         BV_CUDA(cudaGetLastError());
         ++launches;
         prof_mark(h, st, "head_score", 2.0 * B * P * 128 * 128, (double)B * P * 128 * 4);
     }
     h->last_launches = launches;
+    return BV_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int32_t bv_forward(bv_handle* h, const void* frames, int32_t dtype, int32_t B, int32_t C, int32_t H, int32_t W,
+                   void* workspace, size_t workspace_bytes, const bv_outputs* out, bv_stream stream) {
+    return forward_impl(h, frames, dtype, B, C, H, W, workspace, workspace_bytes, out, stream);
+}
+
+int32_t bv_forward_graph(bv_handle* h, const void* frames, int32_t dtype, int32_t B, int32_t C, int32_t H, int32_t W,
+                         void* workspace, size_t workspace_bytes, const bv_outputs* out, bv_stream stream) {
+    if (!h || !frames || !workspace || !out) return fail(BV_ERR_INVALID, "null argument");
+    if (h->profile) return forward_impl(h, frames, dtype, B, C, H, W, workspace, workspace_bytes, out, stream);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    auto up = [](const void* p) { return reinterpret_cast<uintptr_t>(p); };
+    const std::vector<uintptr_t> key = {up(frames), (uintptr_t)dtype, (uintptr_t)B, (uintptr_t)C, (uintptr_t)H, (uintptr_t)W,
+                                        up(workspace), (uintptr_t)workspace_bytes, up(out->global_emb), up(out->patch_emb),
+                                        (uintptr_t)out->normalize_patch, up(out->pooled), up(out->trunk_nhwc_bf16),
+                                        up(out->sim), up(out->prob), up(out->pred), up(out->score), up(out->heat),
+                                        up(h->yn), up(h->heat_t), (uintptr_t)h->L, (uintptr_t)h->P};
+    for (auto& g : h->graphs) {
+        if (g.key == key) {
+            BV_CUDA(cudaGraphLaunch(g.exec, st));
+            h->last_launches = g.launches;
+            return BV_OK;
+        }
+    }
+    // First use of this argument set: record the launches of one forward into a graph (nothing executes while the
+    // stream is capturing), instantiate it and launch it.  Tensor maps and kernel parameters are built on the host
+    // exactly as for a direct call; the capture only sees kernel / memcpy nodes and their programmatic-launch edges.
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    BV_CUDA(cudaStreamIsCapturing(st, &cs));
+    if (cs != cudaStreamCaptureStatusNone)   // the caller is capturing already: just add our nodes to its graph
+        return forward_impl(h, frames, dtype, B, C, H, W, workspace, workspace_bytes, out, stream);
+    BV_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    const int rc = forward_impl(h, frames, dtype, B, C, H, W, workspace, workspace_bytes, out, stream);
+    cudaGraph_t graph = nullptr;
+    const cudaError_t ce = cudaStreamEndCapture(st, &graph);
+    if (rc != BV_OK) {
+        if (graph) cudaGraphDestroy(graph);
+        cudaGetLastError();
+        return rc;
+    }
+    if (ce != cudaSuccess || !graph) {
+        cudaGetLastError();
+        return fail(BV_ERR_CUDA, "stream capture of the forward failed: %s", cudaGetErrorString(ce));
+    }
+    cudaGraphExec_t exec = nullptr;
+    const cudaError_t ie = cudaGraphInstantiate(&exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ie != cudaSuccess) return fail(BV_ERR_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(ie));
+    if (h->graphs.size() >= 8) {   // bounded cache: drop the oldest entry
+        cudaGraphExecDestroy(h->graphs.front().exec);
+        h->graphs.erase(h->graphs.begin());
+    }
+    h->graphs.push_back({key, exec, h->last_launches});
+    BV_CUDA(cudaGraphLaunch(exec, st));
+    return BV_OK;
+}
+
+int32_t bv_jpeg_info(const uint8_t* host_data, size_t length, int32_t* width, int32_t* height, int32_t* components) {
+    if (!host_data || length == 0 || !width || !height) return fail(BV_ERR_INVALID, "bad JPEG arguments");
+    int rc = device_setup();
+    if (rc) return rc;
+    const char* why = nullptr;
+    const jpeg_stage::Api* a = jpeg_stage::api(&why);
+    if (!a) return fail(BV_ERR_CUDA, "nvJPEG unavailable: %s", why);
+    int dev = 0;
+    BV_CUDA(cudaGetDevice(&dev));
+    jpeg_stage::Decoder* d = jpeg_stage::decoder(dev, a, &why);
+    if (!d) return fail(BV_ERR_CUDA, "nvJPEG: %s", why);
+    int ncomp = 0, ws[NVJPEG_MAX_COMPONENT] = {0}, hs[NVJPEG_MAX_COMPONENT] = {0};
+    nvjpegChromaSubsampling_t ss;
+    const nvjpegStatus_t st = a->GetImageInfo(d->handle, host_data, length, &ncomp, &ss, ws, hs);
+    if (st != NVJPEG_STATUS_SUCCESS) return fail(BV_ERR_INVALID, "not a decodable JPEG stream (nvjpegGetImageInfo status %d)", (int)st);
+    *width = ws[0];
+    *height = hs[0];
+    if (components) *components = ncomp;
+    return BV_OK;
+}
+
+int32_t bv_jpeg_decode_gray_u8(const uint8_t* host_data, size_t length, uint8_t* out, int32_t width, int32_t height,
+                               int32_t pitch, bv_stream stream) {
+    if (!host_data || length == 0 || !out || width <= 0 || height <= 0 || pitch < width)
+        return fail(BV_ERR_INVALID, "bad JPEG arguments");
+    int rc = device_setup();
+    if (rc) return rc;
+    const char* why = nullptr;
+    const jpeg_stage::Api* a = jpeg_stage::api(&why);
+    if (!a) return fail(BV_ERR_CUDA, "nvJPEG unavailable: %s", why);
+    int dev = 0;
+    BV_CUDA(cudaGetDevice(&dev));
+    jpeg_stage::Decoder* d = jpeg_stage::decoder(dev, a, &why);
+    if (!d) return fail(BV_ERR_CUDA, "nvJPEG: %s", why);
+    int ncomp = 0, ws[NVJPEG_MAX_COMPONENT] = {0}, hs[NVJPEG_MAX_COMPONENT] = {0};
+    nvjpegChromaSubsampling_t ss;
+    nvjpegStatus_t st = a->GetImageInfo(d->handle, host_data, length, &ncomp, &ss, ws, hs);
+    if (st != NVJPEG_STATUS_SUCCESS) return fail(BV_ERR_INVALID, "not a decodable JPEG stream (status %d)", (int)st);
+    if (ws[0] != width || hs[0] != height)
+        return fail(BV_ERR_INVALID, "JPEG is %dx%d but the output buffer was sized for %dx%d", ws[0], hs[0], width, height);
+    nvjpegImage_t img{};
+    img.channel[0] = out;                    // NVJPEG_OUTPUT_Y: the luma plane only (a grey JPEG's single component)
+    img.pitch[0] = static_cast<size_t>(pitch);
+    st = a->Decode(d->handle, d->state, host_data, length, NVJPEG_OUTPUT_Y, &img, reinterpret_cast<cudaStream_t>(stream));
+    if (st != NVJPEG_STATUS_SUCCESS) return fail(BV_ERR_CUDA, "nvjpegDecode failed (status %d)", (int)st);
+    return BV_OK;
+}
+
+int32_t bv_quantize_frames_f32(const float* x, int32_t B, int32_t C, int32_t H, int32_t W, uint8_t* out, int32_t* bad,
+                               bv_stream stream) {
+    if (!x || !out || !bad || B <= 0 || (C != 1 && C != 3) || H <= 0 || W <= 0) return fail(BV_ERR_INVALID, "bad frame arguments");
+    if (((long long)H * W) % 4 != 0) return fail(BV_ERR_INVALID, "H * W must be a multiple of 4");
+    if ((reinterpret_cast<uintptr_t>(x) & 15u) || (reinterpret_cast<uintptr_t>(out) & 3u))
+        return fail(BV_ERR_INVALID, "frames must be 16-byte aligned, the 8-bit output 4-byte aligned");
+    int rc = device_setup();
+    if (rc) return rc;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    BV_CUDA(cudaMemsetAsync(bad, 0, sizeof(int32_t), st));
+    const long long hw4 = (long long)H * W / 4, total4 = hw4 * B;
+    const int blocks = (int)std::min<long long>((total4 + 255) / 256, (long long)g_num_sms * 16);
+    bv::quantize_frames_kernel<<<blocks, 256, 0, st>>>(x, out, C, hw4, total4, bad);
+    BV_CUDA(cudaGetLastError());
     return BV_OK;
 }
 
@@ -1469,11 +1686,6 @@ int32_t bv_pair_gemm_test(const void* a, const void* w, int32_t M, int32_t N, in
     p.N = N;
     p.K = K;
     p.num_pair_tiles = (M + 255) / 256;
-    static bool attr = false;
-    if (!attr) {
-        BV_CUDA(cudaFuncSetAttribute(bv::pair_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bv::kPairSmemBytes));
-        attr = true;
-    }
     cudaLaunchConfig_t cfg{};
     const int pairs = std::min(p.num_pair_tiles, g_num_sms / 2);
     cfg.gridDim = dim3(2 * pairs, 1, 1);

@@ -193,6 +193,8 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_gemm_kernel(const __gr
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
+    pdl_launch_dependents();   // the next kernel's prologue may overlap this kernel's tail ...
+    pdl_wait();                // ... and this kernel touches activations only once its predecessors have completed
 
     if (Q == 0) {
         // nothing to do (the host never launches more CTAs than tiles)

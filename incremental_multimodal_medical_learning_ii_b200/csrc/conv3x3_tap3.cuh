@@ -105,6 +105,8 @@ __global__ void __launch_bounds__(kTap3Threads, 1) conv3x3_tap3_kernel(const __g
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
+    pdl_launch_dependents();   // the next kernel's prologue may overlap this kernel's tail ...
+    pdl_wait();                // ... and this kernel touches activations only once its predecessors have completed
 
     if (warp == 0) {
         // ===================== TMA producer =====================
@@ -164,19 +166,19 @@ __global__ void __launch_bounds__(kTap3Threads, 1) conv3x3_tap3_kernel(const __g
         uint32_t phase = 0;
         int it = 0;
         long long t_acc = 0, t_full = 0;
-        const long long t_begin = clock64();
+        const long long t_begin = tclock();
         mbar_wait(w_bar, 0);
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
             const int acc = it & 1;
-            long long tw = clock64();
+            long long tw = tclock();
             mbar_wait(&tmem_empty[acc], ((it >> 1) & 1u) ^ 1u);
-            t_acc += clock64() - tw;
+            t_acc += tclock() - tw;
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * 256);
             for (int tr = 0; tr < 3; ++tr) {
-                tw = clock64();
+                tw = tclock();
                 mbar_wait(&full_bar[stage], phase);
-                t_full += clock64() - tw;
+                t_full += tclock() - tw;
                 tc_fence_after();
                 if (elect_one()) {
                     const uint64_t adesc = umma_desc_k_sw128(a_base + static_cast<uint32_t>(stage * kABytes));
@@ -195,8 +197,8 @@ __global__ void __launch_bounds__(kTap3Threads, 1) conv3x3_tap3_kernel(const __g
                 }
             }
         }
-        if (p.dbg && lane == 0) {
-            p.dbg[blockIdx.x * 4 + 0] = clock64() - t_begin;
+        if (kTimingBuild && p.dbg && lane == 0) {
+            p.dbg[blockIdx.x * 4 + 0] = tclock() - t_begin;
             p.dbg[blockIdx.x * 4 + 1] = t_acc;
             p.dbg[blockIdx.x * 4 + 2] = t_full;
         }

@@ -200,6 +200,8 @@ __global__ void __launch_bounds__(gemm_threads(EPI), 1) conv_gemm_kernel(const _
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
+    pdl_launch_dependents();   // the next kernel's prologue may overlap this kernel's tail ...
+    pdl_wait();                // ... and this kernel touches activations only once its predecessors have completed
 
     if (warp == 0) {
         // ===================== TMA producer =====================
@@ -235,9 +237,9 @@ __global__ void __launch_bounds__(gemm_threads(EPI), 1) conv_gemm_kernel(const _
                 const int cblocks = p.seg[0].cblocks;
                 for (int tr = 0; tr < 3; ++tr) {
                     for (int cb = 0; cb < cblocks; ++cb) {
-                        const long long tw = clock64();
+                        const long long tw = tclock();
                         mbar_wait(&empty_bar[stage], phase ^ 1u);
-                        t_empty += clock64() - tw;
+                        t_empty += tclock() - tw;
                         if (elect_one()) {
                             mbar_arrive_expect_tx(&full_bar[stage], kWideRows * 128);
                             tma_load_im2col_4d(&p.tmA[0], &full_bar[stage], smem_a + stage * kAStage, cb * kBlockK,
@@ -265,9 +267,9 @@ __global__ void __launch_bounds__(gemm_threads(EPI), 1) conv_gemm_kernel(const _
                 const ConvSeg sg = p.seg[s];
                 int tap = 0, cb = 0, kofs = 0, tr = 0, ts = 0;
                 for (int kb = 0; kb < sg.kblocks; ++kb) {
-                    const long long tw = clock64();
+                    const long long tw = tclock();
                     mbar_wait(&empty_bar[stage], phase ^ 1u);
-                    t_empty += clock64() - tw;
+                    t_empty += tclock() - tw;
                     if (elect_one()) {
                         mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
 #pragma unroll
@@ -303,11 +305,11 @@ __global__ void __launch_bounds__(gemm_threads(EPI), 1) conv_gemm_kernel(const _
                 }
             }
         }
-        if (p.dbg && lane == 0) p.dbg[blockIdx.x * 4 + 3] = t_empty;
+        if (kTimingBuild && p.dbg && lane == 0) p.dbg[blockIdx.x * 4 + 3] = t_empty;
     } else if (warp == 1) {
         // ===================== MMA issuer (warp-convergent loop, one elected lane issues) =====================
         long long t_acc = 0, t_full = 0;
-        const long long t_begin = clock64();
+        const long long t_begin = tclock();
         constexpr uint32_t idesc = umma_idesc_bf16_f32(kBlockM, BN);
         const uint32_t a_base = smem_u32(smem_a);
         const uint32_t b_base = smem_u32(smem_b);
@@ -320,15 +322,15 @@ __global__ void __launch_bounds__(gemm_threads(EPI), 1) conv_gemm_kernel(const _
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
             const int acc = it & 1;
             const uint32_t acc_phase = (it >> 1) & 1u;
-            long long tw = clock64();
+            long long tw = tclock();
             mbar_wait(&tmem_empty[acc], acc_phase ^ 1u);
-            t_acc += clock64() - tw;
+            t_acc += tclock() - tw;
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * Cfg::kAccStageCols);
             for (int kb = 0; kb < total_kb; ++kb) {
-                tw = clock64();
+                tw = tclock();
                 mbar_wait(&full_bar[stage], phase);
-                t_full += clock64() - tw;
+                t_full += tclock() - tw;
                 tc_fence_after();
                 if constexpr (WIDE) {
                     if (elect_one()) {
@@ -391,8 +393,8 @@ __global__ void __launch_bounds__(gemm_threads(EPI), 1) conv_gemm_kernel(const _
                 }
             }
         }
-        if (p.dbg && lane == 0) {
-            p.dbg[blockIdx.x * 4 + 0] = clock64() - t_begin;
+        if (kTimingBuild && p.dbg && lane == 0) {
+            p.dbg[blockIdx.x * 4 + 0] = tclock() - t_begin;
             p.dbg[blockIdx.x * 4 + 1] = t_acc;
             p.dbg[blockIdx.x * 4 + 2] = t_full;
         }

@@ -306,6 +306,8 @@ __global__ void __launch_bounds__(kL1Threads, 1) l1_block_kernel(const __grid_co
     cluster_sync_all();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
+    pdl_launch_dependents();   // the next kernel's prologue may overlap this kernel's tail ...
+    pdl_wait();                // ... and this kernel touches activations only once its predecessors have completed
     constexpr uint32_t kD1 = 0, kD0 = 256, kD2 = 448;   // TMEM column plan
 
     // image line (global over the batch) and first output column of the four lane quarters of a tile
@@ -379,14 +381,14 @@ __global__ void __launch_bounds__(kL1Threads, 1) l1_block_kernel(const __grid_co
             int stage = 0;
             uint32_t phase = 0;
             long long tw[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // total, d0_empty, full, d1_empty, t2_ready, d2_empty, sub_written
-            const long long t_begin = clock64();
+            const long long t_begin = tclock();
             auto timed_wait = [&](uint64_t* bar, uint32_t parity, int slot) {
-                const long long a = clock64();
+                const long long a = tclock();
                 mbar_wait_cluster(bar, parity);
-                tw[slot] += clock64() - a;
+                tw[slot] += tclock() - a;
             };
             auto trace = [&](int t, int ev) {
-                if (p.dbg && pair == 0 && t >= 10 && t < 12 && lane == 0) p.dbg[2048 + (t - 10) * 32 + ev] = clock64();
+                if (kTimingBuild && p.dbg && pair == 0 && t >= 10 && t < 12 && lane == 0) p.dbg[2048 + (t - 10) * 32 + ev] = tclock();
             };
             auto g0 = [&](int t) {
                 timed_wait(d0_empty, (t & 1u) ^ 1u, 1);
@@ -461,8 +463,8 @@ __global__ void __launch_bounds__(kL1Threads, 1) l1_block_kernel(const __grid_co
                 if (t + 1 < T) g0(t + 1);
                 g2(t);
             }
-            if (p.dbg && lane == 0) {
-                tw[0] = clock64() - t_begin;
+            if (kTimingBuild && p.dbg && lane == 0) {
+                tw[0] = tclock() - t_begin;
                 for (int i = 0; i < 8; ++i) p.dbg[pair * 8 + i] = tw[i];
             }
         }
@@ -578,18 +580,18 @@ __global__ void __launch_bounds__(kL1Threads, 1) l1_block_kernel(const __grid_co
         const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
 
         long long te[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-        long long tl = clock64();
+        long long tl = tclock();
         const long long te_begin = tl;
         auto lap = [&](int slot) {   // cycles since the previous lap go to `slot`
-            const long long now = clock64();
+            const long long now = tclock();
             te[slot] += now - tl;
             tl = now;
         };
-        auto gtime = []() { unsigned long long g; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g)); return static_cast<long long>(g); };
+        auto gtime = []() { unsigned long long g = 0; if constexpr (kTimingBuild) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g)); return static_cast<long long>(g); };
         auto etrace = [&](int t, int ev) {
-            if (p.dbg && pair == 0 && rank == 0 && warp == 2 && lane == 0 && t >= 10 && t < 12) p.dbg[2048 + (t - 10) * 32 + ev] = clock64();
+            if (kTimingBuild && p.dbg && pair == 0 && rank == 0 && warp == 2 && lane == 0 && t >= 10 && t < 12) p.dbg[2048 + (t - 10) * 32 + ev] = tclock();
             // wall-clock (ns) copies for cross-SM comparison: leader at [16 + ev - 8], peer at [24 + ev - 8]
-            if (p.dbg && pair == 0 && warp == 2 && lane == 0 && t >= 10 && t < 12 && ev >= 8)
+            if (kTimingBuild && p.dbg && pair == 0 && warp == 2 && lane == 0 && t >= 10 && t < 12 && ev >= 8)
                 p.dbg[2048 + (t - 10) * 32 + (rank == 0 ? 16 : 24) + (ev - 8)] = gtime();
         };
         auto e0 = [&](int t) {
@@ -678,9 +680,9 @@ __global__ void __launch_bounds__(kL1Threads, 1) l1_block_kernel(const __grid_co
             e1(t);
             if (t + 1 < T) e0(t + 1);
         }
-        if (p.dbg && rank == 0 && warp == 2 && lane == 0) {
+        if (kTimingBuild && p.dbg && rank == 0 && warp == 2 && lane == 0) {
             for (int i = 0; i < 12; ++i) p.dbg[1024 + pair * 12 + i] = te[i];
-            p.dbg[1024 + 74 * 12 + pair] = clock64() - te_begin;
+            p.dbg[1024 + 74 * 12 + pair] = tclock() - te_begin;
         }
     }
 

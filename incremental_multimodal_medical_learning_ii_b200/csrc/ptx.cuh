@@ -13,6 +13,27 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
 
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }
 
+// Wait-cycle instrumentation (BV_TIMING=1 reports) is compiled in only with -DBV_ENABLE_TIMING=1: in the shipped
+// library tclock() is the constant 0, so every `t += tclock() - t0` and every `if (kTimingBuild && p.dbg)` folds away
+// and the producer / MMA-issuer loops carry no clock reads.
+#ifndef BV_ENABLE_TIMING
+#define BV_ENABLE_TIMING 0
+#endif
+constexpr bool kTimingBuild = (BV_ENABLE_TIMING != 0);
+__device__ __forceinline__ long long tclock() {
+    if constexpr (kTimingBuild) return clock64();
+    return 0;
+}
+
+// Programmatic dependent launch (griddepcontrol): every kernel of the forward is launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization.  launch_dependents lets the NEXT kernel's CTAs be scheduled as
+// SMs drain (their barrier init / TMEM allocation / descriptor prefetch then overlaps this kernel's tail); wait blocks
+// until every prerequisite grid has completed and its memory is visible.  All threads call pdl_wait() before their first
+// access to global memory that a previous kernel may have written (or may still be reading).  Both are no-ops when the
+// kernel was launched without the attribute.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;\n" ::: "memory"); }
+
 __device__ __forceinline__ bool elect_one() {
     uint32_t pred = 0;
     asm volatile(

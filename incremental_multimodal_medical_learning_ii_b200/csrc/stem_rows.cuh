@@ -208,6 +208,8 @@ __global__ void __launch_bounds__(sr_threads(CG), 1) stem_rows_kernel(const __gr
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
+    pdl_launch_dependents();   // the next kernel's prologue may overlap this kernel's tail ...
+    pdl_wait();                // ... and this kernel touches activations only once its predecessors have completed
 
     if (warp == 0) {
         // ---------------- raw byte producer ----------------

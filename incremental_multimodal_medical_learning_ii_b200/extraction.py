@@ -35,7 +35,9 @@ def shard_range(n_items: int, rank: int, world_size: int) -> Tuple[int, int]:
 def extract_shard(embed_fn: EmbedFn, frame_source: FrameSource, n_frames: int, batch_size: int, rank: int = 0,
                   world_size: int = 1, keys=GATHERED_KEYS) -> Dict[str, torch.Tensor]:
     """Run ``embed_fn`` over this rank's shard in batches of ``batch_size`` (the last batch may be ragged) and return
-    the concatenated per-frame results plus ``"range"`` = (start, end)."""
+    the concatenated per-frame results plus ``"range"`` = (start, end).  A rank whose shard is empty
+    (``n_frames < world_size``) returns only ``"range"``; :func:`gather_shards` still makes it take part in the
+    collective."""
     start, end = shard_range(n_frames, rank, world_size)
     out: Dict[str, torch.Tensor] = {}
     pos = 0
@@ -54,28 +56,64 @@ def extract_shard(embed_fn: EmbedFn, frame_source: FrameSource, n_frames: int, b
     return out
 
 
-def gather_shards(local: Dict[str, torch.Tensor], n_frames: int, rank: int = 0, world_size: int = 1,
-                  keys=GATHERED_KEYS) -> Dict[str, torch.Tensor]:
-    """All-gather the ranks' shard results into full ``[n_frames, ...]`` tensors in the reference's sequential order.
+def pack_rows(tensors) -> torch.Tensor:
+    """``[n, ...]`` tensors of any dtype -> ONE ``[n, row_bytes]`` uint8 tensor (each row: the rows of the inputs, byte for
+    byte, one after the other).  This is the staging buffer of the single all-gather."""
+    n = tensors[0].shape[0]
+    width = lambda t: int(t[0:1].numel()) if n else int(torch.Size(t.shape[1:]).numel())   # noqa: E731  (elements per row)
+    return torch.cat([t.contiguous().view(n, width(t)).view(torch.uint8) for t in tensors], dim=1)
 
-    Shards differ by at most one row, so every rank pads to the largest shard, ONE collective per key moves the padded
-    blocks, and the padding rows are dropped using the shard sizes (which every rank can compute locally)."""
+
+def unpack_rows(packed: torch.Tensor, specs) -> list:
+    """Inverse of :func:`pack_rows`; ``specs`` = [(trailing shape, dtype), ...] in the packing order."""
+    n, out, col = packed.shape[0], [], 0
+    for shape, dtype in specs:
+        width = int(torch.empty(0, dtype=dtype).element_size())
+        for d in shape:
+            width *= d
+        out.append(packed[:, col:col + width].reshape(-1).clone().view(dtype).view((n,) + tuple(shape)))
+        col += width
+    return out
+
+
+def gather_shards(local: Dict[str, torch.Tensor], n_frames: int, rank: int = 0, world_size: int = 1,
+                  keys=GATHERED_KEYS, specs: Optional[Dict[str, tuple]] = None, device=None) -> Dict[str, torch.Tensor]:
+    """All-gather the ranks' shard results into full ``[n_frames, ...]`` tensors in the reference's sequential order
+    with ONE collective: embeddings, probabilities and labels of a frame are packed into one byte row (582 B for 14
+    labels), every rank pads its block to the largest shard (shards differ by at most one row), one
+    ``all_gather_into_tensor`` moves the blocks, and the padding rows are dropped using the shard sizes, which every
+    rank computes locally.
+
+    ``specs`` ({key: (trailing shape, dtype)}) and ``device`` are only needed by a rank whose shard is EMPTY
+    (``n_frames < world_size``): it has no tensors to read them from but must enter the collective like every other
+    rank; when omitted they are exchanged with a small ``all_gather_object`` first."""
+    present = [k for k in keys if k in local]
     if world_size == 1:
-        return {k: local[k] for k in keys if k in local}
+        return {k: local[k] for k in present}
     sizes = [shard_range(n_frames, r, world_size) for r in range(world_size)]
     longest = max(e - s for s, e in sizes)
-    full: Dict[str, torch.Tensor] = {}
-    for k in keys:
-        if k not in local:
-            continue
-        t = local[k]
-        padded = torch.zeros((longest,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
-        padded[: t.shape[0]].copy_(t)
-        gathered = torch.empty((world_size * longest,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
-        dist.all_gather_into_tensor(gathered, padded)
-        blocks = gathered.view((world_size, longest) + tuple(t.shape[1:]))
-        full[k] = torch.cat([blocks[r, : e - s] for r, (s, e) in enumerate(sizes)], dim=0)
-    return full
+    if n_frames < world_size and specs is None:
+        mine = {k: (tuple(local[k].shape[1:]), local[k].dtype) for k in present}
+        everyone = [None] * world_size
+        dist.all_gather_object(everyone, mine)
+        specs = next(m for m in everyone if m)
+    if specs is None:
+        specs = {k: (tuple(local[k].shape[1:]), local[k].dtype) for k in present}
+    order = [k for k in keys if k in specs]
+    if present:
+        device = local[present[0]].device
+        block = pack_rows([local[k] for k in order])
+    else:
+        if device is None:
+            device = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+        block = pack_rows([torch.empty((0,) + tuple(specs[k][0]), dtype=specs[k][1], device=device) for k in order])
+    padded = torch.zeros((longest, block.shape[1]), dtype=torch.uint8, device=device)
+    padded[: block.shape[0]].copy_(block)
+    gathered = torch.empty((world_size * longest, block.shape[1]), dtype=torch.uint8, device=device)
+    dist.all_gather_into_tensor(gathered, padded)
+    blocks = gathered.view(world_size, longest, block.shape[1])
+    rows = torch.cat([blocks[r, : e - s] for r, (s, e) in enumerate(sizes)], dim=0)
+    return dict(zip(order, unpack_rows(rows, [specs[k] for k in order])))
 
 
 def save_embedding_chunks(embeddings: torch.Tensor, labels: torch.Tensor, out_dir: str, chunk: int = 5000,
@@ -123,11 +161,15 @@ def extract_embeddings(model, frame_source: FrameSource, n_frames: int, batch_si
 
 def extract_to_store(model, raw_frame_source: Callable[[int, int], torch.Tensor],
                      label_source: Callable[[int, int], torch.Tensor], n_frames: int, out_dir: str,
-                     resize: int = 512, crop: int = 480, batch_size: int = 512, chunk: int = 5000,
+                     resize: int = 512, crop: int = 512, batch_size: int = 512, chunk: int = 5000,
                      rank: int = 0, world_size: int = 1) -> list:
     """The whole ``chexpert-get-embedding.py`` job for this rank's shard, on the device end to end:
     raw 8-bit frames -> GPU Resize/CenterCrop (PIL-exact) -> ``ImageModel`` -> un-normalised ``[n,128]`` embeddings ->
     reference-format chunk files written by a background thread (``embedding_store.AsyncChunkWriter``).
+
+    The defaults are the extraction script's transform, ``DataRetrieval(size=512)`` = ``Resize(512)`` then
+    ``CenterCrop(512)`` (DataRetrieval.py:175-178; 16x16 patch grid); ``resize=512, crop=480`` is the OTHER transform of the
+    code base, ``ImageInferenceEngine``'s (image/utils.py:11-12; 15x15 grid, the benchmark's frame size).
 
     ``raw_frame_source(first, count)`` returns decoded frames ``[count,h,w]`` uint8 (same size within a call) on the
     model's device or on the host; ``label_source(first, count)`` the ``[count,5]`` labels.  Each rank writes its

@@ -60,20 +60,33 @@ class ImageModelOutput(torch.Tensor):
     __torch_function__ = torch._C._disabled_torch_function_impl
 
     @staticmethod
-    def _wrap(global_emb: torch.Tensor, model: "ImageModel", frames: torch.Tensor) -> "ImageModelOutput":
+    def _wrap(global_emb: torch.Tensor, model: "ImageModel", frames: Optional[torch.Tensor],
+              extras: Optional[Dict[str, torch.Tensor]] = None) -> "ImageModelOutput":
         out = torch.Tensor._make_subclass(ImageModelOutput, global_emb, False)
         out._model = model
-        out._frames = frames
-        out._extras = None
+        out._frames = frames                       # None when the extras were computed eagerly
+        out._frames_version = None if frames is None else frames._version
+        out._extras = extras
         return out
 
     def _full(self) -> Dict[str, torch.Tensor]:
         if getattr(self, "_extras", None) is None:
-            model = getattr(self, "_model", None)
-            if model is None:
+            model, frames = getattr(self, "_model", None), getattr(self, "_frames", None)
+            if model is None or frames is None:
                 raise AttributeError("this tensor no longer carries ImageModel outputs")
-            self._extras = model._run(self._frames, patch=True, pooled=True, trunk=True)
+            if frames._version != self._frames_version:
+                # a staging / DataLoader buffer that was refilled: the extras would describe OTHER frames than the
+                # embedding this tensor holds.  Fail instead of returning inconsistent fields.
+                raise RuntimeError("the input batch was modified in place after forward(); read the extra outputs "
+                                   "before reusing the buffer, or set model.eager_outputs = True")
+            self._extras = model._run(frames, patch=True, pooled=True, trunk=True)
+            self._frames = None                    # the input is not needed (and not kept alive) any longer
         return self._extras
+
+    def release(self) -> "ImageModelOutput":
+        """Drop the reference to the input batch (callers that keep many outputs, e.g. in a list)."""
+        self._frames = None
+        return self
 
     @property
     def projected_global_embedding(self) -> torch.Tensor:
@@ -109,6 +122,8 @@ class _Engine:
         with torch.cuda.device(device):
             N.check(self.lib.bv_create(ctypes.byref(self.handle), self.weights.pointer(), device.index or 0))
         self._workspaces: Dict[Tuple[int, int, int, int], torch.Tensor] = {}
+        self._static: Dict[tuple, dict] = {}          # forward_graphed: static buffers per call signature
+        self._bad_flag = torch.zeros(1, dtype=torch.int32, device=device)
         self.num_labels = 0
         self._prompt_keep = None
 
@@ -150,6 +165,52 @@ class _Engine:
         with torch.cuda.device(self.device):
             N.check(self.lib.bv_forward(self.handle, N.ptr(frames), dtype, B, C, H, W, N.ptr(ws), ws.numel(),
                                         ctypes.byref(outs), N.current_stream_handle(self.device)))
+
+    def quantize(self, x: torch.Tensor) -> Optional[torch.Tensor]:
+        """fp32 frames [B,C,H,W] -> uint8 [B,1,H,W] when they are 8-bit data (k/255, identical channels), else None.
+        One kernel + one 4-byte flag read (the only host synchronisation of a float-input call)."""
+        B, C, H, W = x.shape
+        u8 = torch.empty(B, 1, H, W, dtype=torch.uint8, device=self.device)
+        with torch.cuda.device(self.device):
+            N.check(self.lib.bv_quantize_frames_f32(N.ptr(x), B, C, H, W, N.ptr(u8), N.ptr(self._bad_flag),
+                                                    N.current_stream_handle(self.device)))
+        return u8 if int(self._bad_flag.item()) == 0 else None
+
+    def forward_graphed(self, frames: torch.Tensor, shapes, normalize_patch: bool) -> Dict[str, torch.Tensor]:
+        """Small-batch path: static input / output buffers per call signature, the whole forward replayed as ONE CUDA
+        graph launch (``bv_forward_graph``), results returned as copies of the static outputs (one packed buffer, one
+        copy).  The reference's extraction loop calls the model with batch size 1 (chexpert-get-embedding.py:47-49):
+        45 launches of a few microseconds each are launch-bound, a graph replay is not."""
+        B, C, H, W = frames.shape
+        key = (B, C, H, W, frames.dtype, tuple(sorted(shapes)), bool(normalize_patch), self.num_labels)
+        st = self._static.get(key)
+        if st is None:
+            if len(self._static) >= 4:
+                self._static.pop(next(iter(self._static)))
+            offs, total = {}, 0
+            for k, (shape, dt) in shapes.items():
+                nbytes = int(torch.empty(0, dtype=dt).element_size())
+                for d in shape:
+                    nbytes *= d
+                offs[k] = (total, nbytes)
+                total += (nbytes + 255) // 256 * 256
+            packed = torch.empty(max(total, 256), dtype=torch.uint8, device=self.device)
+            views = {k: packed[o:o + n].view(shapes[k][1]).view(shapes[k][0]) for k, (o, n) in offs.items()}
+            outs = N.BvOutputs()
+            outs.normalize_patch = 1 if normalize_patch else 0
+            for k, t in views.items():
+                setattr(outs, _OUT_FIELD[k], t.data_ptr())
+            st = {"frames": torch.empty_like(frames), "packed": packed, "offs": offs, "outs": outs,
+                  "ws": torch.empty(self.lib.bv_workspace_bytes(B, C, H, W), dtype=torch.uint8, device=self.device)}
+            self._static[key] = st
+        st["frames"].copy_(frames)
+        dtype = N.BV_DTYPE_U8 if frames.dtype == torch.uint8 else N.BV_DTYPE_F32
+        with torch.cuda.device(self.device):
+            N.check(self.lib.bv_forward_graph(self.handle, N.ptr(st["frames"]), dtype, B, C, H, W, N.ptr(st["ws"]),
+                                              st["ws"].numel(), ctypes.byref(st["outs"]),
+                                              N.current_stream_handle(self.device)))
+        result = st["packed"].clone()
+        return {k: result[o:o + n].view(shapes[k][1]).view(shapes[k][0]) for k, (o, n) in st["offs"].items()}
 
     def score(self, emb: torch.Tensor) -> Dict[str, torch.Tensor]:
         B = emb.shape[0]
@@ -196,6 +257,11 @@ class ImageEncoder(nn.Module):
             raise NotImplementedError("BioViL uses resnet50; the B200 path implements the Bottleneck trunk only")
         return resnet50(pretrained=True, **kwargs)
 
+    def __getstate__(self):
+        state = self.__dict__.copy()
+        state["_owner"] = None                  # weak reference to the owning ImageModel: re-made by its __setstate__
+        return state
+
     def forward(self, x: torch.Tensor, return_patch_embeddings: bool = False) -> TypeImageEncoder:
         owner = object.__getattribute__(self, "_owner")
         if owner is None:
@@ -241,7 +307,10 @@ class ImageModel(nn.Module):
         self.encoder._owner = weakref.ref(self)
         self._engine: Optional[_Engine] = None
         self._engine_version = None
+        self._version_tensors = None
         self._prompts = None
+        self.eager_outputs = False      # forward() computes patch / pooled / trunk outputs eagerly instead of on access
+        self.cuda_graphs = "auto"       # replay small batches as one CUDA graph launch: True, False or "auto" (B <= 32)
         self.train()
 
         if pretrained_model_path is not None:
@@ -260,6 +329,9 @@ class ImageModel(nn.Module):
         return self
 
     def forward(self, x: torch.Tensor) -> ImageModelOutput:
+        if self.eager_outputs:                     # every upstream field in the same pass; the input is not retained
+            res = self._run(x, patch=True, pooled=True, trunk=True)
+            return ImageModelOutput._wrap(res["global"], self, None, res)
         res = self._run(x)
         return ImageModelOutput._wrap(res["global"], self, x)
 
@@ -322,51 +394,74 @@ class ImageModel(nn.Module):
         return eng.score(emb.to(eng.device, torch.float32).contiguous())
 
     # ---- machinery ----------------------------------------------------------------------------------------
+    GRAPH_MAX_BATCH = 32     # "auto": batches up to this size are launch-bound (45 launches of a few microseconds each)
+
     def _apply(self, fn, *args, **kwargs):
         self._engine = None
+        self._version_tensors = None
         return super()._apply(fn, *args, **kwargs)
 
     def load_state_dict(self, *args, **kwargs):
         self._engine = None
+        self._version_tensors = None
         return super().load_state_dict(*args, **kwargs)
 
+    def __getstate__(self):
+        # the native handle (ctypes) and the packed weights are a cache derived from the parameters: never pickled / copied
+        state = self.__dict__.copy()
+        state["_engine"] = None
+        state["_engine_version"] = None
+        state["_version_tensors"] = None
+        return state
+
+    def __setstate__(self, state):
+        self.__dict__.update(state)
+        import weakref
+        self.encoder._owner = weakref.ref(self)
+
     def _param_version(self):
-        return sum(int(t._version) for t in list(self.parameters()) + list(self.buffers()))
+        # in-place updates of any parameter / buffer bump its version counter; the tensor list itself is cached (walking
+        # the module tree costs ~0.2 ms, which is most of a batch-1 call) and rebuilt when the module is moved / reloaded
+        if self._version_tensors is None:
+            self._version_tensors = list(self.parameters()) + list(self.buffers())
+        return sum(t._version for t in self._version_tensors)
 
     def _get_engine(self) -> _Engine:
-        device = next(self.parameters()).device
         version = self._param_version()
+        device = self._version_tensors[0].device
         if self._engine is None or self._engine.device != device or self._engine_version != version:
+            self._version_tensors = None
+            version = self._param_version()
             self._engine = _Engine(self.state_dict(), device)
             self._engine_version = version
             if self._prompts is not None:
                 self._engine.set_prompts(*self._prompts)
         return self._engine
 
-    def _prepare_frames(self, x: torch.Tensor, device: torch.device) -> torch.Tensor:
+    def _prepare_frames(self, x: torch.Tensor, eng: "_Engine") -> torch.Tensor:
+        device = eng.device
         if x.dim() != 4 or x.shape[1] not in (1, 3):
             raise ValueError(f"expected frames [B, 1|3, H, W], got {tuple(x.shape)}")
         if x.device != device:
             raise RuntimeError(f"input is on {x.device} but the model is on {device}")
+        if x.shape[2] % 32 or x.shape[3] % 32:
+            raise ValueError(f"frame size {x.shape[2]}x{x.shape[3]} must be a multiple of 32")
         if x.dtype == torch.uint8:
             if x.shape[1] == 3:
                 if not bool((x[:, :1] == x).all()):
                     raise ValueError("uint8 frames with three different channels are not a BioViL input")
                 x = x[:, :1]
             return x.contiguous()
-        x = x.float()
+        x = x.float().contiguous()
         # Frames made by ToTensor + ExpandChannels (transforms.py:12-38) are k/255 with identical channels: send the
-        # exact 8-bit integers through the single-channel stem instead of rounding k/255 to bf16.
-        one = x[:, :1]
-        same = x.shape[1] == 1 or bool((one == x).all())
-        if same:
-            k255 = one * 255.0
-            k = torch.round(k255)
-            # |x*255 - k| far below one grey level: the frame is 8-bit data (ToTensor's k/255 up to fp32 rounding)
-            if bool(((k255 - k).abs() <= 1e-3).all()) and bool(((k >= 0) & (k <= 255)).all()):
-                return k.to(torch.uint8).contiguous()
-            return one.contiguous()
-        return x.contiguous()
+        # exact 8-bit integers through the single-channel stem instead of rounding k/255 to bf16.  One kernel converts
+        # and validates (|x*255 - k| <= 1e-3 grey levels, 0 <= k <= 255, channels equal); one flag read decides.
+        u8 = eng.quantize(x)
+        if u8 is not None:
+            return u8
+        if x.shape[1] == 3 and bool((x[:, :1] == x).all()):
+            return x[:, :1].contiguous()
+        return x
 
     def _run(self, x: torch.Tensor, want_global: bool = True, patch: bool = False, normalize_patch: bool = False,
              pooled: bool = False, trunk: bool = False, score: bool = False, heat: bool = False):
@@ -376,39 +471,42 @@ class ImageModel(nn.Module):
         eng = self._get_engine()
         dev = eng.device
         with torch.no_grad():
-            frames = self._prepare_frames(x, dev)
+            frames = self._prepare_frames(x, eng)
             B, C, H, W = frames.shape
-            if H % 32 or W % 32:
-                raise ValueError(f"frame size {H}x{W} must be a multiple of 32")
             gh, gw = H // 32, W // 32
             L = eng.num_labels
-            f32 = dict(dtype=torch.float32, device=dev)
-            res: Dict[str, torch.Tensor] = {}
+            shapes = {}
             if want_global or score:
-                res["global"] = torch.empty(B, JOINT_FEATURE_SIZE, **f32)
+                shapes["global"] = ((B, JOINT_FEATURE_SIZE), torch.float32)
             if patch:
-                res["patch"] = torch.empty(B, gh, gw, JOINT_FEATURE_SIZE, **f32)
+                shapes["patch"] = ((B, gh, gw, JOINT_FEATURE_SIZE), torch.float32)
             if pooled:
-                res["pooled"] = torch.empty(B, 2048, **f32)
+                shapes["pooled"] = ((B, 2048), torch.float32)
             if trunk:
-                res["trunk"] = torch.empty(B, gh, gw, 2048, dtype=torch.bfloat16, device=dev)
+                shapes["trunk"] = ((B, gh, gw, 2048), torch.bfloat16)
             if score:
-                res["sim"] = torch.empty(B, L, 2, **f32)
-                res["prob"] = torch.empty(B, L, **f32)
-                res["pred"] = torch.empty(B, L, dtype=torch.uint8, device=dev)
-                res["score"] = torch.empty(B, L, **f32)
+                shapes["sim"] = ((B, L, 2), torch.float32)
+                shapes["prob"] = ((B, L), torch.float32)
+                shapes["pred"] = ((B, L), torch.uint8)
+                shapes["score"] = ((B, L), torch.float32)
             if heat:
-                res["heat"] = torch.empty(B, gh, gw, L, **f32)
-            field = {"global": "global_emb", "patch": "patch_emb", "pooled": "pooled", "trunk": "trunk_nhwc_bf16",
-                     "sim": "sim", "prob": "prob", "pred": "pred", "score": "score", "heat": "heat"}
+                shapes["heat"] = ((B, gh, gw, L), torch.float32)
+            graphs = self.cuda_graphs
+            if (graphs is True or (graphs == "auto" and B <= self.GRAPH_MAX_BATCH)) and B <= self.MAX_BATCH:
+                return eng.forward_graphed(frames, shapes, normalize_patch)
+            res = {k: torch.empty(shape, dtype=dt, device=dev) for k, (shape, dt) in shapes.items()}
             for b0 in range(0, B, self.MAX_BATCH):
                 b1 = min(B, b0 + self.MAX_BATCH)
                 outs = N.BvOutputs()
                 outs.normalize_patch = 1 if normalize_patch else 0
                 for k, t in res.items():
-                    setattr(outs, field[k], t[b0:b1].data_ptr())
+                    setattr(outs, _OUT_FIELD[k], t[b0:b1].data_ptr())
                 eng.forward(frames[b0:b1], outs)
         return res
+
+
+_OUT_FIELD = {"global": "global_emb", "patch": "patch_emb", "pooled": "pooled", "trunk": "trunk_nhwc_bf16",
+              "sim": "sim", "prob": "prob", "pred": "pred", "score": "score", "heat": "heat"}
 
 
 def get_biovil_resnet(pretrained) -> ImageModel:

@@ -12,7 +12,7 @@ stay on torch.  The text encoder is not part of this path: prompts arrive as ``[
 from __future__ import annotations
 
 import ctypes
-from typing import Dict, Optional
+from typing import Dict
 
 import torch
 
@@ -75,28 +75,36 @@ class ZeroShotScorer:
         return out
 
 
-_default_scorer: Optional[ZeroShotScorer] = None
-
-
 @torch.no_grad()
 def my_cosine_similarity(x: torch.Tensor, y: torch.Tensor, use_grad: bool = False, to_plot: bool = False,
                          train: bool = False, pos: bool = True, max_emb: bool = False) -> torch.Tensor:
     """Drop-in for ``Trainer.myCosineSimilarity(x, y, ...)`` (Trainer.py:1682-1704) in no-grad mode.
 
-    ``x`` [B,128] image embeddings, ``y`` [1,128] (mean prompt embedding) or [P,128] with ``max_emb`` (max over the P
-    per-prompt cosines).  Returns ``[B,1]`` like the reference."""
-    global _default_scorer
+    ``x`` [B,128] image embeddings, ``y`` [128] / [1,128] (mean prompt embedding) or [P,128] with ``max_emb`` (max over
+    the P per-prompt cosines, :1691-1694).  Returns ``[B,1]`` (``[B]`` with ``max_emb``, as ``torch.max(res, dim=1)``
+    does in the reference); ``to_plot`` compares one vector with one vector (:1687-1688) -> ``[1,1]``.
+    One stateless kernel launch (``bv_pairwise_cosine``): no prompt installation, no allocation besides the result."""
     if use_grad:
         raise RuntimeError("the CUDA scorer is inference-only; keep training-time cosines on torch autograd")
+    if not x.is_cuda:
+        raise RuntimeError("my_cosine_similarity runs on a CUDA device (sm_100a); there is no CPU fallback")
     dev = x.device
-    if _default_scorer is None or _default_scorer.device != dev:
-        _default_scorer = ZeroShotScorer(dev)
-    y = y.reshape(-1, y.shape[-1])
-    if not max_emb and y.shape[0] != 1:
-        raise ValueError("without max_emb the reference compares against a single [1,128] embedding")
-    prompts = torch.stack([y, y], dim=0).unsqueeze(0)            # [1, 2, P, 128]: same vectors as pos and neg
-    _default_scorer.set_prompts(prompts, reduce="max")
-    return _default_scorer.score(x)["sim"][:, 0, :1].contiguous()
+    if to_plot:
+        x = x.reshape(1, -1)
+        y = y.reshape(1, -1)
+    else:
+        y = y.reshape(1, -1) if not max_emb else y.reshape(-1, y.shape[-1])
+    x = x.to(torch.float32).contiguous()
+    y = y.to(dev, torch.float32).contiguous()
+    if x.dim() != 2 or x.shape[1] != 128 or y.shape[1] != 128:
+        raise ValueError(f"expected [B,128] embeddings against [P,128] prompts, got {tuple(x.shape)} and {tuple(y.shape)}")
+    B, P = x.shape[0], y.shape[0]
+    reduce_max = bool(max_emb and not to_plot)
+    out = torch.empty((B,) if reduce_max else (B, P), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        N.check(N.lib().bv_pairwise_cosine(N.ptr(x), N.ptr(y), B, P, 1 if reduce_max else 0, N.ptr(out),
+                                           N.current_stream_handle(dev)))
+    return out
 
 
 class TrainerEvalScorer:
@@ -131,3 +139,89 @@ class TrainerEvalScorer:
         tmp_score = (pos - neg + 2) / 4 if self.pred_logit_diff else r["score"]
         logits = r["logit"] if self.train_logit_diff else pos
         return {"predicted_labels": r["pred"].float(), "tmp_score": tmp_score, "logits": logits, "sim": r["sim"]}
+
+
+def _trainer_switches(trainer):
+    """The module-level switches of the reference's ``Trainer.py`` (:41-56) as the trainer's own module holds them."""
+    mod = type(trainer).__init__.__globals__             # the globals of the module that defines the class
+    return mod, {k: bool(mod[k]) for k in ("IMAGE_MODEL", "TEXT_MODEL", "MAX_EMB", "TRAIN_LOGIT_DIFF", "PRED_LOGIT_DIFF")}
+
+
+@torch.no_grad()
+def trainer_prompt_tensor(trainer) -> torch.Tensor:
+    """``[L,2,P,128]`` prompt embeddings of a reference ``Trainer``: ``bert_forward_mean`` (Trainer.py:1657-1680, text
+    adapter included) called ONCE per label instead of once per label and batch (:816, :1030) - in evaluation the
+    prompts and both adapters are constant.  Mean-reduced prompts arrive as ``[128]`` (P = 1); with ``MAX_EMB`` the
+    per-prompt rows are kept and ragged prompt lists are padded by repeating a row (the max is unchanged)."""
+    _, sw = _trainer_switches(trainer)
+    rows = []
+    for label_name in trainer.class_names:
+        pos_prompt = trainer.prompts[label_name]["positive"]
+        neg_prompt = trainer.prompts[label_name]["negative"] if sw["TRAIN_LOGIT_DIFF"] else pos_prompt   # :809-814
+        pos_e, neg_e = trainer.bert_forward_mean(pos_prompt, neg_prompt, use_grad=False)
+        rows.append([e.reshape(-1, e.shape[-1]).float() for e in (pos_e, neg_e)])
+    P = max(e.shape[0] for pair in rows for e in pair)
+    pad = lambda e: torch.cat([e, e[:1].expand(P - e.shape[0], -1)]) if e.shape[0] < P else e   # noqa: E731
+    return torch.stack([torch.stack([pad(p), pad(n)]) for p, n in rows])
+
+
+def patch_trainer_eval(trainer, scorer_factory=None):
+    """Make a reference ``Trainer`` instance evaluate on the fused scorer: ``trainer.val`` / ``trainer.test`` keep their
+    signatures and everything around the label loop (adapters, ``change_labels``, criterion, TensorBoard scalar,
+    ``evaluate_model``, the plots after ``test``: Trainer.py:773-866, 989-1072), but the 2 x L ``myCosineSimilarity``
+    calls and the 2 x L CXR-BERT forwards per batch become one prompt installation per call and one kernel launch per
+    batch (``TrainerEvalScorer``).  Returns the trainer.
+
+    ``scorer_factory(prompts, device, train_logit_diff, pred_logit_diff, max_emb)`` builds the per-batch scorer; the
+    default is the CUDA ``TrainerEvalScorer`` (no CPU fallback).  Tests inject the oracle here to check this plumbing
+    against the unpatched reference loop on a machine without a GPU."""
+    mod, _ = _trainer_switches(trainer)
+    factory = scorer_factory or (lambda prompts, device, tld, pld, mx: TrainerEvalScorer(prompts, device, tld, pld, mx))
+
+    def _evaluate(loader, criterion, epoch, split, desc):
+        _, sw = _trainer_switches(trainer)              # read at call time: scripts flip the switches between runs
+        if sw["IMAGE_MODEL"]:
+            trainer.image_adapter.eval()
+        if sw["TEXT_MODEL"]:
+            trainer.text_adapter.eval()
+        scorer = factory(trainer_prompt_tensor(trainer), trainer.device, sw["TRAIN_LOGIT_DIFF"], sw["PRED_LOGIT_DIFF"],
+                         sw["MAX_EMB"])
+        y_true, y_pred, y_score = [], [], []
+        for batch_idx, (embs, labels) in enumerate(mod["tqdm"](loader, desc=desc), start=1):
+            embs, labels = embs.to(trainer.device), labels.to(trainer.device)
+            new_embs = trainer.image_adapter(embs) if sw["IMAGE_MODEL"] else embs
+            r = scorer(new_embs)
+            kept = labels
+            if criterion is not None:                   # val only (:839-848)
+                if trainer.change_labels:
+                    labels = mod["change_values"](labels)
+                loss = criterion(r["logits"], labels)
+                if trainer.writer is not None:
+                    trainer.writer.add_scalar(f"{split}/Loss", loss.item(), (epoch - 1) * len(loader) + batch_idx)
+            y_true.append(kept.cpu().numpy())
+            y_pred.append(r["predicted_labels"].cpu().numpy())
+            y_score.append(r["tmp_score"].cpu().numpy())
+        import numpy as np
+        return np.concatenate(y_true), np.concatenate(y_pred), np.concatenate(y_score), sw
+
+    @torch.no_grad()
+    def val(val_loader, criterion, epoch, epochs, mode="joint", tasks_order=None):
+        y_true, y_pred, y_score, _ = _evaluate(val_loader, criterion, epoch, "val",
+                                               "Validating on chexpert mode: " + mode + ", Epoch " + str(epoch))
+        trainer.evaluate_model(y_true, y_pred, y_score, mode, epoch, "val", epochs, tasks_order)
+
+    @torch.no_grad()
+    def test(test_loader, criterion, epoch, epochs, mode="joint", tasks_order=None, plot_tsne_array=None):
+        y_true, y_pred, y_score, sw = _evaluate(test_loader, None, epoch, "test", "Testing on chexpert mode: " + mode)
+        trainer.evaluate_model(y_true, y_pred, y_score, mode, epoch, "test", epochs, tasks_order)
+        if sw["TRAIN_LOGIT_DIFF"]:                      # :1062-1072
+            trainer.plot_cosine_similarity_text_embs(epoch, epochs)
+        else:
+            trainer.plot_cosine_similarity_text_embs_only_pos_prompts(epoch, epochs)
+        trainer.plot_new_text_embeddings(epoch, epochs)
+        if plot_tsne_array is not None:
+            trainer.plot_tsne_sani_malati(plot_tsne_array[1], epoch, epochs)
+            trainer.plot_tsne_multiclass(plot_tsne_array[0], epoch, epochs)
+
+    trainer.val, trainer.test = val, test
+    return trainer

@@ -1,72 +1,9 @@
-"""Deterministic random-init BioViL ``state_dict`` for the parity tests (TEST INFRASTRUCTURE ONLY).
+"""Seeded random-init BioViL ``state_dict`` for the parity tests (TEST INFRASTRUCTURE ONLY).
 
-The real BioViL checkpoint cannot be downloaded (no network), so goldens use seeded random weights with the same
-distributions the reference's constructors use: torchvision ResNet convs ``kaiming_normal_(fan_out, relu)``, BatchNorm
-identity (gamma 1, beta 0, mean 0, var 1), projector convs / fc PyTorch-default ``kaiming_uniform_(a=sqrt(5))``.
-Built from an explicit ``torch.Generator`` on CPU so the GPU box regenerates the same tensors without
-``/root/reference``.  Keys, shapes and dtypes equal the reference's 328-key state_dict (checked in
-``oracle/make_golden.py`` against the reference itself).
+The generator itself is input data shared with the benchmark, so it lives in the package
+(``incremental_multimodal_medical_learning_ii_b200/synthetic_weights.py``); this module re-exports it under the name the
+tests and ``oracle/make_golden.py`` have always used.  ``oracle/make_golden.py`` checks keys, shapes and dtypes of the
+result against the reference's own ``ImageModel.state_dict()``.
 """
-from __future__ import annotations
-
-import math
-from collections import OrderedDict
-from typing import Dict
-
-import torch
-
-from biovil_oracle import LAYER_PLAN, LAYER_WIDTH, EXPANSION, randomize_batchnorm_
-
-
-def _kaiming_normal(g, cout, cin, k):
-    std = math.sqrt(2.0 / (cout * k * k))
-    return torch.randn(cout, cin, k, k, generator=g) * std
-
-
-def _uniform(g, shape, bound):
-    return (torch.rand(*shape, generator=g) * 2.0 - 1.0) * bound
-
-
-def _bn(sd, name, n):
-    sd[name + ".weight"] = torch.ones(n)
-    sd[name + ".bias"] = torch.zeros(n)
-    sd[name + ".running_mean"] = torch.zeros(n)
-    sd[name + ".running_var"] = torch.ones(n)
-    sd[name + ".num_batches_tracked"] = torch.tensor(0, dtype=torch.long)
-
-
-def make_state_dict(seed: int = 27, randomize_bn: bool = False, bn_seed: int = 28) -> Dict[str, torch.Tensor]:
-    g = torch.Generator().manual_seed(seed)
-    sd: Dict[str, torch.Tensor] = OrderedDict()
-    e = "encoder.encoder."
-    sd[e + "conv1.weight"] = _kaiming_normal(g, 64, 3, 7)
-    _bn(sd, e + "bn1", 64)
-    inplanes = 64
-    for li, (n, width) in enumerate(zip(LAYER_PLAN, LAYER_WIDTH), start=1):
-        for bi in range(n):
-            p = f"{e}layer{li}.{bi}"
-            sd[p + ".conv1.weight"] = _kaiming_normal(g, width, inplanes, 1)
-            _bn(sd, p + ".bn1", width)
-            sd[p + ".conv2.weight"] = _kaiming_normal(g, width, width, 3)
-            _bn(sd, p + ".bn2", width)
-            sd[p + ".conv3.weight"] = _kaiming_normal(g, width * EXPANSION, width, 1)
-            _bn(sd, p + ".bn3", width * EXPANSION)
-            if bi == 0:
-                sd[p + ".downsample.0.weight"] = _kaiming_normal(g, width * EXPANSION, inplanes, 1)
-                _bn(sd, p + ".downsample.1", width * EXPANSION)
-            inplanes = width * EXPANSION
-    sd[e + "fc.weight"] = _uniform(g, (1000, 2048), 1.0 / math.sqrt(2048))
-    sd[e + "fc.bias"] = _uniform(g, (1000,), 1.0 / math.sqrt(2048))
-    pm = "projector.model."
-    sd[pm + "0.weight"] = _uniform(g, (128, 2048, 1, 1), 1.0 / math.sqrt(2048))
-    _bn(sd, pm + "1", 128)
-    sd[pm + "3.weight"] = _uniform(g, (128, 128, 1, 1), 1.0 / math.sqrt(128))
-    sd[pm + "3.bias"] = _uniform(g, (128,), 1.0 / math.sqrt(128))
-    if randomize_bn:
-        randomize_batchnorm_(sd, seed=bn_seed)
-    return sd
-
-
-def state_dict_checksum(sd: Dict[str, torch.Tensor]) -> float:
-    """Order-independent fingerprint (sum of |w| in float64 over floating tensors)."""
-    return float(sum(v.double().abs().sum() for v in sd.values() if v.is_floating_point()))
+from incremental_multimodal_medical_learning_ii_b200.synthetic_weights import (  # noqa: F401
+    make_state_dict, randomize_batchnorm_, state_dict_checksum)

@@ -14,7 +14,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "oracle"))
 import biovil_oracle as O  # noqa: E402
-import weights as Wt  # noqa: E402
+from incremental_multimodal_medical_learning_ii_b200 import synthetic_weights as Wt  # noqa: E402
 from incremental_multimodal_medical_learning_ii_b200 import frames as FR  # noqa: E402
 
 

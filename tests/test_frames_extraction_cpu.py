@@ -56,13 +56,18 @@ def _worker(rank, world, n, port, outdir):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         local = extract_shard(_stub_embed, _source, n, batch_size=4, rank=rank, world_size=world)
+        calls = []
+        real = dist.all_gather_into_tensor
+        dist.all_gather_into_tensor = lambda out, inp, *a, **k: (calls.append(tuple(inp.shape)), real(out, inp, *a, **k))[1]
         full = gather_shards(local, n, rank, world)
+        dist.all_gather_into_tensor = real
+        assert len(calls) == 1, calls            # ONE collective for embeddings + probabilities + labels
         torch.save((rank, full, local["range"].tolist()), os.path.join(outdir, f"rank{rank}.pt"))
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("n", [23, 16])
+@pytest.mark.parametrize("n", [23, 16, 1])        # n = 1: rank 1 owns an EMPTY shard and must still enter the collective
 def test_two_rank_extraction_matches_sequential(n, tmp_path):
     world = 2
     seq = extract_shard(_stub_embed, _source, n, batch_size=5)
@@ -94,3 +99,16 @@ def test_embedding_store_layout(tmp_path):
     glued = torch.utils.data.ConcatDataset(parts)                  # CSV_reformatting/glue_dataset.py:33-38
     assert torch.equal(torch.cat([d.tensors[0] for d in glued.datasets]), emb)     # Trainer.py:1252-1271 access pattern
     assert torch.equal(torch.cat([d.tensors[1] for d in glued.datasets]), labels)
+
+
+def test_pack_and_unpack_rows_round_trip():
+    from incremental_multimodal_medical_learning_ii_b200.extraction import pack_rows, unpack_rows
+    g = torch.Generator().manual_seed(0)
+    emb, prob = torch.randn(7, 128, generator=g), torch.rand(7, 14, generator=g)
+    pred = (prob > 0.5).to(torch.uint8)
+    packed = pack_rows([emb, prob, pred])
+    assert packed.shape == (7, 128 * 4 + 14 * 4 + 14) and packed.dtype == torch.uint8       # 582 bytes per frame
+    e2, p2, d2 = unpack_rows(packed, [((128,), torch.float32), ((14,), torch.float32), ((14,), torch.uint8)])
+    assert torch.equal(e2, emb) and torch.equal(p2, prob) and torch.equal(d2, pred)
+    empty = pack_rows([emb[:0], prob[:0], pred[:0]])
+    assert empty.shape == (0, 582)

@@ -9,7 +9,7 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "oracle"))
-import weights as Wt  # noqa: E402
+from incremental_multimodal_medical_learning_ii_b200 import synthetic_weights as Wt  # noqa: E402
 from incremental_multimodal_medical_learning_ii_b200 import frames as FR  # noqa: E402
 from incremental_multimodal_medical_learning_ii_b200.image import get_biovil_resnet  # noqa: E402
 

@@ -1,6 +1,6 @@
 import os, sys, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "oracle"))
-import weights as Wt
+from incremental_multimodal_medical_learning_ii_b200 import synthetic_weights as Wt
 from incremental_multimodal_medical_learning_ii_b200 import frames as FR
 from incremental_multimodal_medical_learning_ii_b200.image import get_biovil_resnet
 m = get_biovil_resnet(None); m.load_state_dict(Wt.make_state_dict(27)); m.eval().to("cuda:0")
