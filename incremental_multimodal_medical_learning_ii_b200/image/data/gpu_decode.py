@@ -1,0 +1,70 @@
+"""GPU JPEG decode in front of the GPU resize (the stage VERDICT r1 listed as absent).
+
+The reference decodes every radiograph on the host: ``torchvision.io.read_image`` in ``CustomDataset.__getitem__``
+(DataRetrieval.py:70-96) inside 4 DataLoader worker processes, then PIL resizes it (:175-180).  Here the compressed
+bytes go to nvJPEG (``bv_jpeg_decode_gray_u8``; a library call, resolved with ``dlopen``), the 8-bit luma plane lands in
+device memory and ``GpuResizeCenterCrop`` + the stem kernel take it from there: decoded pixels never exist on the host.
+
+Parity: JPEG decoders differ in IDCT rounding, so this stage - unlike the resize - is not bit-exact against the
+reference's libjpeg path; ``tests/test_jpeg_gpu.py`` bounds the difference at 2 grey levels per pixel (the tolerance is
+stated there) and shows the embedding of a decoded + resized frame stays within the north_star cosine bound.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import List, Sequence, Tuple, Union
+
+import torch
+
+from ... import _native as N
+from .gpu_transforms import GpuResizeCenterCrop
+
+Bytes = Union[bytes, bytearray, memoryview]
+
+
+class GpuJpegDecoder:
+    """Decodes grey (or colour: luma plane) JPEG streams held in host memory into uint8 ``[h,w]`` CUDA tensors."""
+
+    def __init__(self, device="cuda:0"):
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("GpuJpegDecoder needs a CUDA device (the host path is the reference's own PIL decode)")
+        self.lib = N.lib()
+
+    @staticmethod
+    def _buffer(data: Bytes):
+        buf = (ctypes.c_uint8 * len(data)).from_buffer_copy(data)       # nvJPEG parses the stream on the host
+        return buf, len(data)
+
+    def info(self, data: Bytes) -> Tuple[int, int, int]:
+        """``(width, height, components)`` from the JPEG header."""
+        buf, n = self._buffer(data)
+        w, h, c = ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32()
+        with torch.cuda.device(self.device):
+            N.check(self.lib.bv_jpeg_info(buf, n, ctypes.byref(w), ctypes.byref(h), ctypes.byref(c)))
+        return w.value, h.value, c.value
+
+    def decode(self, data: Bytes) -> torch.Tensor:
+        buf, n = self._buffer(data)
+        w, h, c = ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32()
+        with torch.cuda.device(self.device):
+            N.check(self.lib.bv_jpeg_info(buf, n, ctypes.byref(w), ctypes.byref(h), ctypes.byref(c)))
+            out = torch.empty(h.value, w.value, dtype=torch.uint8, device=self.device)
+            N.check(self.lib.bv_jpeg_decode_gray_u8(buf, n, N.ptr(out), w.value, h.value, w.value,
+                                                    N.current_stream_handle(self.device)))
+        return out
+
+    def decode_batch(self, datas: Sequence[Bytes]) -> List[torch.Tensor]:
+        return [self.decode(d) for d in datas]
+
+
+class GpuJpegPipeline:
+    """``read_image -> Resize(size) -> CenterCrop(crop)`` of the reference's dataset pipeline (DataRetrieval.py:70-96,
+    175-180) on the device: JPEG bytes in, the ``[n,1,crop,crop]`` uint8 batch ``ImageModel`` takes out."""
+
+    def __init__(self, device="cuda:0", resize: int = 512, center_crop_size: int = 512):
+        self.decoder = GpuJpegDecoder(device)
+        self.transform = GpuResizeCenterCrop(resize, center_crop_size)
+
+    def __call__(self, datas: Sequence[Bytes]) -> torch.Tensor:
+        return self.transform(self.decoder.decode_batch(datas))

@@ -415,7 +415,7 @@ class ImageModel(nn.Module):
         return state
 
     def __setstate__(self, state):
-        self.__dict__.update(state)
+        super().__setstate__(state)
         import weakref
         self.encoder._owner = weakref.ref(self)
 

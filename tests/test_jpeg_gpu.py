@@ -1,0 +1,81 @@
+"""GPU JPEG decode stage (nvJPEG behind bv_jpeg_decode_gray_u8) against the reference's host decode (PIL / libjpeg-turbo,
+what torchvision.io.read_image and ToPILImage give DataRetrieval.py:70-96).
+
+Tolerance: JPEG decoders may round the inverse DCT differently; |difference| <= 2 grey levels per pixel and <= 0.25 on
+average is asserted (measured: see the printed line).  Everything AFTER the decode is bit-exact (tests/test_resize_gpu.py).
+"""
+import io
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _radiograph_like(h, w, seed):
+    rng = np.random.default_rng(seed)
+    base = rng.integers(30, 220, size=(h // 16 + 1, w // 16 + 1)).astype(np.float32)
+    img = np.kron(base, np.ones((16, 16), np.float32))[:h, :w]
+    yy, xx = np.mgrid[0:h, 0:w]
+    img = 0.6 * img + 60 * np.sin(yy / 37.0) * np.cos(xx / 23.0) + rng.normal(0, 4, size=(h, w))
+    return np.clip(img, 0, 255).astype(np.uint8)
+
+
+def _jpeg_bytes(arr, quality):
+    from PIL import Image
+    b = io.BytesIO()
+    Image.fromarray(arr, mode="L").save(b, format="JPEG", quality=quality)
+    return b.getvalue()
+
+
+@pytest.mark.parametrize("h,w,quality", [(320, 390, 90), (512, 512, 75), (333, 257, 95), (64, 48, 50)])
+def test_decode_matches_pil_within_idct_rounding(h, w, quality):
+    from PIL import Image
+    from incremental_multimodal_medical_learning_ii_b200.image.data.gpu_decode import GpuJpegDecoder
+    data = _jpeg_bytes(_radiograph_like(h, w, seed=h + w), quality)
+    dec = GpuJpegDecoder(DEV)
+    assert dec.info(data) == (w, h, 1)
+    got = dec.decode(data).cpu().numpy()
+    ref = np.asarray(Image.open(io.BytesIO(data)).convert("L"))
+    assert got.shape == ref.shape == (h, w)
+    diff = np.abs(got.astype(np.int16) - ref.astype(np.int16))
+    print(f"{h}x{w} q{quality}: max |diff| {diff.max()}, mean {diff.mean():.4f}, differing pixels {(diff > 0).mean():.3%}")
+    assert diff.max() <= 2 and diff.mean() <= 0.25
+
+
+def test_decode_rejects_garbage_and_wrong_device():
+    from incremental_multimodal_medical_learning_ii_b200._native import NativeError
+    from incremental_multimodal_medical_learning_ii_b200.image.data.gpu_decode import GpuJpegDecoder
+    with pytest.raises(RuntimeError):
+        GpuJpegDecoder("cpu")
+    with pytest.raises(NativeError):
+        GpuJpegDecoder(DEV).decode(b"definitely not a jpeg stream" * 10)
+
+
+def test_jpeg_to_embedding_pipeline():
+    """JPEG bytes -> nvJPEG -> GPU Resize(128)/CenterCrop(96) -> ImageModel, against PIL decode + PIL resize + the same
+    model: the embedding moves by far less than the north_star bound (cosine >= 0.999) although a few pixels differ by a
+    grey level after the decode."""
+    from PIL import Image
+    import pil_resize_oracle as R
+    from incremental_multimodal_medical_learning_ii_b200 import synthetic_weights as SW
+    from incremental_multimodal_medical_learning_ii_b200.image import get_biovil_resnet
+    from incremental_multimodal_medical_learning_ii_b200.image.data.gpu_decode import GpuJpegPipeline
+    model = get_biovil_resnet(None)
+    model.load_state_dict(SW.make_state_dict(27, randomize_bn=True))
+    model.eval().to(DEV)
+    datas = [_jpeg_bytes(_radiograph_like(200 + 10 * i, 240 - 8 * i, seed=i), 90) for i in range(5)]
+    pipe = GpuJpegPipeline(DEV, resize=128, center_crop_size=96)
+    batch = pipe(datas)
+    assert batch.shape == (5, 1, 96, 96) and batch.dtype == torch.uint8 and batch.is_cuda
+    host = np.stack([R.resize_center_crop(np.asarray(Image.open(io.BytesIO(d)).convert("L")), 128, 96) for d in datas])
+    d = np.abs(batch[:, 0].cpu().numpy().astype(np.int16) - host.astype(np.int16))
+    assert d.max() <= 2
+    a = model(batch).projected_global_embedding
+    b = model(torch.from_numpy(host).unsqueeze(1).to(DEV)).projected_global_embedding
+    cos = F.cosine_similarity(a, b, dim=-1).min().item()
+    print(f"decode-path embedding cosine vs host-decode path: {cos:.6f}")
+    assert cos >= 0.9999

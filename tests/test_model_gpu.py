@@ -234,3 +234,111 @@ def test_batch_invariance_and_ragged_batches(setup):
     a = m.embed_and_score(small)
     b = m.embed_and_score(small[2:5].contiguous())
     assert torch.equal(a["global"][2:5], b["global"])
+
+
+def test_cuda_graph_replay_equals_direct_launches(setup):
+    """Small batches replay the whole forward as ONE CUDA graph launch (bv_forward_graph): same kernels, same buffers,
+    bit-identical results; different frame contents reuse the graph (static input buffer), a new shape records a new one."""
+    from incremental_multimodal_medical_learning_ii_b200 import frames as FR
+    variant, m, sd, golden = setup
+    m.set_prompts(FR.synthetic_prompt_embeddings(14, 1, 128, seed=29), reduce="mean")
+    for (B, S) in ((1, 512), (3, 96), (8, 480)):
+        outs = {}
+        for mode in (False, "auto", True):
+            m.cuda_graphs = mode
+            runs = []
+            for rep in range(3):
+                fr = FR.synthetic_frames_u8(50 + rep, B, S, kind="structured", seed=7).to(DEV)
+                r = m.embed_and_score(fr)
+                runs.append({k: r[k].clone() for k in ("global", "prob", "pred", "sim")})
+            outs[mode] = runs
+        for rep in range(3):
+            for k in ("global", "prob", "pred", "sim"):
+                assert torch.equal(outs[False][rep][k], outs["auto"][rep][k]), (B, S, rep, k)
+                assert torch.equal(outs[False][rep][k], outs[True][rep][k]), (B, S, rep, k)
+        assert not torch.equal(outs["auto"][0]["global"], outs["auto"][1]["global"])      # replays saw the new frames
+    m.cuda_graphs = "auto"
+    # results are copies: a later call must not overwrite an earlier result
+    a = m(FR.synthetic_frames_u8(1, 1, 96, kind="iid", seed=1).to(DEV)).clone()
+    keep = m(FR.synthetic_frames_u8(1, 1, 96, kind="iid", seed=1).to(DEV))
+    m(FR.synthetic_frames_u8(2, 1, 96, kind="iid", seed=1).to(DEV))
+    assert torch.equal(keep, a)
+
+
+def test_float_frames_are_quantised_on_device_only_when_they_are_8bit(setup):
+    """ToTensor + ExpandChannels input (k/255, identical channels) takes the exact 8-bit stem through one conversion kernel;
+    anything else (off-grid values, out-of-range, NaN, differing channels) takes the float stems."""
+    import biovil_oracle as O
+    from incremental_multimodal_medical_learning_ii_b200 import frames as FR
+    variant, m, sd, golden = setup
+    fr = FR.synthetic_frames_u8(3, 2, 96, kind="structured", seed=9)
+    ref = m(fr.to(DEV)).clone()
+    x3 = FR.frames_as_reference_input(fr).to(DEV)
+    assert torch.equal(m(x3), ref)                                      # [B,3,H,W] float k/255
+    assert torch.equal(m(x3[:, :1].contiguous()), ref)                  # [B,1,H,W] float k/255
+    eng = m._get_engine()
+    assert eng.quantize(x3) is not None
+    off = x3.clone(); off[0, :, 5, 7] += 0.3 / 255                      # not 8-bit data any more
+    assert eng.quantize(off) is None
+    ch = x3.clone(); ch[1, 2, 0, 0] = 0.5                               # channels differ
+    assert eng.quantize(ch) is None
+    big = x3.clone(); big[0, :, 1, 1] = 256.0 / 255                     # k = 256 out of range
+    assert eng.quantize(big) is None
+    nan = x3.clone(); nan[0, :, 2, 2] = float("nan")
+    assert eng.quantize(nan) is None
+    out = m(off)                                                        # general float path still within tolerance
+    o = O.image_model_forward(sd, off.cpu())["projected_global_embedding"]
+    assert F.cosine_similarity(out.float().cpu(), o, dim=-1).min().item() >= 0.999
+
+
+def test_output_guards_and_copies(setup):
+    """ImageModelOutput: lazily computed fields refuse to describe a refilled input buffer; eager_outputs computes them in
+    the same pass; deepcopy / torch.save of a model that has run work (the native handle is a derived cache)."""
+    import copy
+    import io
+    from incremental_multimodal_medical_learning_ii_b200 import frames as FR
+    variant, m, sd, golden = setup
+    buf = FR.synthetic_frames_u8(0, 2, 96, kind="iid", seed=3).to(DEV)
+    out = m(buf)
+    buf.copy_(FR.synthetic_frames_u8(9, 2, 96, kind="iid", seed=3).to(DEV))     # staging buffer refilled
+    with pytest.raises(RuntimeError):
+        out.img_embedding
+    m.eager_outputs = True
+    out = m(buf)
+    pooled = out.img_embedding.clone()
+    buf.zero_()
+    assert torch.equal(out.img_embedding, pooled) and out._frames is None
+    m.eager_outputs = False
+    m2 = copy.deepcopy(m)
+    b = io.BytesIO()
+    torch.save(m, b)
+    b.seek(0)
+    m3 = torch.load(b, weights_only=False)
+    x = FR.synthetic_frames_u8(4, 2, 96, kind="structured", seed=3).to(DEV)
+    assert torch.equal(m2(x), m(x)) and torch.equal(m3.eval()(x), m(x))
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs in one process")
+def test_two_devices_in_one_process():
+    """kernel attributes / SM count / cluster capability are per-device state - an ImageModel on cuda:1 and a
+    scorer on cuda:0 in the same process must both launch (dynamic shared memory opt-in applies per device)."""
+    from incremental_multimodal_medical_learning_ii_b200 import frames as FR
+    from incremental_multimodal_medical_learning_ii_b200.scorer import ZeroShotScorer
+    m0, sd = _model(True)
+    fr = FR.synthetic_frames_u8(0, 4, 480, kind="structured", seed=0)
+    a = m0(fr.to("cuda:0")).cpu()
+    m1 = get_model_on("cuda:1", sd)
+    b = m1(fr.to("cuda:1")).cpu()
+    assert torch.equal(a, b)
+    prompts = FR.synthetic_prompt_embeddings(14, 1, 128, seed=29)
+    s0, s1 = ZeroShotScorer("cuda:0"), ZeroShotScorer("cuda:1")
+    s0.set_prompts(prompts); s1.set_prompts(prompts)
+    assert torch.equal(s0.score(a)["prob"].cpu(), s1.score(a)["prob"].cpu())
+
+
+def get_model_on(device, sd):
+    from incremental_multimodal_medical_learning_ii_b200.image import get_biovil_resnet
+    m = get_biovil_resnet(None)
+    m.load_state_dict(sd)
+    m.eval().to(device)
+    return m
