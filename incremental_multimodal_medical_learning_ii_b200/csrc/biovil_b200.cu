@@ -181,16 +181,21 @@ struct ConvOperand {
 };
 
 // Kernel configurations <BN, STAGES, NBUF> (see ConvGemmCfg): picked per layer by arithmetic intensity.
-enum ConvCfg { kCfg256Deep = 0, kCfg256Res, kCfg128Res, kCfg128Deep, kCfg64, kCfg64BRes, kCfg64Wide, kCfg64Tap3, kCfg128M2, kCfg128TR, kNumCfg };
+enum ConvCfg { kCfg256Deep = 0, kCfg256Res, kCfg128Res, kCfg128Deep, kCfg64, kCfg64BRes, kCfg64Wide, kCfg64Tap3, kCfg128M2, kCfg128TR,
+               kCfg256PairDeep, kCfg256PairRes, kNumCfg };
 // kCfg64Tap3 is a different kernel (conv3x3_tap3.cuh): the three horizontal taps of a filter row in one N = 192 MMA
+// kCfg256Pair*: the 256-wide tile on CTA PAIRS (cta_group::2, M = 256 over two SMs, half of every weight stage per CTA):
+// 32 KB instead of 48 KB per ring stage -> 6 stages (long K) or 4 stages + 6 staging tiles (residual stream)
 #define BV_FOR_EACH_CFG(X)                                                                                        \
-    X(kCfg256Deep, 256, 4, 2, false, false, 1, 8, false) X(kCfg256Res, 256, 3, 5, false, false, 1, 16, false)                 \
-    X(kCfg128Res, 128, 3, 7, false, false, 1, 16, false) X(kCfg128Deep, 128, 6, 2, false, false, 1, 16, false)                \
-    X(kCfg64, 64, 8, 2, false, false, 1, 16, false) X(kCfg64BRes, 64, 6, 2, true, false, 1, 16, false)                        \
-    X(kCfg64Wide, 64, 6, 2, true, true, 1, 16, false) X(kCfg128M2, 128, 4, 2, false, false, 2, 16, false)                     \
-    X(kCfg128TR, 128, 4, 2, false, false, 2, 16, true)
-const int kCfgBN[kNumCfg] = {256, 256, 128, 128, 64, 64, 64, 64, 128, 128};
-const int kCfgMT[kNumCfg] = {1, 1, 1, 1, 1, 1, 1, 1, 2, 2};
+    X(kCfg256Deep, 256, 4, 2, false, false, 1, 8, false, false) X(kCfg256Res, 256, 3, 5, false, false, 1, 16, false, false)   \
+    X(kCfg128Res, 128, 3, 7, false, false, 1, 16, false, false) X(kCfg128Deep, 128, 6, 2, false, false, 1, 16, false, false)  \
+    X(kCfg64, 64, 8, 2, false, false, 1, 16, false, false) X(kCfg64BRes, 64, 6, 2, true, false, 1, 16, false, false)          \
+    X(kCfg64Wide, 64, 6, 2, true, true, 1, 16, false, false) X(kCfg128M2, 128, 4, 2, false, false, 2, 16, false, false)       \
+    X(kCfg128TR, 128, 4, 2, false, false, 2, 16, true, false)                                                                \
+    X(kCfg256PairDeep, 256, 6, 2, false, false, 1, 8, false, true) X(kCfg256PairRes, 256, 4, 6, false, false, 1, 16, false, true)
+const int kCfgBN[kNumCfg] = {256, 256, 128, 128, 64, 64, 64, 64, 128, 128, 256, 256};
+const int kCfgMT[kNumCfg] = {1, 1, 1, 1, 1, 1, 1, 1, 2, 2, 1, 1};
+const bool kCfgPair[kNumCfg] = {false, false, false, false, false, false, false, false, false, false, true, true};
 
 struct ConvLaunch {
     bv::ConvGemmParams p;
@@ -236,6 +241,7 @@ struct DeviceState {
     bool ready = false;
     int num_sms = 0;
     int l1_launchable = -1;        // -1 = not probed yet
+    int pair_launchable = -1;
     long long* dbg = nullptr;      // BV_TIMING builds: per-CTA wait-cycle counters of the most recent launch
 };
 DeviceState g_dev[kMaxDevices];
@@ -244,10 +250,10 @@ thread_local DeviceState* t_dev = nullptr;   // state of the calling thread's cu
 thread_local int g_num_sms = 0;              // == t_dev->num_sms
 
 int set_kernel_attributes() {
-#define BV_SET_ATTR(id, BN, ST, NB, BR, WD, MT, EP, TR)                                             \
-    BV_CUDA(cudaFuncSetAttribute(bv::conv_gemm_kernel<BN, ST, NB, BR, WD, MT, EP, TR>,              \
+#define BV_SET_ATTR(id, BN, ST, NB, BR, WD, MT, EP, TR, PR)                                         \
+    BV_CUDA(cudaFuncSetAttribute(bv::conv_gemm_kernel<BN, ST, NB, BR, WD, MT, EP, TR, PR>,          \
                                  cudaFuncAttributeMaxDynamicSharedMemorySize,                       \
-                                 bv::ConvGemmCfg<BN, ST, NB, BR, WD, MT, EP, TR>::kSmemBytes));
+                                 bv::ConvGemmCfg<BN, ST, NB, BR, WD, MT, EP, TR, PR>::kSmemBytes));
     BV_FOR_EACH_CFG(BV_SET_ATTR)
 #undef BV_SET_ATTR
 #define BV_SET_CHAIN_ATTR(id, N2, ST, NB)                                                           \
@@ -305,6 +311,32 @@ int device_setup() {
 
 int conv_out_dim(int in, int k, int stride, int pad) { return (in + 2 * pad - k) / stride + 1; }
 
+// Can this device co-schedule CTA pairs of the 256-wide convolution kernel (cluster launch with ~225 KB of shared memory
+// per CTA)?  Queried once per device; when it cannot (MIG slice, odd SM count per TPC) the single-CTA form is used.
+bool pair_launchable() {
+    if (!t_dev) return false;
+    int& cached = t_dev->pair_launchable;
+    if (cached >= 0) return cached == 1;
+    auto kernel = bv::conv_gemm_kernel<256, 6, 2, false, false, 1, 8, false, true>;
+    using Cfg = bv::ConvGemmCfg<256, 6, 2, false, false, 1, 8, false, true>;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(2, 1, 1);
+    cfg.blockDim = dim3(Cfg::kThreads, 1, 1);
+    cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    int clusters = 0;
+    const cudaError_t e = cudaOccupancyMaxActiveClusters(&clusters, kernel, &cfg);
+    if (e != cudaSuccess) cudaGetLastError();
+    cached = (e == cudaSuccess && clusters >= 1) ? 1 : 0;
+    return cached == 1;
+}
+
 // Build the kernel parameters (tensor maps included) for one fused convolution.
 int build_conv(ConvLaunch* L, int B, const ConvOperand* ops, int nops, const void* residual, int relu, void* out,
                int out_fp32) {
@@ -339,9 +371,20 @@ int build_conv(ConvLaunch* L, int B, const ConvOperand* ops, int nops, const voi
     if (cfg == kCfg128M2 && tr_ok && !env_flag("BV_NO_TR")) cfg = kCfg128TR;
     const bool tap3_ok = wide_ok && c0.cin == 64;
     if (cfg == kCfg64Wide && tap3_ok && !env_flag("BV_NO_TAP3")) cfg = kCfg64Tap3;
+    // 256-wide tiles on CTA pairs where the device can co-schedule them.  BV_PAIR (bit 0: long-K / no residual stream,
+    // bit 1: residual stream; default 3) and BV_PAIR_MINKB (smallest K, in 64-wide blocks, that takes the pair form)
+    // are the A/B switches.
+    {
+        static const int pair_mask = getenv("BV_PAIR") ? atoi(getenv("BV_PAIR")) : 3;
+        static const int pair_minkb = getenv("BV_PAIR_MINKB") ? atoi(getenv("BV_PAIR_MINKB")) : 0;
+        if (!out_fp32 && total_kblocks >= pair_minkb && pair_launchable()) {
+            if (cfg == kCfg256Deep && (pair_mask & 1)) cfg = kCfg256PairDeep;
+            else if (cfg == kCfg256Res && (pair_mask & 2)) cfg = kCfg256PairRes;
+        }
+    }
     if (const char* force = getenv("BV_FORCE_CFG")) {
         const int f = atoi(force);
-        if (f >= 0 && f < kNumCfg && N % kCfgBN[f] == 0 &&
+        if (f >= 0 && f < kNumCfg && N % kCfgBN[f] == 0 && (!kCfgPair[f] || (!out_fp32 && pair_launchable())) &&
             (f != kCfg64BRes || (N == 64 && total_kblocks <= bv::kMaxResidentKB)) && (f != kCfg128M2 || (!residual && !out_fp32)) && (f != kCfg128TR || tr_ok))
             cfg = f;
     }
@@ -375,7 +418,9 @@ int build_conv(ConvLaunch* L, int B, const ConvOperand* ops, int nops, const voi
                                   tap3 ? 32 : 0);
         }
         if (rc) return rc;
-        rc = make_tmap_2d(&p.tmB[i], c.w, (uint64_t)c.r * c.s * c.cin, (uint64_t)N, bv::kBlockK, (uint32_t)bn);
+        // (CTA pairs: each CTA loads half of the n-block's weight rows per stage)
+        rc = make_tmap_2d(&p.tmB[i], c.w, (uint64_t)c.r * c.s * c.cin, (uint64_t)N, bv::kBlockK,
+                          (uint32_t)(kCfgPair[cfg] ? bn / 2 : bn));
         if (rc) return rc;
         p.bias[i] = c.bias;
     }
@@ -407,11 +452,11 @@ int build_conv(ConvLaunch* L, int B, const ConvOperand* ops, int nops, const voi
     int nacc = 1;
     if (const char* f = getenv("BV_FORCE_NACC")) nacc = std::max(1, std::min(256 / bn, atoi(f)));
     p.nacc = nacc;
-    const int mt = kCfgMT[cfg];
+    const int mt = kCfgPair[cfg] ? 2 : kCfgMT[cfg];
     const long long tiles = (long long)((p.num_m_blocks + mt - 1) / mt) * p.num_n_blocks;
     if (mt > 1) nacc = 1;
     p.nacc = nacc;
-    L->grid = (int)std::min<long long>(tiles, g_num_sms);
+    L->grid = kCfgPair[cfg] ? 2 * (int)std::min<long long>(tiles, g_num_sms / 2) : (int)std::min<long long>(tiles, g_num_sms);
     return BV_OK;
 }
 
@@ -425,11 +470,11 @@ int launch_conv(const ConvLaunch& L0, cudaStream_t st) {
         L.p.dbg = g_dbg;
     }
     switch (L.cfg) {
-#define BV_LAUNCH(id, BN, ST, NB, BR, WD, MT, EP, TR)                                                     \
+#define BV_LAUNCH(id, BN, ST, NB, BR, WD, MT, EP, TR, PR)                                                 \
     case id:                                                                                              \
-        launch_ex(bv::conv_gemm_kernel<BN, ST, NB, BR, WD, MT, EP, TR>, L.grid,                           \
-                  bv::ConvGemmCfg<BN, ST, NB, BR, WD, MT, EP, TR>::kThreads,                              \
-                  bv::ConvGemmCfg<BN, ST, NB, BR, WD, MT, EP, TR>::kSmemBytes, st, 1, L.p);               \
+        launch_ex(bv::conv_gemm_kernel<BN, ST, NB, BR, WD, MT, EP, TR, PR>, L.grid,                       \
+                  bv::ConvGemmCfg<BN, ST, NB, BR, WD, MT, EP, TR, PR>::kThreads,                          \
+                  bv::ConvGemmCfg<BN, ST, NB, BR, WD, MT, EP, TR, PR>::kSmemBytes, st, PR ? 2 : 1, L.p);  \
         break;
         BV_FOR_EACH_CFG(BV_LAUNCH)
 #undef BV_LAUNCH
@@ -729,6 +774,7 @@ struct bv_handle {
         int launches;
     };
     std::vector<GraphEntry> graphs;
+    cudaStream_t capture_stream = nullptr;
 };
 
 namespace {
@@ -830,6 +876,7 @@ void bv_destroy(bv_handle* h) {
     if (h->heat_t) cudaFree(h->heat_t);
     for (cudaEvent_t e : h->events) cudaEventDestroy(e);
     for (auto& g : h->graphs) cudaGraphExecDestroy(g.exec);
+    if (h->capture_stream) cudaStreamDestroy(h->capture_stream);
     delete h;
 }
 
@@ -1252,10 +1299,13 @@ int32_t bv_forward_graph(bv_handle* h, const void* frames, int32_t dtype, int32_
     BV_CUDA(cudaStreamIsCapturing(st, &cs));
     if (cs != cudaStreamCaptureStatusNone)   // the caller is capturing already: just add our nodes to its graph
         return forward_impl(h, frames, dtype, B, C, H, W, workspace, workspace_bytes, out, stream);
-    BV_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-    const int rc = forward_impl(h, frames, dtype, B, C, H, W, workspace, workspace_bytes, out, stream);
+    // The capture runs on a private stream: the caller's stream may be the legacy default stream (torch's default),
+    // which cannot be captured.  Nothing executes during capture; the instantiated graph is launched on the caller's stream.
+    if (!h->capture_stream) BV_CUDA(cudaStreamCreateWithFlags(&h->capture_stream, cudaStreamNonBlocking));
+    BV_CUDA(cudaStreamBeginCapture(h->capture_stream, cudaStreamCaptureModeThreadLocal));
+    const int rc = forward_impl(h, frames, dtype, B, C, H, W, workspace, workspace_bytes, out, h->capture_stream);
     cudaGraph_t graph = nullptr;
-    const cudaError_t ce = cudaStreamEndCapture(st, &graph);
+    const cudaError_t ce = cudaStreamEndCapture(h->capture_stream, &graph);
     if (rc != BV_OK) {
         if (graph) cudaGraphDestroy(graph);
         cudaGetLastError();

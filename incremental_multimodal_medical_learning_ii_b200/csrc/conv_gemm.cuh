@@ -34,6 +34,7 @@
 // (fp32 output, used only by the tiny projector conv, keeps a direct per-thread store path.)
 #pragma once
 #include "ptx.cuh"
+#include "pair_gemm.cuh"
 
 namespace bv {
 
@@ -99,7 +100,14 @@ constexpr int kMaxResidentKB = 9;
 // accumulator is then channel-major (TMEM lane = channel, column = pixel); the epilogue transposes it on the way into
 // the swizzled staging tiles with 2-byte stores (32 per thread and sub-tile: the 32 lanes of a store cover 64 contiguous
 // bytes of one pixel row; two lanes share each bank word = one extra wavefront, far off the critical path).
-template <int BN, int STAGES, int NBUF, bool BRES = false, bool WIDE = false, int MT = 1, int EPI = 16, bool TR = false>
+// PAIR = the tile is computed by a CTA PAIR (cluster of 2, tcgen05 cta_group::2): one MMA of M = 256 spans the two SMs, each
+// CTA owns its own 128-pixel m-tile (A loads, TMEM lanes, epilogue, stores are CTA-local) and holds only HALF of every
+// weight stage (BN/2 rows).  Per SM the weight stream from L2 halves and a ring stage shrinks from 48 to 32 KB; the
+// layer3/layer4 convolutions, whose tiles are bound by the L2 -> SM operand stream, are the target.  Protocol as in
+// pair_gemm.cuh / l1_block.cuh: both producers credit the LEADER's full barrier, only the leader issues MMAs, commits are
+// multicast to both CTAs, "accumulator drained" arrives on the leader's barrier from the epilogue warps of both.
+template <int BN, int STAGES, int NBUF, bool BRES = false, bool WIDE = false, int MT = 1, int EPI = 16, bool TR = false,
+          bool PAIR = false>
 struct ConvGemmCfg {
     static_assert(EPI == 8 || EPI == 16, "epilogue warps");
     static_assert(!TR || (MT == 2 && BN == 128 && EPI == 16 && NBUF == 2), "transposed tiles: 128 channels x 2 m-tiles");
@@ -107,7 +115,8 @@ struct ConvGemmCfg {
     static constexpr int kThreads = gemm_threads(EPI);
     static_assert(!WIDE || BRES, "the wide 3x3 mode keeps the weights resident");
     static_assert(MT == 1 || (MT == 2 && BN == 128 && !BRES && !WIDE), "two m-tiles per stage: BN = 128, streamed weights only");
-    static constexpr int kBBytes = BN * kBlockK * 2;
+    static_assert(!PAIR || (BN == 256 && MT == 1 && !BRES && !WIDE && !TR), "CTA pairs: 256-wide tiles, streamed weights");
+    static constexpr int kBBytes = (PAIR ? BN / 2 : BN) * kBlockK * 2;
     static constexpr int kAStage = WIDE ? kWideABytes : MT * kABytes;
     static constexpr int kStageBytes = kAStage + (BRES ? 0 : kBBytes);
     static constexpr int kResidentBytes = BRES ? kMaxResidentKB * kBBytes : 0;
@@ -135,9 +144,10 @@ __device__ __forceinline__ void tmem_ld_32x16b(uint32_t taddr, uint32_t (&r)[16]
         : "memory");
 }
 
-template <int BN, int STAGES, int NBUF, bool BRES = false, bool WIDE = false, int MT = 1, int EPI = 16, bool TR = false>
+template <int BN, int STAGES, int NBUF, bool BRES = false, bool WIDE = false, int MT = 1, int EPI = 16, bool TR = false,
+          bool PAIR = false>
 __global__ void __launch_bounds__(gemm_threads(EPI), 1) conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
-    using Cfg = ConvGemmCfg<BN, STAGES, NBUF, BRES, WIDE, MT, EPI, TR>;
+    using Cfg = ConvGemmCfg<BN, STAGES, NBUF, BRES, WIDE, MT, EPI, TR, PAIR>;
     constexpr int kEpiWarps = EPI;
     constexpr int kDmaWarp = 2 + EPI;
     constexpr int kWarpCols = kChunkCols / (EPI / 4);   // columns of a 64-column sub-tile per epilogue warp
@@ -166,8 +176,17 @@ __global__ void __launch_bounds__(gemm_threads(EPI), 1) conv_gemm_kernel(const _
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    // a "tile" below is MT consecutive m-blocks x one n-block
-    const int num_tiles = ((p.num_m_blocks + MT - 1) / MT) * p.num_n_blocks;
+    // a "tile" below is MT consecutive m-blocks x one n-block; with PAIR it is the pair's two m-blocks (this CTA computes
+    // m-block 2q + rank) x one n-block, and tiles are dealt to CTA pairs instead of CTAs
+    const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+    const int tile0 = PAIR ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+    const int tile_stride = PAIR ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
+    const int num_tiles = ((p.num_m_blocks + (PAIR ? 2 : MT) - 1) / (PAIR ? 2 : MT)) * p.num_n_blocks;
+    auto tile_mn = [&](int tile, int& m_blk, int& n_blk) {
+        const int mq = tile / p.num_n_blocks;
+        n_blk = tile - mq * p.num_n_blocks;
+        m_blk = PAIR ? 2 * mq + static_cast<int>(rank) : mq;
+    };
     // ring stages consumed per tile (kSegWide: one per filter row and channel block) / resident weight k-blocks
     const int total_kb = WIDE ? 3 * p.seg[0].cblocks : p.seg[0].kblocks + (p.nseg > 1 ? p.seg[1].kblocks : 0);
     const int total_wkb = p.seg[0].kblocks + (p.nseg > 1 ? p.seg[1].kblocks : 0);
@@ -183,7 +202,7 @@ __global__ void __launch_bounds__(gemm_threads(EPI), 1) conv_gemm_kernel(const _
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tmem_full[i], 1);
-            mbar_init(&tmem_empty[i], kEpiWarps);  // one arrival per epilogue warp
+            mbar_init(&tmem_empty[i], (PAIR ? 2 : 1) * kEpiWarps);  // one arrival per epilogue warp (of both CTAs of a pair)
         }
         for (int i = 0; i < kBufs; ++i) {
             mbar_init(&buf_ready[i], 1);
@@ -193,11 +212,17 @@ __global__ void __launch_bounds__(gemm_threads(EPI), 1) conv_gemm_kernel(const _
         fence_barrier_init();
     }
     if (warp == 1) {
-        tmem_alloc(tmem_ptr, Cfg::kTmemCols);
-        tmem_relinquish();
+        if constexpr (PAIR) {
+            tmem_alloc_pair(tmem_ptr, Cfg::kTmemCols);
+            tmem_relinquish_pair();
+        } else {
+            tmem_alloc(tmem_ptr, Cfg::kTmemCols);
+            tmem_relinquish();
+        }
     }
     tc_fence_before();
-    __syncthreads();
+    if constexpr (PAIR) cluster_sync_all();   // the peer's barriers must be initialised before any remote arrival
+    else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
     pdl_launch_dependents();   // the next kernel's prologue may overlap this kernel's tail ...
@@ -223,9 +248,9 @@ __global__ void __launch_bounds__(gemm_threads(EPI), 1) conv_gemm_kernel(const _
             }
             __syncwarp();
         }
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-            const int m_blk = tile / p.num_n_blocks;
-            const int n_blk = tile - m_blk * p.num_n_blocks;
+        for (int tile = tile0; tile < num_tiles; tile += tile_stride) {
+            int m_blk, n_blk;
+            tile_mn(tile, m_blk, n_blk);
             const int m0 = m_blk * kBlockM;
             if constexpr (WIDE) {
                 // rows enumerate (image, p, q') with q' = -1 .. Wo: window origin of row m0 is (q' - 1, p - 1)
@@ -271,6 +296,20 @@ __global__ void __launch_bounds__(gemm_threads(EPI), 1) conv_gemm_kernel(const _
                     mbar_wait(&empty_bar[stage], phase ^ 1u);
                     t_empty += tclock() - tw;
                     if (elect_one()) {
+                        if constexpr (PAIR) {
+                            // the leader's barrier collects the bytes of both CTAs' loads of this stage
+                            void* dst_a = smem_a + stage * kAStage;
+                            if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2u * Cfg::kStageBytes);
+                            if (sg.mode == kSegTiled)
+                                tma_load_2d_pair(&p.tmA[s], &full_bar[stage], dst_a, cb * kBlockK, m_blk * kBlockM, kEvictNormal);
+                            else
+                                tma_load_im2col_4d_pair(&p.tmA[s], &full_bar[stage], dst_a, cb * kBlockK,
+                                                        sg.lower + oq[0] * sg.stride, sg.lower + op[0] * sg.stride, img[0],
+                                                        static_cast<uint16_t>(ts), static_cast<uint16_t>(tr), kEvictNormal);
+                            // this CTA's half of the weight stage: rows [rank * BN/2, (rank + 1) * BN/2) of the n-block
+                            tma_load_2d_pair(&p.tmB[s], &full_bar[stage], smem_b + stage * Cfg::kBBytes, kofs,
+                                             n_blk * BN + static_cast<int>(rank) * (BN / 2), kEvictLast);
+                        } else {
                         mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
 #pragma unroll
                         for (int u = 0; u < MT; ++u) {
@@ -287,6 +326,7 @@ __global__ void __launch_bounds__(gemm_threads(EPI), 1) conv_gemm_kernel(const _
                         if constexpr (!BRES)
                             tma_load_2d(&p.tmB[s], &full_bar[stage], smem_b + stage * Cfg::kBBytes, kofs, n_blk * BN,
                                         kEvictLast);
+                        }
                     }
                     __syncwarp();
                     kofs += kBlockK;
@@ -319,17 +359,20 @@ __global__ void __launch_bounds__(gemm_threads(EPI), 1) conv_gemm_kernel(const _
         uint32_t phase = 0;
         int it = 0;
         if constexpr (BRES) mbar_wait(bres_bar, 0);
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        // (CTA pairs: only the leader issues; cluster-scope acquires because the barriers collect remote arrivals)
+        for (int tile = tile0; tile < num_tiles && (!PAIR || rank == 0); tile += tile_stride, ++it) {
             const int acc = it & 1;
             const uint32_t acc_phase = (it >> 1) & 1u;
             long long tw = tclock();
-            mbar_wait(&tmem_empty[acc], acc_phase ^ 1u);
+            if constexpr (PAIR) mbar_wait_cluster(&tmem_empty[acc], acc_phase ^ 1u);
+            else mbar_wait(&tmem_empty[acc], acc_phase ^ 1u);
             t_acc += tclock() - tw;
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * Cfg::kAccStageCols);
             for (int kb = 0; kb < total_kb; ++kb) {
                 tw = tclock();
-                mbar_wait(&full_bar[stage], phase);
+                if constexpr (PAIR) mbar_wait_cluster(&full_bar[stage], phase);
+                else mbar_wait(&full_bar[stage], phase);
                 t_full += tclock() - tw;
                 tc_fence_after();
                 if constexpr (WIDE) {
@@ -367,6 +410,18 @@ __global__ void __launch_bounds__(gemm_threads(EPI), 1) conv_gemm_kernel(const _
                         umma_commit(&empty_bar[stage]);
                         if (kb == total_kb - 1) umma_commit(&tmem_full[acc]);
                     }
+                } else if constexpr (PAIR) {
+                    if (elect_one()) {
+                        // D[256 x BN] over the two SMs: own A tile x (own half | peer half) of the weight stage
+                        const uint64_t adesc = umma_desc_k_sw128(a_base + static_cast<uint32_t>(stage * kAStage));
+                        const uint64_t bdesc = umma_desc_k_sw128(b_base + static_cast<uint32_t>(stage * Cfg::kBBytes));
+#pragma unroll
+                        for (int k = 0; k < kBlockK / 16; ++k)
+                            umma_bf16_ss_pair(d_tmem, adesc + static_cast<uint64_t>(2 * k), bdesc + static_cast<uint64_t>(2 * k),
+                                              umma_idesc_bf16_f32(2 * kBlockM, BN), (kb != 0 || k != 0) ? 1u : 0u);
+                        umma_commit_pair(&empty_bar[stage]);                          // frees the stage in BOTH CTAs
+                        if (kb == total_kb - 1) umma_commit_pair(&tmem_full[acc]);    // both epilogues may start
+                    }
                 } else if (elect_one()) {
                     const uint64_t bdesc =
                         umma_desc_k_sw128(b_base + static_cast<uint32_t>((BRES ? kb : stage) * Cfg::kBBytes));
@@ -402,13 +457,12 @@ __global__ void __launch_bounds__(gemm_threads(EPI), 1) conv_gemm_kernel(const _
         // ===================== epilogue DMA (residual prefetch + output stores) =====================
         if (!p.out_fp32 && !WIDE) {
             const bool has_res = p.residual != nullptr;
-            const int my_tiles = (num_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) /
-                                 static_cast<int>(gridDim.x);
+            const int my_tiles = (num_tiles - tile0 + tile_stride - 1) / tile_stride;
             const int total = my_tiles * MT * kChunks;  // sub-tiles this CTA produces
             auto coords = [&](int g, int& row0, int& col0) {
-                const int tile = static_cast<int>(blockIdx.x) + (g / (MT * kChunks)) * static_cast<int>(gridDim.x);
-                const int m_blk = tile / p.num_n_blocks;
-                const int n_blk = tile - m_blk * p.num_n_blocks;
+                const int tile = tile0 + (g / (MT * kChunks)) * tile_stride;
+                int m_blk, n_blk;
+                tile_mn(tile, m_blk, n_blk);
                 row0 = (m_blk * MT + (g / kChunks) % MT) * kBlockM;
                 col0 = n_blk * BN + (g % kChunks) * kChunkCols;
             };
@@ -452,9 +506,10 @@ __global__ void __launch_bounds__(gemm_threads(EPI), 1) conv_gemm_kernel(const _
         const bool has_res = p.residual != nullptr;
         int it = 0;
         int g = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-            const int m_blk = tile / p.num_n_blocks;
-            const int n_blk = tile - m_blk * p.num_n_blocks;
+        for (int tile = tile0; tile < num_tiles; tile += tile_stride, ++it) {
+            int m_blk, n_blk;
+            tile_mn(tile, m_blk, n_blk);
+            (void)m_blk;
             const int acc = it & 1;
             const uint32_t acc_phase = (it >> 1) & 1u;
             mbar_wait(&tmem_full[acc], acc_phase);
@@ -565,15 +620,18 @@ __global__ void __launch_bounds__(gemm_threads(EPI), 1) conv_gemm_kernel(const _
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+            if (lane == 0) {
+                if constexpr (PAIR) mbar_arrive_leader(&tmem_empty[acc]);   // the leader's MMA thread reuses the accumulator
+                else mbar_arrive(&tmem_empty[acc]);
+            }
         }
     } else {
         // ===================== epilogue, direct fp32 stores: the warps of a lane quarter split the BN/32 column chunks =====
         const int quarter = warp & 3;  // TMEM lane quarter this warp may access
         int it = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-            const int m_blk = tile / p.num_n_blocks;
-            const int n_blk = tile - m_blk * p.num_n_blocks;
+        for (int tile = tile0; tile < num_tiles; tile += tile_stride, ++it) {
+            int m_blk, n_blk;
+            tile_mn(tile, m_blk, n_blk);
             const int acc = it & 1;
             const uint32_t acc_phase = (it >> 1) & 1u;
             mbar_wait(&tmem_full[acc], acc_phase);
@@ -668,15 +726,20 @@ __global__ void __launch_bounds__(gemm_threads(EPI), 1) conv_gemm_kernel(const _
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+            if (lane == 0) {
+                if constexpr (PAIR) mbar_arrive_leader(&tmem_empty[acc]);
+                else mbar_arrive(&tmem_empty[acc]);
+            }
         }
     }
 
     tc_fence_before();
-    __syncthreads();
+    if constexpr (PAIR) cluster_sync_all();   // neither CTA may exit (or free TMEM) while the pair's last MMAs / arrivals are in flight
+    else __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, Cfg::kTmemCols);
+        if constexpr (PAIR) tmem_dealloc_pair(tmem_base, Cfg::kTmemCols);
+        else tmem_dealloc(tmem_base, Cfg::kTmemCols);
     }
 }
 

@@ -85,6 +85,42 @@ __device__ __forceinline__ void tma_load_2d_pair(const CUtensorMap* m, uint64_t*
         : "memory");
 }
 
+__device__ __forceinline__ void mbar_arrive_leader_release(uint64_t* bar) {
+    const uint32_t a = cluster_addr_of(bar, 0);
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];\n" ::"r"(a) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+    if (mbar_try_wait_cluster(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait_cluster(bar, parity)) {
+        if (clock64() - t0 > 4000000000LL) __trap();
+    }
+}
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;\n" ::: "memory"); }
+
+// im2col-mode load whose completion bytes are credited to the LEADER's barrier (pair MMAs consume it)
+__device__ __forceinline__ void tma_load_im2col_4d_pair(const CUtensorMap* m, uint64_t* bar, void* dst, int c, int w,
+                                                        int h, int n, uint16_t off_w, uint16_t off_h, uint64_t policy) {
+    const uint32_t bar_addr = smem_u32(bar) & kPeerBitMask;
+    asm volatile(
+        "cp.async.bulk.tensor.4d.im2col.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+        " [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8}, %9;\n" ::"r"(smem_u32(dst)),
+        "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_addr), "r"(c), "r"(w), "r"(h), "r"(n), "h"(off_w), "h"(off_h),
+        "l"(policy)
+        : "memory");
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // Minimal pair GEMM: out[M, N] (fp32) = A[M, K] * W[N, K]^T, bf16 operands.  M is tiled in 256-row pair tiles
 // (128 rows per CTA), the whole N (<= 256, multiple of 32) is one tile, K in 64-wide blocks.  Validation vehicle.
