@@ -182,7 +182,7 @@ struct ConvOperand {
 
 // Kernel configurations <BN, STAGES, NBUF> (see ConvGemmCfg): picked per layer by arithmetic intensity.
 enum ConvCfg { kCfg256Deep = 0, kCfg256Res, kCfg128Res, kCfg128Deep, kCfg64, kCfg64BRes, kCfg64Wide, kCfg64Tap3, kCfg128M2, kCfg128TR,
-               kCfg256PairDeep, kCfg256PairRes, kNumCfg };
+               kCfg256PairDeep, kCfg256PairRes, kCfg256PairDeepE16, kCfg256PairRes37, kNumCfg };
 // kCfg64Tap3 is a different kernel (conv3x3_tap3.cuh): the three horizontal taps of a filter row in one N = 192 MMA
 // kCfg256Pair*: the 256-wide tile on CTA PAIRS (cta_group::2, M = 256 over two SMs, half of every weight stage per CTA):
 // 32 KB instead of 48 KB per ring stage -> 6 stages (long K) or 4 stages + 6 staging tiles (residual stream)
@@ -192,10 +192,11 @@ enum ConvCfg { kCfg256Deep = 0, kCfg256Res, kCfg128Res, kCfg128Deep, kCfg64, kCf
     X(kCfg64, 64, 8, 2, false, false, 1, 16, false, false) X(kCfg64BRes, 64, 6, 2, true, false, 1, 16, false, false)          \
     X(kCfg64Wide, 64, 6, 2, true, true, 1, 16, false, false) X(kCfg128M2, 128, 4, 2, false, false, 2, 16, false, false)       \
     X(kCfg128TR, 128, 4, 2, false, false, 2, 16, true, false)                                                                \
-    X(kCfg256PairDeep, 256, 6, 2, false, false, 1, 8, false, true) X(kCfg256PairRes, 256, 4, 6, false, false, 1, 16, false, true)
-const int kCfgBN[kNumCfg] = {256, 256, 128, 128, 64, 64, 64, 64, 128, 128, 256, 256};
-const int kCfgMT[kNumCfg] = {1, 1, 1, 1, 1, 1, 1, 1, 2, 2, 1, 1};
-const bool kCfgPair[kNumCfg] = {false, false, false, false, false, false, false, false, false, false, true, true};
+    X(kCfg256PairDeep, 256, 6, 2, false, false, 1, 8, false, true) X(kCfg256PairRes, 256, 4, 6, false, false, 1, 16, false, true)   \
+    X(kCfg256PairDeepE16, 256, 6, 2, false, false, 1, 16, false, true) X(kCfg256PairRes37, 256, 3, 7, false, false, 1, 16, false, true)
+const int kCfgBN[kNumCfg] = {256, 256, 128, 128, 64, 64, 64, 64, 128, 128, 256, 256, 256, 256};
+const int kCfgMT[kNumCfg] = {1, 1, 1, 1, 1, 1, 1, 1, 2, 2, 1, 1, 1, 1};
+const bool kCfgPair[kNumCfg] = {false, false, false, false, false, false, false, false, false, false, true, true, true, true};
 
 struct ConvLaunch {
     bv::ConvGemmParams p;
@@ -371,15 +372,19 @@ int build_conv(ConvLaunch* L, int B, const ConvOperand* ops, int nops, const voi
     if (cfg == kCfg128M2 && tr_ok && !env_flag("BV_NO_TR")) cfg = kCfg128TR;
     const bool tap3_ok = wide_ok && c0.cin == 64;
     if (cfg == kCfg64Wide && tap3_ok && !env_flag("BV_NO_TAP3")) cfg = kCfg64Tap3;
-    // 256-wide tiles on CTA pairs where the device can co-schedule them.  BV_PAIR (bit 0: long-K / no residual stream,
-    // bit 1: residual stream; default 3) and BV_PAIR_MINKB (smallest K, in 64-wide blocks, that takes the pair form)
-    // are the A/B switches.
+    // 256-wide tiles on CTA pairs where the device can co-schedule them.  Same-box A/B (profiles/r2b_*): every long-K
+    // tile gains 6-14 % (layer3/4 3x3 and 1x1: the per-SM weight stream halves), residual-stream tiles 7-11 % from six
+    // k-blocks on (layer4 conv3 + identity, layer2.0 conv3 + downsample) and 0-2 % below (layer3 conv3 + identity, K = 256:
+    // HBM-bound on the identity rows either way).  End to end +3.9 % (long-K only) / +5.5 % (everything) on one box.
+    // BV_PAIR (bit 0: long-K, bit 1: residual stream; default 3) and BV_PAIR_RES_MINKB (default 0) are the A/B switches.
     {
         static const int pair_mask = getenv("BV_PAIR") ? atoi(getenv("BV_PAIR")) : 3;
-        static const int pair_minkb = getenv("BV_PAIR_MINKB") ? atoi(getenv("BV_PAIR_MINKB")) : 0;
-        if (!out_fp32 && total_kblocks >= pair_minkb && pair_launchable()) {
-            if (cfg == kCfg256Deep && (pair_mask & 1)) cfg = kCfg256PairDeep;
-            else if (cfg == kCfg256Res && (pair_mask & 2)) cfg = kCfg256PairRes;
+        static const int res_minkb = getenv("BV_PAIR_RES_MINKB") ? atoi(getenv("BV_PAIR_RES_MINKB")) : 0;
+        static const int variant = getenv("BV_PAIR_VARIANT") ? atoi(getenv("BV_PAIR_VARIANT")) : 0;   // experiment: bit 0 / bit 1
+        if (!out_fp32 && pair_launchable()) {
+            if (cfg == kCfg256Deep && (pair_mask & 1)) cfg = (variant & 1) ? kCfg256PairDeepE16 : kCfg256PairDeep;
+            else if (cfg == kCfg256Res && (pair_mask & 2) && total_kblocks >= res_minkb)
+                cfg = (variant & 2) ? kCfg256PairRes37 : kCfg256PairRes;
         }
     }
     if (const char* force = getenv("BV_FORCE_CFG")) {

@@ -246,3 +246,71 @@ def test_two_m_tiles_per_stage(env, case, monkeypatch):
     assert torch.equal(out, ref), f"transposed tile: max abs diff {(out.float() - ref.float()).abs().max().item()}"
     ref_lin = ref64.permute(0, 2, 3, 1).float().to(torch.bfloat16)
     assert torch.equal(_conv_native(lib, N, x, conv, relu=False, out_fp32=False), ref_lin)
+
+
+PAIR_CASES = [
+    # name,               B,  H,  Cin, Cout, k, stride, pad, residual, cfg
+    ("1x1_k1024_n256",     2, 30, 1024,  256, 1, 1, 0, False, 10),
+    ("1x1_odd_blocks",     5, 15, 2048,  512, 1, 1, 0, False, 10),      # 1125 rows = 9 m-blocks: the last pair is half empty
+    ("3x3_c256",           3, 30,  256,  256, 3, 1, 1, False, 10),
+    ("3x3_s2_c256",        3, 60,  256,  256, 3, 2, 1, False, 10),
+    ("3x3_c512_longK",     2, 15,  512,  512, 3, 1, 1, False, 10),
+    ("many_tiles",         8, 60,  128,  512, 1, 1, 0, False, 10),      # 225 m-blocks x 2 n-blocks = 226 pair tiles > 74 pairs
+    ("res_k256_n1024",     5, 30,  256, 1024, 1, 1, 0, True, 11),
+    ("res_k512_n2048",     2, 15,  512, 2048, 1, 1, 0, True, 11),
+    ("res_odd_blocks",     3, 15,  512,  256, 1, 1, 0, True, 11),       # 675 rows = 6 blocks; B=1 below gives 2 blocks
+    ("res_many_tiles",     8, 60,  128,  512, 1, 1, 0, True, 11),
+    ("res_3x3",            4, 30,  192,  256, 3, 1, 1, True, 11),
+    ("deep_with_res",      4, 30,  192,  256, 3, 1, 1, True, 10),
+]
+
+
+@pytest.mark.parametrize("case", PAIR_CASES, ids=[c[0] for c in PAIR_CASES])
+def test_cta_pair_configurations(env, case, monkeypatch):
+    """The 256-wide tile on CTA pairs (tcgen05 cta_group::2; kCfg256PairDeep = 10, kCfg256PairRes = 11): every shape is
+    computed by the forced pair configuration AND by the single-CTA configuration it replaces, both bit-exact against
+    the fp64 reference on integer operands."""
+    N, lib, packing = env
+    name, B, H, cin, cout, k, stride, pad, with_res, cfg = case
+    gen = torch.Generator().manual_seed(zlib.crc32(name.encode()))
+    dev = torch.device("cuda:0")
+    x = torch.randint(-2, 3, (B, H, H, cin), generator=gen).float().to(torch.bfloat16).to(dev)
+    w = torch.randint(-1, 2, (cout, cin, k, k), generator=gen).float().to(torch.bfloat16)
+    b = torch.randint(-2, 3, (cout,), generator=gen).float()
+    conv = packing.pack_single_conv(w, b, stride, pad, dev)
+    ref64 = F.conv2d(x.double().permute(0, 3, 1, 2), w.to(dev).double(), b.to(dev).double(), stride=stride, padding=pad)
+    ref = ref64.permute(0, 2, 3, 1)
+    res = None
+    if with_res:
+        res = torch.randint(-2, 3, tuple(ref.shape), generator=gen).float().to(torch.bfloat16).to(dev)
+        ref = ref + res.double()
+    ref = torch.relu(ref).float().to(torch.bfloat16)
+    for forced in (cfg, 0 if cfg == 10 else 1):
+        monkeypatch.setenv("BV_FORCE_CFG", str(forced))
+        out = _conv_native(lib, N, x, conv, residual=res, relu=True, out_fp32=False)
+        assert not torch.isnan(out.float()).any(), f"cfg {forced}: unwritten rows"
+        assert torch.equal(out, ref), f"cfg {forced}: max abs diff {(out.float() - ref.float()).abs().max().item()}"
+
+
+@pytest.mark.parametrize("stride", [1, 2])
+def test_cta_pair_fused_downsample(env, stride, monkeypatch):
+    """Two K segments (conv3 over t2 + strided downsample over the block input) accumulated by the pair kernel."""
+    N, lib, packing = env
+    gen = torch.Generator().manual_seed(70 + stride)
+    dev = torch.device("cuda:0")
+    B, Hin, cin, mid = 3, 30, 512, 256
+    cout = mid * 4
+    Ho = Hin // stride
+    x = torch.randint(-2, 3, (B, Hin, Hin, cin), generator=gen).float().to(torch.bfloat16).to(dev)
+    t2 = torch.randint(-2, 3, (B, Ho, Ho, mid), generator=gen).float().to(torch.bfloat16).to(dev)
+    w3 = torch.randint(-1, 2, (cout, mid, 1, 1), generator=gen).float().to(torch.bfloat16)
+    wd = torch.randint(-1, 2, (cout, cin, 1, 1), generator=gen).float().to(torch.bfloat16)
+    b3 = torch.randint(-2, 3, (cout,), generator=gen).float()
+    bd = torch.randint(-2, 3, (cout,), generator=gen).float()
+    c3 = packing.pack_single_conv(w3, b3, 1, 0, dev)
+    cd = packing.pack_single_conv(wd, bd, stride, 0, dev)
+    ref = torch.relu(_ref(t2, w3.to(dev), b3.to(dev), 1, 0) + _ref(x, wd.to(dev), bd.to(dev), stride, 0)).to(torch.bfloat16)
+    for forced in (10, 0):
+        monkeypatch.setenv("BV_FORCE_CFG", str(forced))
+        out = _conv_native(lib, N, t2, c3, x2=x, conv2=cd, relu=True, out_fp32=False)
+        assert torch.equal(out, ref), f"cfg {forced}"
