@@ -200,6 +200,13 @@ int32_t bv_l1_block_nhwc(const void* t1, int32_t batch, int32_t height, int32_t 
                          const bv_conv* host_c3, const void* residual, void* out1, const bv_conv* host_next, void* out2,
                          bv_stream stream);
 
+/* The same kernel for the FIRST block of the layer (downsample branch instead of an identity, resnet.py:39 with
+ * Bottleneck.downsample): out1 = relu(conv1x1(t2, c3) + c3.bias + conv1x1(x0, ds) + ds.bias), x0 [B,H,W,64] the block
+ * input, ds a 64 -> 256 1x1 stride-1 bv_conv; everything else as bv_l1_block_nhwc. */
+int32_t bv_l1_block_ds_nhwc(const void* t1, int32_t batch, int32_t height, int32_t width, const bv_conv* host_c2,
+                            const bv_conv* host_c3, const void* x0, const bv_conv* host_ds, void* out1,
+                            const bv_conv* host_next, void* out2, bv_stream stream);
+
 /* Validation vehicle for the CTA-pair (tcgen05 cta_group::2) building blocks in csrc/pair_gemm.cuh:
  *   out[M,N] (fp32) = a[M,K] (bf16) x w[N,K]^T (bf16);  N multiple of 32 in [32,256], K multiple of 64. */
 int32_t bv_pair_gemm_test(const void* a, const void* w, int32_t m, int32_t n, int32_t k, float* out, bv_stream stream);

@@ -68,7 +68,7 @@ EXPORTED_SYMBOLS = (
     "bv_conv2d_nhwc", "bv_conv_chain_nhwc", "bv_smooth_heatmaps",
     "bv_resize_workspace_bytes", "bv_resize_center_crop_u8", "bv_pair_gemm_test", "bv_l1_block_nhwc",
     "bv_stem_u8_nhwc", "bv_stem_conv1_u8_nhwc", "bv_forward_graph", "bv_pairwise_cosine", "bv_quantize_frames_f32",
-    "bv_jpeg_info", "bv_jpeg_decode_gray_u8",
+    "bv_jpeg_info", "bv_jpeg_decode_gray_u8", "bv_l1_block_ds_nhwc",
 )
 
 _lib = None
@@ -144,6 +144,9 @@ def lib() -> ctypes.CDLL:
     l.bv_l1_block_nhwc.restype = c_int32
     l.bv_l1_block_nhwc.argtypes = [c_void_p, c_int32, c_int32, c_int32, POINTER(BvConv), POINTER(BvConv), c_void_p, c_void_p,
                                    POINTER(BvConv), c_void_p, c_void_p]
+    l.bv_l1_block_ds_nhwc.restype = c_int32
+    l.bv_l1_block_ds_nhwc.argtypes = [c_void_p, c_int32, c_int32, c_int32, POINTER(BvConv), POINTER(BvConv), c_void_p,
+                                      POINTER(BvConv), c_void_p, POINTER(BvConv), c_void_p, c_void_p]
     l.bv_stem_u8_nhwc.restype = c_int32
     l.bv_stem_u8_nhwc.argtypes = [c_void_p, c_int32, c_int32, c_int32, POINTER(BvConv), c_void_p, c_int32, c_void_p]
     l.bv_stem_conv1_u8_nhwc.restype = c_int32

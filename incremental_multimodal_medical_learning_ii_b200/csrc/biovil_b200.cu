@@ -126,11 +126,13 @@ bool env_flag(const char* name) {
     return v && v[0] && v[0] != '0';
 }
 
-// Every kernel of the forward goes through here: optional thread-block cluster, and programmatic dependent launch
-// (ptx.cuh: pdl_launch_dependents / pdl_wait) so that the next kernel's prologue overlaps this kernel's tail.
-// BV_NO_PDL=1 launches with plain stream serialisation (A/B switch).
+// Every kernel of the forward goes through here: optional thread-block cluster and - opt-in, BV_PDL=1 - programmatic
+// dependent launch (ptx.cuh: pdl_launch_dependents / pdl_wait; the next kernel's prologue would overlap this kernel's
+// tail).  PDL is OFF by default: same-box A/B showed no gain at batch 512 (21.28k / 21.51k img/s with, 21.37k without:
+// one CTA per SM with ~200 KB of shared memory leaves nothing to overlap but the prologue), and a stress loop of 5000
+// forwards (tools/stress_forward.py) hit an "unspecified launch failure" twice with it on and never with it off.
 bool pdl_enabled() {
-    static const bool on = !env_flag("BV_NO_PDL");
+    static const bool on = env_flag("BV_PDL");
     return on;
 }
 template <typename... KArgs, typename... Args>
@@ -222,6 +224,7 @@ struct ChainLaunch {
 struct L1Launch {
     bv::L1BlockParams p;
     int grid;
+    bool ds;   // first block of the layer: downsample branch as a second K segment instead of an identity tensor
 };
 
 // One step of the forward plan: a single fused convolution, a chained pair, or a fused layer1 block.
@@ -267,6 +270,8 @@ int set_kernel_attributes() {
                                  bv::kTap3SmemBytes));
     BV_CUDA(cudaFuncSetAttribute(bv::l1_block_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  bv::L1Cfg<64>::kSmemBytes));
+    BV_CUDA(cudaFuncSetAttribute(bv::l1_block_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 bv::L1Cfg<64, true>::kSmemBytes));
     BV_CUDA(cudaFuncSetAttribute(bv::head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
     BV_CUDA(cudaFuncSetAttribute(bv::stem_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  bv::kStemSmemRequest));
@@ -585,19 +590,34 @@ bool l1_block_supported(const bv_conv& c2, const bv_conv& c3, const bv_conv& nex
            next.stride == 1 && next.pad == 0 && next.cin == 256 && next.cout == 64;
 }
 
+bool l1_ds_supported(const bv_conv& ds) {
+    return ds.w != nullptr && ds.r == 1 && ds.s == 1 && ds.stride == 1 && ds.pad == 0 && ds.cin == 64 && ds.cout == 256;
+}
+
 // t1 [B,H,W,64] -> out1 = relu(conv3(relu(conv2(t1))) + residual) [B,H,W,256], out2 = relu(next(out1)) [B,H,W,64]
+// With a downsample branch (x0 [B,H,W,64], ds 64 -> 256 1x1) instead of a residual: out1 = relu(conv3(..) + ds(x0)).
 int build_l1_block(L1Launch* L, int B, int H, int W, const void* t1, const bv_conv& c2, const bv_conv& c3,
-                   const void* residual, void* out1, const bv_conv& next, void* out2) {
+                   const void* residual, void* out1, const bv_conv& next, void* out2, const void* x0 = nullptr,
+                   const bv_conv* ds = nullptr) {
     if (!l1_block_supported(c2, c3, next, W))
         return fail(BV_ERR_INVALID, "unsupported shapes for the fused layer1 block (64->64 3x3, 64->256, 256->64, width %% 30 == 0)");
-    if (!residual) return fail(BV_ERR_INVALID, "the fused layer1 block needs an identity residual");
+    const bool use_ds = x0 != nullptr && ds != nullptr;
+    if (use_ds && (residual || !l1_ds_supported(*ds)))
+        return fail(BV_ERR_INVALID, "the downsample form of the fused layer1 block takes a 64 -> 256 1x1 stride-1 branch and no residual");
+    if (!use_ds && !residual) return fail(BV_ERR_INVALID, "the fused layer1 block needs an identity residual or a downsample branch");
     memset(&L->p, 0, sizeof(L->p));
     bv::L1BlockParams& p = L->p;
     const long long groups = (long long)B * H * (W / bv::kTap3Group);
     if (groups <= 0 || groups > 0x7fffffffLL / 64) return fail(BV_ERR_INVALID, "too many rows (%lld lane quarters)", groups);
     int rc;
     if ((rc = make_tmap_im2col(&p.tmA, t1, B, H, W, 64, 3, 3, 1, 1, true, 32))) return rc;
-    if ((rc = make_tmap_lines(&p.tmRes, residual, B * H, W, 256, 32))) return rc;
+    if (use_ds) {
+        if ((rc = make_tmap_lines(&p.tmX0, x0, B * H, W, 64, 32))) return rc;
+        if ((rc = make_tmap_2d(&p.tmWd, ds->w, 64, 256, bv::kBlockK, 128))) return rc;
+        p.bias_ds = ds->bias;
+    } else {
+        if ((rc = make_tmap_lines(&p.tmRes, residual, B * H, W, 256, 32))) return rc;
+    }
     if ((rc = make_tmap_2d(&p.tmW2, c2.w, 576, 64, bv::kBlockK, 32))) return rc;
     if ((rc = make_tmap_2d(&p.tmW3, c3.w, 64, 256, bv::kBlockK, 128))) return rc;
     if ((rc = make_tmap_2d(&p.tmW1, next.w, 256, 64, bv::kBlockK, 32))) return rc;
@@ -613,6 +633,7 @@ int build_l1_block(L1Launch* L, int B, int H, int W, const void* t1, const bv_co
     p.num_tiles = (int)((groups + 3) / 4);
     p.num_pair_tiles = (p.num_tiles + 1) / 2;
     L->grid = 2 * std::min(p.num_pair_tiles, g_num_sms / 2);
+    L->ds = use_ds;
     return BV_OK;
 }
 
@@ -650,7 +671,8 @@ int launch_l1_block(const L1Launch& L, cudaStream_t st) {
         cudaMemsetAsync(g_dbg, 0, 4 * 8 * 1024, st);
         prm.dbg = g_dbg;
     }
-    BV_CUDA(launch_ex(bv::l1_block_kernel<64>, L.grid, bv::kL1Threads, bv::L1Cfg<64>::kSmemBytes, st, 2, prm));
+    if (L.ds) BV_CUDA(launch_ex(bv::l1_block_kernel<64, true>, L.grid, bv::kL1Threads, bv::L1Cfg<64, true>::kSmemBytes, st, 2, prm));
+    else BV_CUDA(launch_ex(bv::l1_block_kernel<64>, L.grid, bv::kL1Threads, bv::L1Cfg<64>::kSmemBytes, st, 2, prm));
     if (prm.dbg) {
         static long long host[8 * 128];
         const int pairs = L.grid / 2;
@@ -831,9 +853,10 @@ void chain_cost(const ChainLaunch& L, double* flops, double* bytes, char* name, 
 
 void l1_cost(const L1Launch& L, double* flops, double* bytes, char* name, size_t n) {
     const double Mr = (double)L.p.num_groups * bv::kTap3Group;   // output pixels
-    *flops = 2.0 * Mr * 64 * 576 + 2.0 * Mr * 256 * 64 + 2.0 * Mr * 64 * 256;
-    *bytes = Mr * 64 * 2 + Mr * 256 * 2 * 2 + Mr * 64 * 2 + (576.0 * 64 + 64 * 256 + 256 * 64) * 2;
-    snprintf(name, n, "l1_block<64> M=%.0f 3x3(64)+1x1(256)+res+1x1(64)", Mr);
+    *flops = 2.0 * Mr * 64 * 576 + 2.0 * Mr * 256 * 64 * (L.ds ? 2 : 1) + 2.0 * Mr * 64 * 256;
+    *bytes = Mr * 64 * 2 + (L.ds ? Mr * 64 * 2 + Mr * 256 * 2 : Mr * 256 * 2 * 2) + Mr * 64 * 2 +
+             (576.0 * 64 + 64 * 256 * (L.ds ? 2 : 1) + 256 * 64) * 2;
+    snprintf(name, n, "l1_block<64> M=%.0f 3x3(64)+1x1(256)+%s+1x1(64)", Mr, L.ds ? "ds" : "res");
 }
 
 void step_cost(const PlanStep& s, double* flops, double* bytes, char* name, size_t n) {
@@ -1034,11 +1057,14 @@ static int build_plan(bv_handle* h, const void* frames, int dtype, int B, int C,
             }
             // layer1 blocks with an identity residual whose successor's conv1 is 64 wide: the whole tail of the block
             // (conv2 3x3, conv3 + identity, next conv1) is one CTA-pair kernel
-            if (!env_flag("BV_NO_L1_FUSED") && l1_block_launchable() && ds.w == nullptr && blk + 1 < BV_NUM_BLOCKS &&
+            const bool l1_ds = ds.w != nullptr && l1_ds_supported(ds) && !env_flag("BV_NO_L1_DS");
+            if (!env_flag("BV_NO_L1_FUSED") && l1_block_launchable() && (ds.w == nullptr || l1_ds) && blk + 1 < BV_NUM_BLOCKS &&
                 l1_block_supported(c2, c3, h->w.conv1[blk + 1], cw)) {
                 PlanStep s;
                 s.l1 = true;
-                if ((rc = build_l1_block(&s.l1b, B, ch, cw, t1, c2, c3, cur, nxt, h->w.conv1[blk + 1], t2))) return rc;
+                if (l1_ds) rc = build_l1_block(&s.l1b, B, ch, cw, t1, c2, c3, nullptr, nxt, h->w.conv1[blk + 1], t2, cur, &ds);
+                else rc = build_l1_block(&s.l1b, B, ch, cw, t1, c2, c3, cur, nxt, h->w.conv1[blk + 1], t2);
+                if (rc) return rc;
                 h->steps.push_back(s);
                 // the next block's conv1 output went to t2: swap the roles of the two scratch buffers
                 std::swap(t1, t2);
@@ -1659,6 +1685,16 @@ int32_t bv_l1_block_nhwc(const void* t1, int32_t B, int32_t H, int32_t W, const 
     if (rc) return rc;
     L1Launch L;
     if ((rc = build_l1_block(&L, B, H, W, t1, *c2, *c3, residual, out1, *next, out2))) return rc;
+    return launch_l1_block(L, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int32_t bv_l1_block_ds_nhwc(const void* t1, int32_t B, int32_t H, int32_t W, const bv_conv* c2, const bv_conv* c3,
+                            const void* x0, const bv_conv* ds, void* out1, const bv_conv* next, void* out2, bv_stream stream) {
+    if (!t1 || !c2 || !c3 || !x0 || !ds || !out1 || !next || !out2) return fail(BV_ERR_INVALID, "null argument");
+    int rc = device_setup();
+    if (rc) return rc;
+    L1Launch L;
+    if ((rc = build_l1_block(&L, B, H, W, t1, *c2, *c3, nullptr, out1, *next, out2, x0, ds))) return rc;
     return launch_l1_block(L, reinterpret_cast<cudaStream_t>(stream));
 }
 

@@ -32,6 +32,13 @@
 // through tiled 3-D TMA stores of [1 line x 30 pixels x 64 channels]: the two overlap rows of each lane quarter are
 // not part of the box and the padding columns are out of bounds, so neither is written; per-thread copy-out loops
 // stalled the epilogue warps on the store queue for 40 % of their time).
+//
+// DS = the FIRST block of the layer (torchvision Bottleneck with a downsample branch, resnet.py:39): there is no identity
+// tensor; y = relu(conv3(t2) + b3 + downsample_1x1(x0) + b_ds) is one accumulation over two K segments ([t2 | x0] against
+// [W3 | W_ds]) in the same TMEM tile.  The loader warp fetches the 64-channel x0 rows of the tile (16 KB, instead of 64 KB of
+// identity rows) into their own A tile; the y staging ring carries no prefetched residual and shrinks to three sub-tiles,
+// which pays for the W_ds panel and the x0 tile.  Neither t2 nor the re-read of y touches HBM: 6.6 GB per 512-frame batch
+// instead of 10.4 GB for the tap-fused 3x3 kernel + the chained conv3/downsample/conv1 kernel it replaces.
 #pragma once
 #include "conv3x3_tap3.cuh"
 #include "pair_gemm.cuh"
@@ -40,8 +47,9 @@ namespace bv {
 
 constexpr int kL1Threads = 24 * 32;
 constexpr int kL1Stages = 2;      // A ring (a tile needs three stages: the third load waits for the first MMA group)
-constexpr int kL1YBufs = 5;       // y / identity staging sub-tiles: 4 per tile + 1, so that the identity rows of the next
-                                  // tile's sub-tile j only wait for THIS tile's sub-tile j-1 to drain
+// y / identity staging sub-tiles (L1Cfg::kYBufs): 4 per tile + 1 with an identity stream, so that the identity rows of the
+// next tile's sub-tile j only wait for THIS tile's sub-tile j-1 to drain; 3 in the downsample form (nothing is prefetched
+// into them)
 constexpr int kL1DmaWarp = 18;
 constexpr int kL1StoreWarp = 19;
 constexpr int kL1E2Warp0 = 20;   // warps 20..23: epilogue of the second GEMM, one warp per TMEM lane quarter
@@ -51,19 +59,24 @@ constexpr int kL1OffW2 = kL1OffA + kL1Stages * kABytes;    // 3 filter rows x [9
 constexpr int kL1OffW3 = kL1OffW2 + 3 * 96 * 128;          // [128 rows x 128 B]
 constexpr int kL1OffW1 = kL1OffW3 + 128 * 128;             // 4 k-blocks x [N2/2 rows x 128 B]
 
-template <int N2>
+template <int N2, bool DS = false>
 struct L1Cfg {
     static_assert(N2 == 64, "second-GEMM width supported by the TMEM plan (D1 256 + D0 192 + D2 64 columns)");
+    static constexpr int kYBufs = DS ? 3 : 5;
     static constexpr int kW1Bytes = 4 * (N2 / 2) * 128;
-    static constexpr int kOffT2 = kL1OffW1 + kW1Bytes;
-    static constexpr int kOffStg1 = kOffT2 + kABytes;          // 4 sub-tiles x 16 KB
-    static constexpr int kOffStg2 = kOffStg1 + kL1YBufs * kStagingBytes;
+    static constexpr int kWdBytes = DS ? 128 * 128 : 0;          // this CTA's half of the downsample weights [128 rows x 128 B]
+    static constexpr int kOffWd = kL1OffW1 + kW1Bytes;
+    static constexpr int kOffX0 = kOffWd + kWdBytes;             // DS: x0 A tile [128 rows x 128 B]
+    static constexpr int kOffT2 = kOffX0 + (DS ? kABytes : 0);
+    static constexpr int kOffStg1 = kOffT2 + kABytes;            // kYBufs sub-tiles x 16 KB
+    static constexpr int kOffStg2 = kOffStg1 + kYBufs * kStagingBytes;
     static constexpr int kOffBars = kOffStg2 + (N2 / 64) * kStagingBytes;
-    static constexpr int kNumBars = 2 * kL1Stages + 1 + 8 + 24 + kL1YBufs + 2;
+    static constexpr int kNumBars = 2 * kL1Stages + 1 + 8 + 24 + kYBufs + 2 + 2;
     static constexpr int kOffBias = (kOffBars + kNumBars * 8 + 16 + 15) / 16 * 16;               // fp32: bias3[256] | bias2[64] | bias1[N2]
     static constexpr int kSmemBytes = kOffBias + (256 + 64 + N2) * 4;
-    static constexpr uint32_t kWeightBytes = 3 * 96 * 128 + 128 * 128 + kW1Bytes;
-    static_assert(kOffT2 % 1024 == 0 && kOffStg1 % 1024 == 0 && kOffStg2 % 1024 == 0, "operand tiles need 1024-byte alignment");
+    static constexpr uint32_t kWeightBytes = 3 * 96 * 128 + 128 * 128 + kW1Bytes + kWdBytes;
+    static_assert(kOffWd % 1024 == 0 && kOffX0 % 1024 == 0 && kOffT2 % 1024 == 0 && kOffStg1 % 1024 == 0 && kOffStg2 % 1024 == 0,
+                  "operand tiles need 1024-byte alignment");
     static_assert(kSmemBytes <= 232448, "exceeds the 227 KB of shared memory a CTA may use");
 };
 
@@ -73,6 +86,9 @@ struct L1BlockParams {
     CUtensorMap tmW2;   // [64, 576]  box 64 x 32
     CUtensorMap tmW3;   // [256, 64]  box 64 x 128
     CUtensorMap tmW1;   // [N2, 256]  box 64 x N2/2
+    CUtensorMap tmX0;   // DS: block input x0 as (64, W, B*H), tiled, box 64 channels x 32 pixels x 1 line
+    CUtensorMap tmWd;   // DS: downsample weights [256, 64], box 64 x 128
+    const float* bias_ds;   // DS: added to bias3
     CUtensorMap tmOut1; // y   as (256, W, B*H), tiled, box 64 channels x 30 pixels x 1 line
     CUtensorMap tmOut2; // t1' as (N2,  W, B*H), tiled, box 64 channels x 30 pixels x 1 line
     const float* bias2;
@@ -104,6 +120,16 @@ __device__ __forceinline__ void tma_load_3d(const CUtensorMap* m, uint64_t* bar,
         "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
         " [%0], [%1, {%3, %4, %5}], [%2], %6;\n" ::"r"(smem_u32(dst)),
         "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c), "r"(w), "r"(line), "l"(policy)
+        : "memory");
+}
+// the same load with its completion bytes credited to the LEADER's barrier (the pair MMA consumes both CTAs' tiles)
+__device__ __forceinline__ void tma_load_3d_pair(const CUtensorMap* m, uint64_t* bar, void* dst, int c, int w, int line,
+                                                 uint64_t policy) {
+    const uint32_t bar_addr = smem_u32(bar) & kPeerBitMask;
+    asm volatile(
+        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+        " [%0], [%1, {%3, %4, %5}], [%2], %6;\n" ::"r"(smem_u32(dst)),
+        "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_addr), "r"(c), "r"(w), "r"(line), "l"(policy)
         : "memory");
 }
 // Pull one box into L2 (no smem destination, no completion tracking).
@@ -155,7 +181,9 @@ __device__ __forceinline__ void l1_convert_row32(const uint32_t (&v)[32], const 
     }
 }
 
-// 16 accumulator columns (two 16-byte groups, index g2 = 0..3 inside the 64-column sub-tile) of one row
+// 16 accumulator columns (two 16-byte groups, index g2 = 0..3 inside the 64-column sub-tile) of one row; RES = the staging
+// row holds the identity values to add (otherwise it is only written)
+template <bool RES = true>
 __device__ __forceinline__ void l1_convert_row16(const uint32_t (&v)[16], const float* __restrict__ bias_s, uint8_t* row_ptr,
                                                  int l, int g2) {
     const float4* bp = reinterpret_cast<const float4*>(bias_s);
@@ -164,7 +192,8 @@ __device__ __forceinline__ void l1_convert_row16(const uint32_t (&v)[16], const 
     for (int j2 = 0; j2 < 2; ++j2) {
         const int jj = g2 * 2 + j2;
         uint4* sp = reinterpret_cast<uint4*>(row_ptr + ((jj ^ (l & 7)) << 4));
-        const uint4 rv = *sp;
+        uint4 rv = make_uint4(0u, 0u, 0u, 0u);
+        if constexpr (RES) rv = *sp;
         const uint32_t r[4] = {rv.x, rv.y, rv.z, rv.w};
         const float4 b0 = bp[2 * j2], b1 = bp[2 * j2 + 1];
         const float2 bb[4] = {make_float2(b0.x, b0.y), make_float2(b0.z, b0.w), make_float2(b1.x, b1.y), make_float2(b1.z, b1.w)};
@@ -173,7 +202,7 @@ __device__ __forceinline__ void l1_convert_row16(const uint32_t (&v)[16], const 
         for (int e = 0; e < 4; ++e) {
             float2 a = make_float2(__uint_as_float(v[8 * j2 + 2 * e]), __uint_as_float(v[8 * j2 + 2 * e + 1]));
             a = add2(a, bb[e]);
-            a = add2(a, make_float2(__uint_as_float(r[e] << 16), __uint_as_float(r[e] & 0xFFFF0000u)));
+            if constexpr (RES) a = add2(a, make_float2(__uint_as_float(r[e] << 16), __uint_as_float(r[e] & 0xFFFF0000u)));
             __nv_bfloat162 h = __floats2bfloat162_rn(a.x, a.y);
             h = __hmax2(h, zero2);
             w[e] = *reinterpret_cast<const uint32_t*>(&h);
@@ -182,15 +211,18 @@ __device__ __forceinline__ void l1_convert_row16(const uint32_t (&v)[16], const 
     }
 }
 
-template <int N2>
+template <int N2, bool DS = false>
 __global__ void __launch_bounds__(kL1Threads, 1) l1_block_kernel(const __grid_constant__ L1BlockParams p) {
-    using Cfg = L1Cfg<N2>;
+    using Cfg = L1Cfg<N2, DS>;
+    constexpr int kL1YBufs = Cfg::kYBufs;
     extern __shared__ __align__(1024) uint8_t smem[];
     if ((smem_u32(smem) & 1023u) != 0u) __trap();
     uint8_t* smem_a = smem + kL1OffA;
     uint8_t* smem_w2 = smem + kL1OffW2;
     uint8_t* smem_w3 = smem + kL1OffW3;
     uint8_t* smem_w1 = smem + kL1OffW1;
+    uint8_t* smem_wd = smem + Cfg::kOffWd;      // DS only
+    uint8_t* x0_tile = smem + Cfg::kOffX0;      // DS only
     uint8_t* t2_tile = smem + Cfg::kOffT2;
     uint8_t* stg1 = smem + Cfg::kOffStg1;
     uint8_t* stg2 = smem + Cfg::kOffStg2;
@@ -215,10 +247,13 @@ __global__ void __launch_bounds__(kL1Threads, 1) l1_block_kernel(const __grid_co
     uint64_t* y_local = res_ready + kL1YBufs;            // [4] per CTA, 16 warps: y sub-tile j written (for the storer)
     uint64_t* e2_local = y_local + 4;             // per CTA, 16 warps: t1' tile written
     uint64_t* stg2_free = e2_local + 1;           // per CTA: the TMA stores of t1' have read smem
+    uint64_t* x0_full = stg2_free + 1;            // DS, leader: the x0 tiles of BOTH CTAs have landed (TMA tx)
+    uint64_t* x0_free = x0_full + 1;              // DS, per CTA (multicast commit after G1): the x0 tile may be refilled
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + Cfg::kNumBars);
     float* bias_s = reinterpret_cast<float*>(smem + Cfg::kOffBias);
     for (int i = threadIdx.x; i < 256 + 64 + N2; i += kL1Threads)
-        bias_s[i] = (i < 256) ? __ldg(p.bias3 + i) : (i < 320 ? __ldg(p.bias2 + i - 256) : __ldg(p.bias1 + i - 320));
+        bias_s[i] = (i < 256) ? __ldg(p.bias3 + i) + (DS ? __ldg(p.bias_ds + i) : 0.0f)
+                              : (i < 320 ? __ldg(p.bias2 + i - 256) : __ldg(p.bias1 + i - 320));
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -230,7 +265,12 @@ __global__ void __launch_bounds__(kL1Threads, 1) l1_block_kernel(const __grid_co
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&p.tmA);
-        tma_prefetch_desc(&p.tmRes);
+        if constexpr (DS) {
+            tma_prefetch_desc(&p.tmX0);
+            tma_prefetch_desc(&p.tmWd);
+        } else {
+            tma_prefetch_desc(&p.tmRes);
+        }
         tma_prefetch_desc(&p.tmW2);
         tma_prefetch_desc(&p.tmW3);
         tma_prefetch_desc(&p.tmW1);
@@ -252,6 +292,8 @@ __global__ void __launch_bounds__(kL1Threads, 1) l1_block_kernel(const __grid_co
         mbar_init(e2_local, 4);
         for (int b = 0; b < kL1YBufs; ++b) mbar_init(&res_ready[b], 1);
         mbar_init(stg2_free, 1);
+        mbar_init(x0_full, 1);
+        mbar_init(x0_free, 1);
         for (int j = 0; j < 4; ++j) {
             mbar_init(&sub_written[j], 32);
             mbar_init(&sub_consumed[j], 1);
@@ -306,6 +348,7 @@ __global__ void __launch_bounds__(kL1Threads, 1) l1_block_kernel(const __grid_co
             for (int kb = 0; kb < 4; ++kb)
                 tma_load_2d_pair(&p.tmW1, w_bar, smem_w1 + kb * (N2 / 2) * 128, kb * kBlockK, (N2 / 2) * static_cast<int>(rank),
                                  kEvictLast);
+            if constexpr (DS) tma_load_2d_pair(&p.tmWd, w_bar, smem_wd, 0, 128 * static_cast<int>(rank), kEvictLast);
         }
         __syncwarp();
         int stage = 0;
@@ -333,6 +376,20 @@ __global__ void __launch_bounds__(kL1Threads, 1) l1_block_kernel(const __grid_co
                     stage = 0;
                     phase ^= 1u;
                 }
+            }
+            if constexpr (DS) {
+                // x0 rows of this tile (row j of lane quarter q = pixel gq[q] + j of line gl[q], the output pixel of TMEM
+                // lane 32 q + j).  Issued here, right behind the tile's last filter-row load: the first GEMM-1 of the
+                // PREVIOUS tile (which frees the x0 tile) precedes the G0 that freed that ring stage, and G1 of this tile is
+                // a whole tile time away - the load has microseconds to land.
+                if (t > 0) mbar_wait(x0_free, (t - 1) & 1u);
+                if (elect_one()) {
+                    if (rank == 0) mbar_arrive_expect_tx(x0_full, 2u * kABytes);
+#pragma unroll
+                    for (int g = 0; g < 4; ++g)
+                        tma_load_3d_pair(&p.tmX0, x0_full, x0_tile + g * 4096, 0, gq[g], gl[g], kEvictFirst);
+                }
+                __syncwarp();
             }
         }
     } else if (warp == 1) {
@@ -381,6 +438,7 @@ __global__ void __launch_bounds__(kL1Threads, 1) l1_block_kernel(const __grid_co
             auto g1 = [&](int t) {
                 timed_wait(d1_empty, (t & 1u) ^ 1u, 3);
                 timed_wait(t2_ready, t & 1u, 4);
+                if constexpr (DS) timed_wait(x0_full, t & 1u, 4);
                 trace(t, 1);   // t2_ready seen
                 tc_fence_after();
                 if (elect_one()) {
@@ -390,6 +448,15 @@ __global__ void __launch_bounds__(kL1Threads, 1) l1_block_kernel(const __grid_co
                     for (int k = 0; k < 4; ++k)
                         umma_bf16_ss_pair(tmem_base + kD1, adesc + static_cast<uint64_t>(2 * k),
                                           bdesc + static_cast<uint64_t>(2 * k), idesc1, k != 0 ? 1u : 0u);
+                    if constexpr (DS) {   // second K segment: downsample_1x1(x0) accumulates into the same tile
+                        const uint64_t xdesc = umma_desc_k_sw128(base + static_cast<uint32_t>(Cfg::kOffX0));
+                        const uint64_t wdesc = umma_desc_k_sw128(base + static_cast<uint32_t>(Cfg::kOffWd));
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            umma_bf16_ss_pair(tmem_base + kD1, xdesc + static_cast<uint64_t>(2 * k),
+                                              wdesc + static_cast<uint64_t>(2 * k), idesc1, 1u);
+                        umma_commit_pair(x0_free);
+                    }
                     umma_commit_pair(t2_free);
                     umma_commit_pair(d1_full);
                 }
@@ -441,7 +508,7 @@ __global__ void __launch_bounds__(kL1Threads, 1) l1_block_kernel(const __grid_co
             for (int t = 0; t < T; ++t) {
                 int gl[4], gq[4];
                 group_coords(tile_of(t), gl, gq);
-                if (p.l2_prefetch && t + 1 < T) {
+                if (!DS && p.l2_prefetch && t + 1 < T) {
                     int nl[4], nq[4];
                     group_coords(tile_of(t + 1), nl, nq);
                     for (int j = 0; j < 4; ++j)
@@ -458,11 +525,15 @@ __global__ void __launch_bounds__(kL1Threads, 1) l1_block_kernel(const __grid_co
                         mbar_wait(&store_done[(tp & 1) * 4 + jp], (tp >> 1) & 1u);
                     }
                     const int b = g % kL1YBufs;
-                    mbar_arrive_expect_tx(&res_ready[b], kStagingBytes);
+                    if constexpr (DS) {
+                        mbar_arrive(&res_ready[b]);   // nothing to prefetch: the buffer is simply free again
+                    } else {
+                        mbar_arrive_expect_tx(&res_ready[b], kStagingBytes);
 #pragma unroll
-                    for (int q = 0; q < 4; ++q)
-                        tma_load_3d(&p.tmRes, &res_ready[b], stg1 + b * kStagingBytes + q * 4096, j * kChunkCols, gq[q], gl[q],
-                                    kEvictFirst);
+                        for (int q = 0; q < 4; ++q)
+                            tma_load_3d(&p.tmRes, &res_ready[b], stg1 + b * kStagingBytes + q * 4096, j * kChunkCols, gq[q],
+                                        gl[q], kEvictFirst);
+                    }
                 }
             }
         }
@@ -472,6 +543,7 @@ __global__ void __launch_bounds__(kL1Threads, 1) l1_block_kernel(const __grid_co
             for (int t = 0; t < T; ++t) {
                 int gl[4], gq[4];
                 group_coords(tile_of(t), gl, gq);
+                uint64_t* sd = store_done + (t & 1) * 4;
                 for (int j = 0; j < 4; ++j) {
                     mbar_wait(&y_local[j], t & 1u);
 #pragma unroll
@@ -479,15 +551,24 @@ __global__ void __launch_bounds__(kL1Threads, 1) l1_block_kernel(const __grid_co
                         tma_store_3d(&p.tmOut1, stg1 + ((4 * t + j) % kL1YBufs) * kStagingBytes + g * 4096, j * kChunkCols, gq[g],
                                      gl[g]);
                     tma_store_commit();
+                    if constexpr (DS) {
+                        // three staging buffers: sub-tile 3 of THIS tile reuses the buffer of sub-tile 0, so "drained" must
+                        // be reported as the stores go, not after the tile's last one (which waits for sub-tile 3)
+                        if (j > 0) {
+                            tma_store_wait_read<1>();
+                            mbar_arrive(&sd[j - 1]);
+                        }
+                    }
                 }
                 // bulk groups complete in order: allow the 3 - j most recent ones to be pending
-                uint64_t* sd = store_done + (t & 1) * 4;
-                tma_store_wait_read<3>();
-                mbar_arrive(&sd[0]);
-                tma_store_wait_read<2>();
-                mbar_arrive(&sd[1]);
-                tma_store_wait_read<1>();
-                mbar_arrive(&sd[2]);
+                if constexpr (!DS) {
+                    tma_store_wait_read<3>();
+                    mbar_arrive(&sd[0]);
+                    tma_store_wait_read<2>();
+                    mbar_arrive(&sd[1]);
+                    tma_store_wait_read<1>();
+                    mbar_arrive(&sd[2]);
+                }
                 tma_store_wait_read<0>();
                 mbar_arrive(&sd[3]);
                 mbar_wait(e2_local, t & 1u);
@@ -628,7 +709,7 @@ __global__ void __launch_bounds__(kL1Threads, 1) l1_block_kernel(const __grid_co
                     __syncwarp();
                     if (lane == 0) mbar_arrive_leader(d1_empty);
                 }
-                l1_convert_row16(v, bias_s + j * kChunkCols + cg * 16, sub + l * 128, l, cg);
+                l1_convert_row16<!DS>(v, bias_s + j * kChunkCols + cg * 16, sub + l * 128, l, cg);
                 fence_proxy_async_smem();
                 __syncwarp();
                 if (lane == 0) {

@@ -25,12 +25,12 @@ __device__ __forceinline__ long long tclock() {
     return 0;
 }
 
-// Programmatic dependent launch (griddepcontrol): every kernel of the forward is launched with
-// cudaLaunchAttributeProgrammaticStreamSerialization.  launch_dependents lets the NEXT kernel's CTAs be scheduled as
-// SMs drain (their barrier init / TMEM allocation / descriptor prefetch then overlaps this kernel's tail); wait blocks
-// until every prerequisite grid has completed and its memory is visible.  All threads call pdl_wait() before their first
-// access to global memory that a previous kernel may have written (or may still be reading).  Both are no-ops when the
-// kernel was launched without the attribute.
+// Programmatic dependent launch (griddepcontrol), used only when the host launches with
+// cudaLaunchAttributeProgrammaticStreamSerialization (BV_PDL=1; off by default, see launch_ex in biovil_b200.cu).
+// launch_dependents lets the NEXT kernel's CTAs be scheduled as SMs drain (their barrier init / TMEM allocation /
+// descriptor prefetch then overlaps this kernel's tail); wait blocks until every prerequisite grid has completed and its
+// memory is visible.  All threads call pdl_wait() before their first access to global memory that a previous kernel may
+// have written (or may still be reading).  Both are no-ops when the kernel was launched without the attribute.
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;\n" ::: "memory"); }
 

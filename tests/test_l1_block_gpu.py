@@ -82,3 +82,58 @@ def test_l1_block_rejects_other_widths():
     rc = lib.bv_l1_block_nhwc(N.ptr(t1), 1, 16, 16, ctypes.byref(c2[0]), ctypes.byref(c3[0]), N.ptr(res), N.ptr(out1),
                               ctypes.byref(c1[0]), N.ptr(out2), N.current_stream_handle(dev))
     assert rc == N.BV_ERR_INVALID
+
+
+@pytest.mark.parametrize("B,H", [(1, 30), (3, 30), (2, 60), (2, 120), (20, 60), (5, 90)],
+                         ids=["tiny", "b3h30", "h60", "h120", "persistent", "h90"])
+@pytest.mark.parametrize("integer", [True, False], ids=["int", "gauss"])
+def test_l1_block_downsample_form(B, H, integer):
+    """First block of layer1 (Bottleneck with a downsample branch): conv2 -> conv3 + downsample_1x1(x0) -> next conv1 in
+    one CTA-pair kernel; the downsample is a second K segment of the conv3 accumulation, no identity tensor is read."""
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    from incremental_multimodal_medical_learning_ii_b200 import _native as N
+    from incremental_multimodal_medical_learning_ii_b200 import packing
+    lib = N.lib()
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(B * 1000 + H + 7)
+
+    def rnd(shape, lo, hi, scale):
+        return torch.randint(lo, hi, shape, generator=g).float() if integer else torch.randn(shape, generator=g) * scale
+
+    def sparse(w):
+        return (w * (torch.rand(w.shape, generator=g) < 0.25)).to(torch.bfloat16) if integer else w
+
+    t1 = rnd((B, H, H, 64), 0, 3, 1.0).to(torch.bfloat16).to(dev)
+    x0 = rnd((B, H, H, 64), 0, 3, 1.0).to(torch.bfloat16).to(dev)
+    w2 = sparse(rnd((64, 64, 3, 3), -1, 2, 576 ** -0.5).to(torch.bfloat16))
+    b2 = rnd((64,), -2, 3, 1.0)
+    w3 = sparse(rnd((256, 64, 1, 1), -1, 2, 64 ** -0.5).to(torch.bfloat16))
+    b3 = rnd((256,), -2, 3, 1.0)
+    wd = sparse(rnd((256, 64, 1, 1), -1, 2, 64 ** -0.5).to(torch.bfloat16))
+    bd = rnd((256,), -2, 3, 1.0)
+    w1 = rnd((64, 256, 1, 1), -1, 2, 256 ** -0.5).to(torch.bfloat16)
+    b1 = rnd((64,), -2, 3, 1.0)
+    c2 = packing.pack_single_conv(w2, b2, 1, 1, dev)
+    c3 = packing.pack_single_conv(w3, b3, 1, 0, dev)
+    cd = packing.pack_single_conv(wd, bd, 1, 0, dev)
+    c1 = packing.pack_single_conv(w1, b1, 1, 0, dev)
+
+    t2 = torch.relu(_ref(t1, w2.to(dev), b2.to(dev), 1)).to(torch.bfloat16)
+    y = torch.relu(_ref(t2, w3.to(dev), b3.to(dev), 0) + _ref(x0, wd.to(dev), bd.to(dev), 0)).to(torch.bfloat16)
+    t1n = torch.relu(_ref(y, w1.to(dev), b1.to(dev), 0)).to(torch.bfloat16)
+    if integer:
+        assert t2.float().abs().max() <= 256 and y.float().abs().max() <= 256, "test data must stay exact in bf16"
+    out1 = torch.full((B, H, H, 256), float("nan"), device=dev, dtype=torch.bfloat16)
+    out2 = torch.full((B, H, H, 64), float("nan"), device=dev, dtype=torch.bfloat16)
+    N.check(lib.bv_l1_block_ds_nhwc(N.ptr(t1), B, H, H, ctypes.byref(c2[0]), ctypes.byref(c3[0]), N.ptr(x0),
+                                    ctypes.byref(cd[0]), N.ptr(out1), ctypes.byref(c1[0]), N.ptr(out2),
+                                    N.current_stream_handle(dev)))
+    torch.cuda.synchronize()
+    assert not torch.isnan(out1.float()).any() and not torch.isnan(out2.float()).any(), "unwritten output rows"
+    if integer:
+        assert torch.equal(out1, y), f"out1 max abs diff {(out1.float() - y.float()).abs().max().item()}"
+        assert torch.equal(out2, t1n), f"out2 max abs diff {(out2.float() - t1n.float()).abs().max().item()}"
+    else:
+        torch.testing.assert_close(out1.float(), y.float(), rtol=2e-2, atol=2e-2)
+        torch.testing.assert_close(out2.float(), t1n.float(), rtol=3e-2, atol=3e-2)
