@@ -363,7 +363,7 @@ def run_ours(args):
     eng.set_profile(False)
     prof = prof_runs[-1]
     # every tcgen05 convolution launch of the step, the stem included (FLOP_PER_IMAGE counts the stem's FLOPs)
-    is_conv = lambda name: name.startswith(("conv_gemm", "chain_gemm", "l1_block", "stem_rows", "stem_fused"))  # noqa: E731
+    is_conv = lambda name: name.startswith(("conv_gemm", "chain_gemm", "pair_chain", "l1_block", "stem_rows", "stem_fused"))  # noqa: E731
     conv_ms = sum(ms for (name, fl, by, ms) in prof if is_conv(name))
     conv_flops_issued = sum(fl for (name, fl, by, ms) in prof if is_conv(name))
     conv_bytes = sum(by for (name, fl, by, ms) in prof if is_conv(name))

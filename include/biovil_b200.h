@@ -190,6 +190,12 @@ int32_t bv_conv_chain_nhwc(const void* x, int32_t batch, int32_t height, int32_t
                            const void* x2, int32_t height2, int32_t width2, const bv_conv* host_c2,
                            const void* residual, void* out1, const bv_conv* host_next, void* out2, bv_stream stream);
 
+/* The same chain on CTA pairs (pair_chain.cuh; tcgen05 cta_group::2) for the deep layers' identity blocks:
+ *   out1[B,H,W,N1] = relu(conv1x1(x, c) + c.bias + residual),  out2[B,H,W,N2] = relu(conv1x1(out1, next) + next.bias)
+ * c.cin in {128, 256}, c.cout a multiple of 128, next.cout in {128, 256}; residual is required. */
+int32_t bv_pair_chain_nhwc(const void* x, int32_t batch, int32_t height, int32_t width, const bv_conv* host_c,
+                           const void* residual, void* out1, const bv_conv* host_next, void* out2, bv_stream stream);
+
 /* Fused layer1 Bottleneck tail on CTA pairs (l1_block.cuh), unit-test entry:
  *   t2   = relu(conv3x3(t1, c2) + c2.bias)                       (64 -> 64 channels, stride 1, pad 1; never stored)
  *   out1 = relu(conv1x1(t2, c3) + c3.bias + residual)  [B,H,W,256] bf16

@@ -68,7 +68,7 @@ EXPORTED_SYMBOLS = (
     "bv_conv2d_nhwc", "bv_conv_chain_nhwc", "bv_smooth_heatmaps",
     "bv_resize_workspace_bytes", "bv_resize_center_crop_u8", "bv_pair_gemm_test", "bv_l1_block_nhwc",
     "bv_stem_u8_nhwc", "bv_stem_conv1_u8_nhwc", "bv_forward_graph", "bv_pairwise_cosine", "bv_quantize_frames_f32",
-    "bv_jpeg_info", "bv_jpeg_decode_gray_u8", "bv_l1_block_ds_nhwc",
+    "bv_jpeg_info", "bv_jpeg_decode_gray_u8", "bv_l1_block_ds_nhwc", "bv_pair_chain_nhwc",
 )
 
 _lib = None
@@ -105,11 +105,24 @@ def lib() -> ctypes.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    if not LIB_PATH.exists():
+    path = Path(os.environ.get("BV_LIB_PATH", str(LIB_PATH)))      # A/B of two builds on one box (tools/gpu_ab.sh)
+    if not path.exists():
         raise ImportError(
             f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
             "(the B200 path has no CPU / eager fallback)")
-    l = ctypes.CDLL(str(LIB_PATH))
+    l = ctypes.CDLL(str(path))
+    if "BV_LIB_PATH" in os.environ:
+        # an older build may lack entry points added since: give them a stub so the bindings below still resolve
+        class _Tolerant:
+            def __init__(self, lib):
+                object.__setattr__(self, "_lib", lib)
+
+            def __getattr__(self, name):
+                try:
+                    return getattr(self._lib, name)
+                except AttributeError:
+                    return type("_Missing", (), {"restype": None, "argtypes": None})()
+        l = _Tolerant(l)
     l.bv_last_error.restype = c_char_p
     l.bv_version.restype = c_char_p
     l.bv_workspace_bytes.restype = c_size_t
@@ -147,6 +160,9 @@ def lib() -> ctypes.CDLL:
     l.bv_l1_block_ds_nhwc.restype = c_int32
     l.bv_l1_block_ds_nhwc.argtypes = [c_void_p, c_int32, c_int32, c_int32, POINTER(BvConv), POINTER(BvConv), c_void_p,
                                       POINTER(BvConv), c_void_p, POINTER(BvConv), c_void_p, c_void_p]
+    l.bv_pair_chain_nhwc.restype = c_int32
+    l.bv_pair_chain_nhwc.argtypes = [c_void_p, c_int32, c_int32, c_int32, POINTER(BvConv), c_void_p, c_void_p,
+                                     POINTER(BvConv), c_void_p, c_void_p]
     l.bv_stem_u8_nhwc.restype = c_int32
     l.bv_stem_u8_nhwc.argtypes = [c_void_p, c_int32, c_int32, c_int32, POINTER(BvConv), c_void_p, c_int32, c_void_p]
     l.bv_stem_conv1_u8_nhwc.restype = c_int32

@@ -23,6 +23,7 @@
 #include "conv_gemm.cuh"
 #include "jpeg_stage.h"
 #include "l1_block.cuh"
+#include "pair_chain.cuh"
 #include "pair_gemm.cuh"
 #include "resize.cuh"
 #include "stem_fused.cuh"
@@ -227,13 +228,25 @@ struct L1Launch {
     bool ds;   // first block of the layer: downsample branch as a second K segment instead of an identity tensor
 };
 
-// One step of the forward plan: a single fused convolution, a chained pair, or a fused layer1 block.
+// Chained conv3 + identity -> next conv1 on CTA pairs (pair_chain.cuh): <N2, KB1, STAGES, NSTG> per shape class.
+// (measured, layer3 class: 5 stages + 5 sub-tiles 0.66 ms, 4 + 6 0.61 ms, 3 + 7 0.69 ms per launch - profiles/r2g_*)
+#define BV_FOR_EACH_PAIR_CHAIN(X) X(0, 256, 4, 4, 6) X(1, 256, 2, 6, 6) X(2, 128, 2, 5, 7) X(3, 256, 4, 5, 5) X(4, 256, 4, 3, 7)
+struct PairChainLaunch {
+    bv::PairChainParams p;
+    int cfg;
+    int grid;
+    int n2, k1;
+};
+
+// One step of the forward plan: a single fused convolution, a chained pair, a fused layer1 block, or a pair-chained tail.
 struct PlanStep {
     bool chain = false;
     bool l1 = false;
+    bool pc = false;
     ConvLaunch conv;
     ChainLaunch ch;
     L1Launch l1b;
+    PairChainLaunch pch;
 };
 
 // Per-device state: the dynamic-shared-memory opt-ins (cudaFuncSetAttribute) apply to the device that is current when
@@ -284,6 +297,12 @@ int set_kernel_attributes() {
     BV_CUDA(cudaFuncSetAttribute(bv::stem_rows_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  bv::sr_smem_bytes(true)));
     BV_CUDA(cudaFuncSetAttribute(bv::pair_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bv::kPairSmemBytes));
+#define BV_SET_PC_ATTR(id, N2, KB, ST, NS)                                                          \
+    BV_CUDA(cudaFuncSetAttribute(bv::pair_chain_kernel<N2, KB, ST, NS>,                             \
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize,                       \
+                                 bv::PairChainCfg<N2, KB, ST, NS>::kSmemBytes));
+    BV_FOR_EACH_PAIR_CHAIN(BV_SET_PC_ATTR)
+#undef BV_SET_PC_ATTR
     return BV_OK;
 }
 
@@ -625,7 +644,8 @@ int build_l1_block(L1Launch* L, int B, int H, int W, const void* t1, const bv_co
     p.bias3 = c3.bias;
     p.bias1 = next.bias;
     if ((rc = make_tmap_lines(&p.tmOut1, out1, B * H, W, 256, bv::kTap3Group))) return rc;
-    if ((rc = make_tmap_lines(&p.tmOut2, out2, B * H, W, 64, bv::kTap3Group))) return rc;
+    p.out2 = reinterpret_cast<__nv_bfloat16*>(out2);
+    p.lines = B * H;
     p.Ho = H;
     p.Wo = W;
     p.groups_per_line = W / bv::kTap3Group;
@@ -728,6 +748,69 @@ int launch_chain(const ChainLaunch& L, cudaStream_t st) {
     return BV_OK;
 }
 
+// conv3 (1x1, K1 = 128 / 256) + identity + ReLU chained with the next block's conv1 (1x1, N2 = 128 / 256) on CTA pairs
+int pair_chain_cfg(const bv_conv& c3, const bv_conv& next) {
+    const bool plain3 = c3.r == 1 && c3.s == 1 && c3.stride == 1 && c3.pad == 0;
+    const bool plain1 = next.r == 1 && next.s == 1 && next.stride == 1 && next.pad == 0;
+    if (!plain3 || !plain1 || next.cin != c3.cout || c3.cout % bv::kChainBN1 != 0) return -1;
+    if (next.cout == 256 && c3.cin == 256) return 0;
+    if (next.cout == 256 && c3.cin == 128) return 1;
+    if (next.cout == 128 && c3.cin == 128) return 2;
+    return -1;
+}
+
+int build_pair_chain(PairChainLaunch* L, int B, int H, int W, const void* x, const bv_conv& c3, const void* residual,
+                     void* out1, const bv_conv& next, void* out2) {
+    const int cfg = pair_chain_cfg(c3, next);
+    if (cfg < 0) return fail(BV_ERR_INVALID, "unsupported shapes for the pair-chained kernel (1x1 K=128/256 -> N1 %% 128 == 0 -> 1x1 N2=128/256)");
+    if (!residual) return fail(BV_ERR_INVALID, "the pair-chained kernel needs an identity residual");
+    if (!pair_launchable()) return fail(BV_ERR_INVALID, "this device cannot co-schedule CTA pairs");
+    memset(&L->p, 0, sizeof(L->p));
+    bv::PairChainParams& p = L->p;
+    const long long M = (long long)B * H * W;
+    if (M <= 0 || M > 0x7fffffffLL - 256) return fail(BV_ERR_INVALID, "M=%lld out of range", M);
+    const int N1 = c3.cout, N2 = next.cout, K1 = c3.cin;
+    int rc;
+    if ((rc = make_tmap_2d(&p.tmA, x, (uint64_t)K1, (uint64_t)M, bv::kBlockK, bv::kBlockM))) return rc;
+    if ((rc = make_tmap_2d(&p.tmB1, c3.w, (uint64_t)K1, (uint64_t)N1, bv::kBlockK, 64))) return rc;
+    if ((rc = make_tmap_2d(&p.tmB2, next.w, (uint64_t)N1, (uint64_t)N2, bv::kBlockK, (uint32_t)(N2 / 2)))) return rc;
+    if ((rc = make_tmap_2d(&p.tmRes, residual, (uint64_t)N1, (uint64_t)M, bv::kChunkCols, bv::kBlockM))) return rc;
+    if ((rc = make_tmap_2d(&p.tmOut1, out1, (uint64_t)N1, (uint64_t)M, bv::kChunkCols, bv::kBlockM))) return rc;
+    p.bias1 = c3.bias;
+    p.bias2 = next.bias;
+    p.out2 = reinterpret_cast<__nv_bfloat16*>(out2);
+    p.M = (int)M;
+    p.N1 = N1;
+    p.num_m_blocks = (int)((M + bv::kBlockM - 1) / bv::kBlockM);
+    p.num_pair_tiles = (p.num_m_blocks + 1) / 2;
+    L->cfg = cfg;
+    if (cfg == 0) {   // experiment: ring / staging split of the layer3 class
+        static const int v = getenv("BV_PC_VARIANT") ? atoi(getenv("BV_PC_VARIANT")) : 0;
+        if (v == 1) L->cfg = 3;
+        if (v == 2) L->cfg = 4;
+    }
+    L->n2 = N2;
+    L->k1 = K1;
+    L->grid = 2 * std::min(p.num_pair_tiles, g_num_sms / 2);
+    return BV_OK;
+}
+
+int launch_pair_chain(const PairChainLaunch& L, cudaStream_t st) {
+    switch (L.cfg) {
+#define BV_LAUNCH_PC(id, N2, KB, ST, NS)                                                                   \
+    case id:                                                                                               \
+        launch_ex(bv::pair_chain_kernel<N2, KB, ST, NS>, L.grid, bv::kPcThreads,                           \
+                  bv::PairChainCfg<N2, KB, ST, NS>::kSmemBytes, st, 2, L.p);                               \
+        break;
+        BV_FOR_EACH_PAIR_CHAIN(BV_LAUNCH_PC)
+#undef BV_LAUNCH_PC
+        default:
+            return fail(BV_ERR_INVALID, "unknown pair-chain configuration %d", L.cfg);
+    }
+    BV_CUDA(cudaGetLastError());
+    return BV_OK;
+}
+
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 // Activation buffers inside the caller's workspace.
@@ -736,6 +819,14 @@ struct Layout {
 };
 
 const int kLayerBlocks[4] = {3, 4, 6, 3};
+// Shape classes of the pair-chained kernel that are on by default: NONE.  Measured (profiles/r2f_*, r2g_*): layer3
+// 0.61-0.66 ms per block against 0.415 + 0.212 ms for the pair conv3 + identity kernel followed by the pair conv1 kernel;
+// layer2 1.17 ms against 1.01 ms for the single-CTA chain; layer2 -> layer3 1.42 ms against 0.79 + 0.47 ms.  The kernel
+// removes the HBM re-read of the block output and 60 % of the L2 -> SM operand stream, but every staging sub-tile is held
+// from the identity prefetch until both the TMA store and the second GEMM have read it, and 5-6 sub-tiles (all that fits
+// next to the resident 64 KB input tile) do not cover that span.  Kept (bit-exact, tests/test_chain_gpu.py) behind
+// BV_PAIR_CHAIN for the next attempt.
+const int kPairChainDefault = 0;
 const int kLayerWidth[4] = {64, 128, 256, 512};
 
 Layout make_layout(int B, int C, int H, int W) {
@@ -859,13 +950,23 @@ void l1_cost(const L1Launch& L, double* flops, double* bytes, char* name, size_t
     snprintf(name, n, "l1_block<64> M=%.0f 3x3(64)+1x1(256)+%s+1x1(64)", Mr, L.ds ? "ds" : "res");
 }
 
+void pair_chain_cost(const PairChainLaunch& L, double* flops, double* bytes, char* name, size_t n) {
+    const bv::PairChainParams& p = L.p;
+    *flops = 2.0 * p.M * p.N1 * L.k1 + 2.0 * p.M * L.n2 * p.N1;
+    *bytes = (double)p.M * L.k1 * 2 + (double)p.M * p.N1 * 2 * 2 + (double)p.M * L.n2 * 2 +
+             ((double)L.k1 * p.N1 + (double)p.N1 * L.n2) * 2;
+    snprintf(name, n, "pair_chain<%d> M=%d N1=%d K1=%d +res", L.n2, p.M, p.N1, L.k1);
+}
+
 void step_cost(const PlanStep& s, double* flops, double* bytes, char* name, size_t n) {
-    if (s.l1) l1_cost(s.l1b, flops, bytes, name, n);
+    if (s.pc) pair_chain_cost(s.pch, flops, bytes, name, n);
+    else if (s.l1) l1_cost(s.l1b, flops, bytes, name, n);
     else if (s.chain) chain_cost(s.ch, flops, bytes, name, n);
     else conv_cost(s.conv, flops, bytes, name, n);
 }
 
 int launch_step(const PlanStep& s, cudaStream_t st) {
+    if (s.pc) return launch_pair_chain(s.pch, st);
     if (s.l1) return launch_l1_block(s.l1b, st);
     return s.chain ? launch_chain(s.ch, st) : launch_conv(s.conv, st);
 }
@@ -1089,6 +1190,24 @@ static int build_plan(bv_handle* h, const void* frames, int dtype, int B, int C,
                 }
             }
             t1_ready = false;
+            // Deep-layer identity blocks: conv3 + identity chained with the next conv1 on CTA pairs (pair_chain.cuh).
+            // BV_PAIR_CHAIN selects the shape classes (bit 0: K1 = 256 -> N2 = 256 [layer3], bit 1: K1 = 128 -> N2 = 256
+            // [layer2 -> layer3], bit 2: K1 = 128 -> N2 = 128 [layer2]).
+            {
+                static const int pc_mask = getenv("BV_PAIR_CHAIN") ? atoi(getenv("BV_PAIR_CHAIN")) : kPairChainDefault;
+                const int pcc = (n3 == 1 && res != nullptr && blk + 1 < BV_NUM_BLOCKS) ? pair_chain_cfg(c3, h->w.conv1[blk + 1]) : -1;
+                if (pcc >= 0 && ((pc_mask >> pcc) & 1) && pair_launchable()) {
+                    PlanStep s;
+                    s.pc = true;
+                    if ((rc = build_pair_chain(&s.pch, B, oh, ow, t2, c3, res, nxt, h->w.conv1[blk + 1], t1))) return rc;
+                    h->steps.push_back(s);
+                    t1_ready = true;
+                    std::swap(cur, nxt);
+                    ch = oh;
+                    cw = ow;
+                    continue;
+                }
+            }
             // Measured losses stay unchained: the strided-downsample tail of layer2.0 (six A k-blocks re-streamed per
             // chunk) and the 256-wide second GEMM into layer3 (its staging leaves too little residual prefetch depth).
             const bool chain_l3 = env_flag("BV_CHAIN_L3") && c3.cout == 1024 && n3 == 1;
@@ -1686,6 +1805,16 @@ int32_t bv_l1_block_nhwc(const void* t1, int32_t B, int32_t H, int32_t W, const 
     L1Launch L;
     if ((rc = build_l1_block(&L, B, H, W, t1, *c2, *c3, residual, out1, *next, out2))) return rc;
     return launch_l1_block(L, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int32_t bv_pair_chain_nhwc(const void* x, int32_t B, int32_t H, int32_t W, const bv_conv* c, const void* residual, void* out1,
+                           const bv_conv* next, void* out2, bv_stream stream) {
+    if (!x || !c || !residual || !out1 || !next || !out2) return fail(BV_ERR_INVALID, "null argument");
+    int rc = device_setup();
+    if (rc) return rc;
+    PairChainLaunch L;
+    if ((rc = build_pair_chain(&L, B, H, W, x, *c, residual, out1, *next, out2))) return rc;
+    return launch_pair_chain(L, reinterpret_cast<cudaStream_t>(stream));
 }
 
 int32_t bv_l1_block_ds_nhwc(const void* t1, int32_t B, int32_t H, int32_t W, const bv_conv* c2, const bv_conv* c3,

@@ -25,7 +25,7 @@
 //                         G1(t)      <- t2_ready(t)        E1(t):   D1 + bias + identity (in place in stg1), ReLU;
 //                         G0(t+1)                                   the y sub-tiles feed G2 and the TMA stores
 //                         G2(t)      <- sub_written[j]     E0(t+1): D0 -> taps combined, bias, ReLU -> t2 tile (smem)
-//                                                          E2(t) (own warps): D2 + bias, ReLU -> stg2 -> TMA stores
+//                                                          E2(t) (own warps): D2 + bias, ReLU -> t1' rows stored directly (128 B per thread)
 // Warp roles (768 threads): 0 TMA producer (weights once, A ring), 1 MMA issuer (leader CTA) / idle (peer),
 // 2..17 epilogue of G0/G1, 20..23 epilogue of G2 (its long wait for the second GEMM must not stall the others),
 // 18 loader (residual prefetch into the stg1 sub-tiles as they drain), 19 storer (y and t1' leave
@@ -62,20 +62,19 @@ constexpr int kL1OffW1 = kL1OffW3 + 128 * 128;             // 4 k-blocks x [N2/2
 template <int N2, bool DS = false>
 struct L1Cfg {
     static_assert(N2 == 64, "second-GEMM width supported by the TMEM plan (D1 256 + D0 192 + D2 64 columns)");
-    static constexpr int kYBufs = DS ? 3 : 5;
+    static constexpr int kYBufs = DS ? 4 : 6;   // (t1' leaves through direct stores: its 16 KB staging tile became a y buffer)
     static constexpr int kW1Bytes = 4 * (N2 / 2) * 128;
     static constexpr int kWdBytes = DS ? 128 * 128 : 0;          // this CTA's half of the downsample weights [128 rows x 128 B]
     static constexpr int kOffWd = kL1OffW1 + kW1Bytes;
     static constexpr int kOffX0 = kOffWd + kWdBytes;             // DS: x0 A tile [128 rows x 128 B]
     static constexpr int kOffT2 = kOffX0 + (DS ? kABytes : 0);
     static constexpr int kOffStg1 = kOffT2 + kABytes;            // kYBufs sub-tiles x 16 KB
-    static constexpr int kOffStg2 = kOffStg1 + kYBufs * kStagingBytes;
-    static constexpr int kOffBars = kOffStg2 + (N2 / 64) * kStagingBytes;
+    static constexpr int kOffBars = kOffStg1 + kYBufs * kStagingBytes;
     static constexpr int kNumBars = 2 * kL1Stages + 1 + 8 + 24 + kYBufs + 2 + 2;
     static constexpr int kOffBias = (kOffBars + kNumBars * 8 + 16 + 15) / 16 * 16;               // fp32: bias3[256] | bias2[64] | bias1[N2]
     static constexpr int kSmemBytes = kOffBias + (256 + 64 + N2) * 4;
     static constexpr uint32_t kWeightBytes = 3 * 96 * 128 + 128 * 128 + kW1Bytes + kWdBytes;
-    static_assert(kOffWd % 1024 == 0 && kOffX0 % 1024 == 0 && kOffT2 % 1024 == 0 && kOffStg1 % 1024 == 0 && kOffStg2 % 1024 == 0,
+    static_assert(kOffWd % 1024 == 0 && kOffX0 % 1024 == 0 && kOffT2 % 1024 == 0 && kOffStg1 % 1024 == 0,
                   "operand tiles need 1024-byte alignment");
     static_assert(kSmemBytes <= 232448, "exceeds the 227 KB of shared memory a CTA may use");
 };
@@ -90,7 +89,8 @@ struct L1BlockParams {
     CUtensorMap tmWd;   // DS: downsample weights [256, 64], box 64 x 128
     const float* bias_ds;   // DS: added to bias3
     CUtensorMap tmOut1; // y   as (256, W, B*H), tiled, box 64 channels x 30 pixels x 1 line
-    CUtensorMap tmOut2; // t1' as (N2,  W, B*H), tiled, box 64 channels x 30 pixels x 1 line
+    __nv_bfloat16* out2; // t1' [B*H][W][N2]: written with direct 128-byte-per-thread stores by the second-GEMM epilogue
+    int lines;           // B * H
     const float* bias2;
     const float* bias3;
     const float* bias1;
@@ -225,7 +225,6 @@ __global__ void __launch_bounds__(kL1Threads, 1) l1_block_kernel(const __grid_co
     uint8_t* x0_tile = smem + Cfg::kOffX0;      // DS only
     uint8_t* t2_tile = smem + Cfg::kOffT2;
     uint8_t* stg1 = smem + Cfg::kOffStg1;
-    uint8_t* stg2 = smem + Cfg::kOffStg2;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kOffBars);
     uint64_t* full_bar = bars;                    // [3] leader: A stage loaded in BOTH CTAs
     uint64_t* empty_bar = bars + kL1Stages;       // [3] per CTA: stage consumed (multicast commit)
@@ -275,7 +274,6 @@ __global__ void __launch_bounds__(kL1Threads, 1) l1_block_kernel(const __grid_co
         tma_prefetch_desc(&p.tmW3);
         tma_prefetch_desc(&p.tmW1);
         tma_prefetch_desc(&p.tmOut1);
-        tma_prefetch_desc(&p.tmOut2);
         for (int i = 0; i < kL1Stages; ++i) {
             mbar_init(&full_bar[i], 1);
             mbar_init(&empty_bar[i], 1);
@@ -571,12 +569,6 @@ __global__ void __launch_bounds__(kL1Threads, 1) l1_block_kernel(const __grid_co
                 }
                 tma_store_wait_read<0>();
                 mbar_arrive(&sd[3]);
-                mbar_wait(e2_local, t & 1u);
-#pragma unroll
-                for (int g = 0; g < 4; ++g) tma_store_3d(&p.tmOut2, stg2 + g * 4096, 0, gq[g], gl[g]);
-                tma_store_commit();
-                tma_store_wait_read<0>();
-                mbar_arrive(stg2_free);
             }
             tma_store_wait_all<0>();
         }
@@ -608,15 +600,17 @@ __global__ void __launch_bounds__(kL1Threads, 1) l1_block_kernel(const __grid_co
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_leader(d2_empty);
-            mbar_wait(stg2_free, (t & 1u) ^ 1u);   // the previous tile's t1' stores have read the staging tile
-            uint8_t* rp = stg2 + l * 128;
+            // this thread's row = pixel gq[quarter] + lane of line gl[quarter]; lanes 30, 31 hold the overlap rows of the lane
+            // quarter and the last tile may reach past the last line: neither is stored.  64 channels = one 128-byte line.
+            int gl[4], gq[4];
+            group_coords(tile_of(t), gl, gq);
+            if (lane < kTap3Group && gl[quarter] < p.lines) {
+                uint4* op = reinterpret_cast<uint4*>(p.out2 + (static_cast<size_t>(gl[quarter]) * p.Wo + gq[quarter] + lane) * N2);
 #pragma unroll
-            for (int ch = 0; ch < N2 / 8; ++ch)
-                *reinterpret_cast<uint4*>(rp + ((ch ^ (l & 7)) << 4)) = make_uint4(w[4 * ch], w[4 * ch + 1], w[4 * ch + 2], w[4 * ch + 3]);
-            fence_proxy_async_smem();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(e2_local);
+                for (int ch = 0; ch < N2 / 8; ++ch) op[ch] = make_uint4(w[4 * ch], w[4 * ch + 1], w[4 * ch + 2], w[4 * ch + 3]);
+            }
         }
+        (void)l;
     } else if (warp >= 2 && warp < 18) {
         // ===================== epilogue warps of the first two GEMMs =====================
         const int quarter = warp & 3;

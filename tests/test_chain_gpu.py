@@ -109,3 +109,72 @@ def test_chain_rejects_unsupported_shapes(env):
     rc = lib.bv_conv_chain_nhwc(N.ptr(t2), 1, 8, 8, ctypes.byref(c3[0]), None, 0, 0, None, None, N.ptr(out1),
                                 ctypes.byref(bad[0]), N.ptr(out2), N.current_stream_handle(dev))
     assert rc == N.BV_ERR_INVALID
+
+
+PAIR_CHAIN_CASES = [
+    # name,             B,  H, mid,   N1,  N2
+    ("l3_res",          3, 30, 256, 1024, 256),     # 2700 rows = 22 m-blocks = 11 pair tiles
+    ("l3_odd_blocks",   1, 15, 256, 1024, 256),     # 225 rows = 2 blocks, the second mostly empty
+    ("l3_one_block",    1,  8, 256, 1024, 256),     # 64 rows: the peer CTA's whole tile is out of bounds
+    ("l3_three_blocks", 1, 19, 256, 1024, 256),     # 361 rows = 3 blocks: the last pair has an out-of-bounds peer tile
+    ("l3_persistent",  24, 30, 256, 1024, 256),     # 21600 rows = 169 blocks = 85 pair tiles > 74 pairs: every ring wraps
+    ("l2_to_l3",        2, 30, 128,  512, 256),
+    ("l2_res",          3, 30, 128,  512, 128),
+    ("l2_persistent",  12, 60, 128,  512, 128),     # 43200 rows = 338 blocks = 169 pair tiles
+]
+
+
+@pytest.mark.parametrize("case", PAIR_CHAIN_CASES, ids=[c[0] for c in PAIR_CHAIN_CASES])
+@pytest.mark.parametrize("integer", [True, False], ids=["int", "gauss"])
+def test_pair_chain(env, case, integer):
+    """conv3 + identity + ReLU chained with the next conv1 + ReLU on CTA pairs (csrc/pair_chain.cuh) through
+    ``bv_pair_chain_nhwc``: resident conv3 input tile, half of every weight stage per CTA, y sub-tiles feed both the TMA
+    store and the second GEMM.  Integer operands -> bit-exact against fp32 ``F.conv2d``."""
+    N, lib, packing = env
+    name, B, H, mid, n1, n2 = case
+    gen = torch.Generator().manual_seed(211 + len(name) + B * H)
+    dev = torch.device("cuda:0")
+    t2 = _rand(gen, (B, H, H, mid), integer, 0, 3).to(torch.bfloat16).to(dev)
+    if integer:   # sparse ternary weights keep |y| small enough that y and every partial sum are exact bf16 / fp32 integers
+        w3 = _rand(gen, (n1, mid, 1, 1), True, -1, 2) * (torch.rand(n1, mid, 1, 1, generator=gen) < 0.1)
+        w1 = _rand(gen, (n2, n1, 1, 1), True, -1, 2) * (torch.rand(n2, n1, 1, 1, generator=gen) < 0.05)
+    else:
+        w3 = _rand(gen, (n1, mid, 1, 1), False, scale=mid ** -0.5)
+        w1 = _rand(gen, (n2, n1, 1, 1), False, scale=n1 ** -0.5)
+    w3, w1 = w3.to(torch.bfloat16), w1.to(torch.bfloat16)
+    b3, b1 = _rand(gen, (n1,), integer), _rand(gen, (n2,), integer)
+    res = _rand(gen, (B, H, H, n1), integer).to(torch.bfloat16).to(dev)
+    c3 = packing.pack_single_conv(w3, b3, 1, 0, dev)
+    c1 = packing.pack_single_conv(w1, b1, 1, 0, dev)
+    ref1 = torch.relu(_ref(t2, w3.to(dev), b3.to(dev), 1, 0) + res.float())
+    if integer:
+        assert ref1.abs().max() <= 256, "test data must stay exact in bf16"
+    ref1 = ref1.to(torch.bfloat16)
+    ref2 = torch.relu(_ref(ref1, w1.to(dev), b1.to(dev), 1, 0)).to(torch.bfloat16)
+    out1 = torch.full((B, H, H, n1), float("nan"), device=dev, dtype=torch.bfloat16)
+    out2 = torch.full((B, H, H, n2), float("nan"), device=dev, dtype=torch.bfloat16)
+    N.check(lib.bv_pair_chain_nhwc(N.ptr(t2), B, H, H, ctypes.byref(c3[0]), N.ptr(res), N.ptr(out1), ctypes.byref(c1[0]),
+                                   N.ptr(out2), N.current_stream_handle(dev)))
+    torch.cuda.synchronize()
+    assert not torch.isnan(out1.float()).any() and not torch.isnan(out2.float()).any(), "unwritten output rows"
+    if integer:
+        assert torch.equal(out1, ref1), f"out1 max abs diff {(out1.float() - ref1.float()).abs().max().item()}"
+        assert torch.equal(out2, ref2), f"out2 max abs diff {(out2.float() - ref2.float()).abs().max().item()}"
+    else:
+        torch.testing.assert_close(out1.float(), ref1.float(), rtol=1e-2, atol=1e-2)
+        ref2k = torch.relu(_ref(out1, w1.to(dev), b1.to(dev), 1, 0)).to(torch.bfloat16)
+        torch.testing.assert_close(out2.float(), ref2k.float(), rtol=1e-2, atol=1e-2)
+        torch.testing.assert_close(out2.float(), ref2.float(), rtol=3e-2, atol=3e-2)
+
+
+def test_pair_chain_rejects_unsupported_shapes(env):
+    N, lib, packing = env
+    dev = torch.device("cuda:0")
+    z = lambda *s: torch.zeros(*s, dtype=torch.bfloat16)  # noqa: E731
+    t2, res = z(1, 8, 8, 64).to(dev), z(1, 8, 8, 256).to(dev)
+    c3 = packing.pack_single_conv(z(256, 64, 1, 1), torch.zeros(256), 1, 0, dev)      # K1 = 64: layer1 shape, not supported
+    c1 = packing.pack_single_conv(z(64, 256, 1, 1), torch.zeros(64), 1, 0, dev)
+    out1, out2 = z(1, 8, 8, 256).to(dev), z(1, 8, 8, 64).to(dev)
+    rc = lib.bv_pair_chain_nhwc(N.ptr(t2), 1, 8, 8, ctypes.byref(c3[0]), N.ptr(res), N.ptr(out1), ctypes.byref(c1[0]),
+                                N.ptr(out2), N.current_stream_handle(dev))
+    assert rc == N.BV_ERR_INVALID

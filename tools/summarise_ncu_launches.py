@@ -20,7 +20,7 @@ k = OrderedDict()
 for r in rows:
     e = k.setdefault(r["ID"], {"name": r["Kernel Name"]})
     e[r["Metric Name"]] = float(r["Metric Value"].replace(",", "")) * scale[r["Metric Unit"]]
-conv = [e for e in k.values() if any(t in e["name"] for t in ("conv_gemm", "chain_gemm", "conv3x3_tap3", "l1_block", "stem_rows", "stem_fused"))]
+conv = [e for e in k.values() if any(t in e["name"] for t in ("conv_gemm", "chain_gemm", "pair_chain", "conv3x3_tap3", "l1_block", "stem_rows", "stem_fused"))]
 tot = lambda es, m: sum(e[m] for e in es)  # noqa: E731
 out = {
     "source": os.path.relpath(dst, os.path.dirname(os.path.dirname(os.path.abspath(__file__)))),
