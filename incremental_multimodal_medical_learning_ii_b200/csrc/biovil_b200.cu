@@ -221,11 +221,16 @@ struct ChainLaunch {
     int k1;  // total K of the first GEMM (for cost accounting)
 };
 
+const int kL1ShiftedDefault = 0;   // shifted-tap 3x3 GEMM in the 64-wide forms of the layer1 block kernel (BV_L1_SH)
+const int kL1LastBlockDefault = 0; // the layer's last block (128-wide successor) on the block kernel (BV_L1_LAST)
+
 // Fused layer1 block on CTA pairs (l1_block.cuh): conv2 3x3 + conv3 + identity + next conv1.
 struct L1Launch {
     bv::L1BlockParams p;
     int grid;
     bool ds;   // first block of the layer: downsample branch as a second K segment instead of an identity tensor
+    bool sh;   // shifted-tap form of the 3x3 GEMM (nine N = 64 MMAs into a double-buffered 64-column accumulator)
+    int n2;    // width of the chained next conv1: 64, or 128 (the layer's last block; shifted taps only)
 };
 
 // Chained conv3 + identity -> next conv1 on CTA pairs (pair_chain.cuh): <N2, KB1, STAGES, NSTG> per shape class.
@@ -285,6 +290,12 @@ int set_kernel_attributes() {
                                  bv::L1Cfg<64>::kSmemBytes));
     BV_CUDA(cudaFuncSetAttribute(bv::l1_block_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  bv::L1Cfg<64, true>::kSmemBytes));
+    BV_CUDA(cudaFuncSetAttribute(bv::l1_block_kernel<64, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 bv::L1Cfg<64, false, true>::kSmemBytes));
+    BV_CUDA(cudaFuncSetAttribute(bv::l1_block_kernel<64, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 bv::L1Cfg<64, true, true>::kSmemBytes));
+    BV_CUDA(cudaFuncSetAttribute(bv::l1_block_kernel<128, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 bv::L1Cfg<128, false, true>::kSmemBytes));
     BV_CUDA(cudaFuncSetAttribute(bv::head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
     BV_CUDA(cudaFuncSetAttribute(bv::stem_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  bv::kStemSmemRequest));
@@ -606,7 +617,7 @@ int build_chain(ChainLaunch* L, int B, const ConvOperand* ops, int nops, const v
 bool l1_block_supported(const bv_conv& c2, const bv_conv& c3, const bv_conv& next, int W) {
     return W % bv::kTap3Group == 0 && c2.r == 3 && c2.s == 3 && c2.stride == 1 && c2.pad == 1 && c2.cin == 64 && c2.cout == 64 && c3.r == 1 &&
            c3.s == 1 && c3.stride == 1 && c3.pad == 0 && c3.cin == 64 && c3.cout == 256 && next.r == 1 && next.s == 1 &&
-           next.stride == 1 && next.pad == 0 && next.cin == 256 && next.cout == 64;
+           next.stride == 1 && next.pad == 0 && next.cin == 256 && (next.cout == 64 || next.cout == 128);
 }
 
 bool l1_ds_supported(const bv_conv& ds) {
@@ -621,6 +632,7 @@ int build_l1_block(L1Launch* L, int B, int H, int W, const void* t1, const bv_co
     if (!l1_block_supported(c2, c3, next, W))
         return fail(BV_ERR_INVALID, "unsupported shapes for the fused layer1 block (64->64 3x3, 64->256, 256->64, width %% 30 == 0)");
     const bool use_ds = x0 != nullptr && ds != nullptr;
+    if (next.cout == 128 && use_ds) return fail(BV_ERR_INVALID, "the 128-wide successor form takes an identity residual");
     if (use_ds && (residual || !l1_ds_supported(*ds)))
         return fail(BV_ERR_INVALID, "the downsample form of the fused layer1 block takes a 64 -> 256 1x1 stride-1 branch and no residual");
     if (!use_ds && !residual) return fail(BV_ERR_INVALID, "the fused layer1 block needs an identity residual or a downsample branch");
@@ -639,11 +651,15 @@ int build_l1_block(L1Launch* L, int B, int H, int W, const void* t1, const bv_co
     }
     if ((rc = make_tmap_2d(&p.tmW2, c2.w, 576, 64, bv::kBlockK, 32))) return rc;
     if ((rc = make_tmap_2d(&p.tmW3, c3.w, 64, 256, bv::kBlockK, 128))) return rc;
-    if ((rc = make_tmap_2d(&p.tmW1, next.w, 256, 64, bv::kBlockK, 32))) return rc;
+    if ((rc = make_tmap_2d(&p.tmW1, next.w, 256, (uint64_t)next.cout, bv::kBlockK, (uint32_t)(next.cout / 2)))) return rc;
     p.bias2 = c2.bias;
     p.bias3 = c3.bias;
     p.bias1 = next.bias;
     if ((rc = make_tmap_lines(&p.tmOut1, out1, B * H, W, 256, bv::kTap3Group))) return rc;
+    // shifted-tap 3x3 GEMM: required by the 128-wide successor; for the 64-wide forms an A/B switch (BV_L1_SH, default on/off below)
+    const int sh_mode = getenv("BV_L1_SH") ? atoi(getenv("BV_L1_SH")) : kL1ShiftedDefault;
+    L->n2 = next.cout;
+    L->sh = next.cout == 128 || sh_mode != 0;
     p.out2 = reinterpret_cast<__nv_bfloat16*>(out2);
     p.lines = B * H;
     p.Ho = H;
@@ -691,8 +707,16 @@ int launch_l1_block(const L1Launch& L, cudaStream_t st) {
         cudaMemsetAsync(g_dbg, 0, 4 * 8 * 1024, st);
         prm.dbg = g_dbg;
     }
-    if (L.ds) BV_CUDA(launch_ex(bv::l1_block_kernel<64, true>, L.grid, bv::kL1Threads, bv::L1Cfg<64, true>::kSmemBytes, st, 2, prm));
-    else BV_CUDA(launch_ex(bv::l1_block_kernel<64>, L.grid, bv::kL1Threads, bv::L1Cfg<64>::kSmemBytes, st, 2, prm));
+    if (L.n2 == 128)
+        BV_CUDA(launch_ex(bv::l1_block_kernel<128, false, true>, L.grid, bv::kL1Threads, bv::L1Cfg<128, false, true>::kSmemBytes, st, 2, prm));
+    else if (L.ds && L.sh)
+        BV_CUDA(launch_ex(bv::l1_block_kernel<64, true, true>, L.grid, bv::kL1Threads, bv::L1Cfg<64, true, true>::kSmemBytes, st, 2, prm));
+    else if (L.ds)
+        BV_CUDA(launch_ex(bv::l1_block_kernel<64, true>, L.grid, bv::kL1Threads, bv::L1Cfg<64, true>::kSmemBytes, st, 2, prm));
+    else if (L.sh)
+        BV_CUDA(launch_ex(bv::l1_block_kernel<64, false, true>, L.grid, bv::kL1Threads, bv::L1Cfg<64, false, true>::kSmemBytes, st, 2, prm));
+    else
+        BV_CUDA(launch_ex(bv::l1_block_kernel<64>, L.grid, bv::kL1Threads, bv::L1Cfg<64>::kSmemBytes, st, 2, prm));
     if (prm.dbg) {
         static long long host[8 * 128];
         const int pairs = L.grid / 2;
@@ -827,6 +851,7 @@ const int kLayerBlocks[4] = {3, 4, 6, 3};
 // next to the resident 64 KB input tile) do not cover that span.  Kept (bit-exact, tests/test_chain_gpu.py) behind
 // BV_PAIR_CHAIN for the next attempt.
 const int kPairChainDefault = 0;
+
 const int kLayerWidth[4] = {64, 128, 256, 512};
 
 Layout make_layout(int B, int C, int H, int W) {
@@ -944,10 +969,10 @@ void chain_cost(const ChainLaunch& L, double* flops, double* bytes, char* name, 
 
 void l1_cost(const L1Launch& L, double* flops, double* bytes, char* name, size_t n) {
     const double Mr = (double)L.p.num_groups * bv::kTap3Group;   // output pixels
-    *flops = 2.0 * Mr * 64 * 576 + 2.0 * Mr * 256 * 64 * (L.ds ? 2 : 1) + 2.0 * Mr * 64 * 256;
-    *bytes = Mr * 64 * 2 + (L.ds ? Mr * 64 * 2 + Mr * 256 * 2 : Mr * 256 * 2 * 2) + Mr * 64 * 2 +
-             (576.0 * 64 + 64 * 256 * (L.ds ? 2 : 1) + 256 * 64) * 2;
-    snprintf(name, n, "l1_block<64> M=%.0f 3x3(64)+1x1(256)+%s+1x1(64)", Mr, L.ds ? "ds" : "res");
+    *flops = 2.0 * Mr * 64 * 576 + 2.0 * Mr * 256 * 64 * (L.ds ? 2 : 1) + 2.0 * Mr * L.n2 * 256;
+    *bytes = Mr * 64 * 2 + (L.ds ? Mr * 64 * 2 + Mr * 256 * 2 : Mr * 256 * 2 * 2) + Mr * L.n2 * 2 +
+             (576.0 * 64 + 64 * 256 * (L.ds ? 2 : 1) + 256.0 * L.n2) * 2;
+    snprintf(name, n, "l1_block<%d%s> M=%.0f 3x3(64)+1x1(256)+%s+1x1(%d)", L.n2, L.sh ? "/sh" : "", Mr, L.ds ? "ds" : "res", L.n2);
 }
 
 void pair_chain_cost(const PairChainLaunch& L, double* flops, double* bytes, char* name, size_t n) {
@@ -1159,8 +1184,10 @@ static int build_plan(bv_handle* h, const void* frames, int dtype, int B, int C,
             // layer1 blocks with an identity residual whose successor's conv1 is 64 wide: the whole tail of the block
             // (conv2 3x3, conv3 + identity, next conv1) is one CTA-pair kernel
             const bool l1_ds = ds.w != nullptr && l1_ds_supported(ds) && !env_flag("BV_NO_L1_DS");
+            const int l1_last = getenv("BV_L1_LAST") ? atoi(getenv("BV_L1_LAST")) : kL1LastBlockDefault;
+            const bool l1_wide_next = blk + 1 < BV_NUM_BLOCKS && h->w.conv1[blk + 1].cout == 128;
             if (!env_flag("BV_NO_L1_FUSED") && l1_block_launchable() && (ds.w == nullptr || l1_ds) && blk + 1 < BV_NUM_BLOCKS &&
-                l1_block_supported(c2, c3, h->w.conv1[blk + 1], cw)) {
+                (!l1_wide_next || (l1_last && ds.w == nullptr)) && l1_block_supported(c2, c3, h->w.conv1[blk + 1], cw)) {
                 PlanStep s;
                 s.l1 = true;
                 if (l1_ds) rc = build_l1_block(&s.l1b, B, ch, cw, t1, c2, c3, nullptr, nxt, h->w.conv1[blk + 1], t2, cur, &ds);

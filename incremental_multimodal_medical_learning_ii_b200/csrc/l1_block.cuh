@@ -59,10 +59,19 @@ constexpr int kL1OffW2 = kL1OffA + kL1Stages * kABytes;    // 3 filter rows x [9
 constexpr int kL1OffW3 = kL1OffW2 + 3 * 96 * 128;          // [128 rows x 128 B]
 constexpr int kL1OffW1 = kL1OffW3 + 128 * 128;             // 4 k-blocks x [N2/2 rows x 128 B]
 
-template <int N2, bool DS = false>
+// SH = "shifted taps": the 3x3 GEMM is nine N = 64 MMAs per K step group - the three horizontal taps of a filter row read the
+// SAME A stage through descriptors whose start is shifted by 0 / 1 / 2 pixel rows (128 B each; the 128B swizzle follows
+// absolute address bits, exactly as kSegWide does in conv_gemm.cuh) and accumulate into ONE 64-column tile.  Against the
+// tap-fused N = 192 form: 2.1x the tensor time of G0 (36 x 68 instead of 12 x 96 cycles per tile), but the accumulator
+// shrinks from 192 to 64 TMEM columns - which lets it be double-buffered AND leaves room for a 128-wide second GEMM
+// (D1 256 + D0 2 x 64 + D2 128 = 512 columns: the layer's LAST block, whose successor conv1 is layer2's) - and the first
+// epilogue loses its 32 shuffles and two of its three TMEM loads per thread and tile (the LSU data pipe is 74-79 % busy
+// in the N = 192 form, ncu).  Rows 30, 31 of every lane quarter read their taps from the next quarter's pixels (or past
+// the stage): garbage in rows that were overlap rows anyway and are never stored.
+template <int N2, bool DS = false, bool SH = false>
 struct L1Cfg {
-    static_assert(N2 == 64, "second-GEMM width supported by the TMEM plan (D1 256 + D0 192 + D2 64 columns)");
-    static constexpr int kYBufs = DS ? 4 : 6;   // (t1' leaves through direct stores: its 16 KB staging tile became a y buffer)
+    static_assert(N2 == 64 || (N2 == 128 && SH && !DS), "TMEM plan: D1 256 + D0 192 + D2 64, or (shifted taps) D1 256 + D0 2 x 64 + D2 <= 128");
+    static constexpr int kYBufs = DS ? 4 : (N2 == 64 ? 6 : 5);   // (t1' leaves through direct stores: no staging tile for it)
     static constexpr int kW1Bytes = 4 * (N2 / 2) * 128;
     static constexpr int kWdBytes = DS ? 128 * 128 : 0;          // this CTA's half of the downsample weights [128 rows x 128 B]
     static constexpr int kOffWd = kL1OffW1 + kW1Bytes;
@@ -70,7 +79,7 @@ struct L1Cfg {
     static constexpr int kOffT2 = kOffX0 + (DS ? kABytes : 0);
     static constexpr int kOffStg1 = kOffT2 + kABytes;            // kYBufs sub-tiles x 16 KB
     static constexpr int kOffBars = kOffStg1 + kYBufs * kStagingBytes;
-    static constexpr int kNumBars = 2 * kL1Stages + 1 + 8 + 24 + kYBufs + 2 + 2;
+    static constexpr int kNumBars = 2 * kL1Stages + 1 + 8 + 24 + kYBufs + 2 + 2 + 4;
     static constexpr int kOffBias = (kOffBars + kNumBars * 8 + 16 + 15) / 16 * 16;               // fp32: bias3[256] | bias2[64] | bias1[N2]
     static constexpr int kSmemBytes = kOffBias + (256 + 64 + N2) * 4;
     static constexpr uint32_t kWeightBytes = 3 * 96 * 128 + 128 * 128 + kW1Bytes + kWdBytes;
@@ -211,9 +220,9 @@ __device__ __forceinline__ void l1_convert_row16(const uint32_t (&v)[16], const 
     }
 }
 
-template <int N2, bool DS = false>
+template <int N2, bool DS = false, bool SH = false>
 __global__ void __launch_bounds__(kL1Threads, 1) l1_block_kernel(const __grid_constant__ L1BlockParams p) {
-    using Cfg = L1Cfg<N2, DS>;
+    using Cfg = L1Cfg<N2, DS, SH>;
     constexpr int kL1YBufs = Cfg::kYBufs;
     extern __shared__ __align__(1024) uint8_t smem[];
     if ((smem_u32(smem) & 1023u) != 0u) __trap();
@@ -248,6 +257,8 @@ __global__ void __launch_bounds__(kL1Threads, 1) l1_block_kernel(const __grid_co
     uint64_t* stg2_free = e2_local + 1;           // per CTA: the TMA stores of t1' have read smem
     uint64_t* x0_full = stg2_free + 1;            // DS, leader: the x0 tiles of BOTH CTAs have landed (TMA tx)
     uint64_t* x0_free = x0_full + 1;              // DS, per CTA (multicast commit after G1): the x0 tile may be refilled
+    uint64_t* d0b_full = x0_free + 1;             // SH: [2] per CTA, double-buffered 64-column conv2 accumulator
+    uint64_t* d0b_empty = d0b_full + 2;           // SH: [2] leader, 32
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + Cfg::kNumBars);
     float* bias_s = reinterpret_cast<float*>(smem + Cfg::kOffBias);
     for (int i = threadIdx.x; i < 256 + 64 + N2; i += kL1Threads)
@@ -292,6 +303,10 @@ __global__ void __launch_bounds__(kL1Threads, 1) l1_block_kernel(const __grid_co
         mbar_init(stg2_free, 1);
         mbar_init(x0_full, 1);
         mbar_init(x0_free, 1);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&d0b_full[i], 1);
+            mbar_init(&d0b_empty[i], 32);
+        }
         for (int j = 0; j < 4; ++j) {
             mbar_init(&sub_written[j], 32);
             mbar_init(&sub_consumed[j], 1);
@@ -312,7 +327,7 @@ __global__ void __launch_bounds__(kL1Threads, 1) l1_block_kernel(const __grid_co
     const uint32_t tmem_base = *tmem_ptr;
     pdl_launch_dependents();   // the next kernel's prologue may overlap this kernel's tail ...
     pdl_wait();                // ... and this kernel touches activations only once its predecessors have completed
-    constexpr uint32_t kD1 = 0, kD0 = 256, kD2 = 448;   // TMEM column plan
+    constexpr uint32_t kD1 = 0, kD0 = 256, kD2 = SH ? 384 : 448;   // TMEM column plan (SH: D0 = 2 x 64 columns at 256 / 320)
 
     // image line (global over the batch) and first output column of the four lane quarters of a tile
     auto group_coords = [&](int tile, int (&gl)[4], int (&gq)[4]) {
@@ -336,12 +351,17 @@ __global__ void __launch_bounds__(kL1Threads, 1) l1_block_kernel(const __grid_co
         // ===================== TMA producer: weights once, then the A ring =====================
         if (elect_one()) {
             if (rank == 0) mbar_arrive_expect_tx(w_bar, 2u * Cfg::kWeightBytes);
+            if constexpr (SH) {
+                for (int tap = 0; tap < 9; ++tap)   // this CTA's 32 of the 64 cout rows of every tap
+                    tma_load_2d_pair(&p.tmW2, w_bar, smem_w2 + tap * 4096, tap * kBlockK, 32 * static_cast<int>(rank), kEvictLast);
+            } else {
             for (int tr = 0; tr < 3; ++tr)
                 for (int b = 0; b < 3; ++b) {   // this CTA's 96 of the 192 (tap, cout) rows of filter row tr
                     const int n = 96 * static_cast<int>(rank) + 32 * b;
                     tma_load_2d_pair(&p.tmW2, w_bar, smem_w2 + tr * 12288 + b * 4096, (tr * 3 + n / 64) * kBlockK, n % 64,
                                      kEvictLast);
                 }
+            }
             tma_load_2d_pair(&p.tmW3, w_bar, smem_w3, 0, 128 * static_cast<int>(rank), kEvictLast);
             for (int kb = 0; kb < 4; ++kb)
                 tma_load_2d_pair(&p.tmW1, w_bar, smem_w1 + kb * (N2 / 2) * 128, kb * kBlockK, (N2 / 2) * static_cast<int>(rank),
@@ -410,12 +430,29 @@ __global__ void __launch_bounds__(kL1Threads, 1) l1_block_kernel(const __grid_co
                 if (kTimingBuild && p.dbg && pair == 0 && t >= 10 && t < 12 && lane == 0) p.dbg[2048 + (t - 10) * 32 + ev] = tclock();
             };
             auto g0 = [&](int t) {
-                timed_wait(d0_empty, (t & 1u) ^ 1u, 1);
+                if constexpr (SH) timed_wait(&d0b_empty[t & 1], ((t >> 1) & 1u) ^ 1u, 1);
+                else timed_wait(d0_empty, (t & 1u) ^ 1u, 1);
                 tc_fence_after();
                 for (int tr = 0; tr < 3; ++tr) {
                     timed_wait(&full_bar[stage], phase, 2);
                     tc_fence_after();
                     if (elect_one()) {
+                        if constexpr (SH) {
+                            constexpr uint32_t idesc64 = umma_idesc_bf16_f32(256, 64);
+                            const uint32_t d_tmem = tmem_base + kD0 + static_cast<uint32_t>((t & 1) * 64);
+#pragma unroll
+                            for (int ts = 0; ts < 3; ++ts) {
+                                // tap (tr, ts): the same stage, read from pixel row ts on
+                                const uint64_t adesc = umma_desc_k_sw128(base + static_cast<uint32_t>(kL1OffA + stage * kABytes + ts * 128));
+                                const uint64_t bdesc = umma_desc_k_sw128(base + static_cast<uint32_t>(kL1OffW2 + (tr * 3 + ts) * 4096));
+#pragma unroll
+                                for (int k = 0; k < 4; ++k)
+                                    umma_bf16_ss_pair(d_tmem, adesc + static_cast<uint64_t>(2 * k), bdesc + static_cast<uint64_t>(2 * k),
+                                                      idesc64, (tr != 0 || ts != 0 || k != 0) ? 1u : 0u);
+                            }
+                            umma_commit_pair(&empty_bar[stage]);
+                            if (tr == 2) umma_commit_pair(&d0b_full[t & 1]);
+                        } else {
                         const uint64_t adesc = umma_desc_k_sw128(base + static_cast<uint32_t>(kL1OffA + stage * kABytes));
                         const uint64_t bdesc = umma_desc_k_sw128(base + static_cast<uint32_t>(kL1OffW2 + tr * 12288));
 #pragma unroll
@@ -424,6 +461,7 @@ __global__ void __launch_bounds__(kL1Threads, 1) l1_block_kernel(const __grid_co
                                               bdesc + static_cast<uint64_t>(2 * k), idesc0, (tr != 0 || k != 0) ? 1u : 0u);
                         umma_commit_pair(&empty_bar[stage]);
                         if (tr == 2) umma_commit_pair(d0_full);
+                        }
                     }
                     if (tr == 2) trace(t, 0);   // G0 issued
                     __syncwarp();
@@ -581,33 +619,39 @@ __global__ void __launch_bounds__(kL1Threads, 1) l1_block_kernel(const __grid_co
         for (int t = 0; t < T; ++t) {
             mbar_wait(d2_full, t & 1u);
             tc_fence_after();
-            uint32_t w[N2 / 2];
-#pragma unroll
-            for (int c16 = 0; c16 < N2 / 16; ++c16) {
-                uint32_t v[16];
-                tmem_ld_32x16(lane_base + kD2 + static_cast<uint32_t>(c16 * 16), v);
-                tmem_ld_wait();
-                const float* bp = bias_s + 320 + c16 * 16;
-#pragma unroll
-                for (int c = 0; c < 16; c += 2) {
-                    const float2 a = add2(make_float2(__uint_as_float(v[c]), __uint_as_float(v[c + 1])),
-                                          *reinterpret_cast<const float2*>(bp + c));
-                    __nv_bfloat162 h = __floats2bfloat162_rn(a.x, a.y);
-                    h = __hmax2(h, zero2);
-                    w[c16 * 8 + (c >> 1)] = *reinterpret_cast<const uint32_t*>(&h);
-                }
-            }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive_leader(d2_empty);
-            // this thread's row = pixel gq[quarter] + lane of line gl[quarter]; lanes 30, 31 hold the overlap rows of the lane
-            // quarter and the last tile may reach past the last line: neither is stored.  64 channels = one 128-byte line.
             int gl[4], gq[4];
             group_coords(tile_of(t), gl, gq);
-            if (lane < kTap3Group && gl[quarter] < p.lines) {
-                uint4* op = reinterpret_cast<uint4*>(p.out2 + (static_cast<size_t>(gl[quarter]) * p.Wo + gq[quarter] + lane) * N2);
+            // this thread's row = pixel gq[quarter] + lane of line gl[quarter]; lanes 30, 31 hold the overlap rows of the lane
+            // quarter and the last tile may reach past the last line: neither is stored.  64 channels = one 128-byte line.
+            const bool store_ok = lane < kTap3Group && gl[quarter] < p.lines;
+            uint4* op = reinterpret_cast<uint4*>(p.out2 + (static_cast<size_t>(gl[quarter]) * p.Wo + gq[quarter] + lane) * N2);
+#pragma unroll 1
+            for (int half = 0; half < N2 / 64; ++half) {
+                uint32_t w[32];
 #pragma unroll
-                for (int ch = 0; ch < N2 / 8; ++ch) op[ch] = make_uint4(w[4 * ch], w[4 * ch + 1], w[4 * ch + 2], w[4 * ch + 3]);
+                for (int c16 = 0; c16 < 4; ++c16) {
+                    uint32_t v[16];
+                    tmem_ld_32x16(lane_base + kD2 + static_cast<uint32_t>(half * 64 + c16 * 16), v);
+                    tmem_ld_wait();
+                    const float* bp = bias_s + 320 + half * 64 + c16 * 16;
+#pragma unroll
+                    for (int c = 0; c < 16; c += 2) {
+                        const float2 a = add2(make_float2(__uint_as_float(v[c]), __uint_as_float(v[c + 1])),
+                                              *reinterpret_cast<const float2*>(bp + c));
+                        __nv_bfloat162 h = __floats2bfloat162_rn(a.x, a.y);
+                        h = __hmax2(h, zero2);
+                        w[c16 * 8 + (c >> 1)] = *reinterpret_cast<const uint32_t*>(&h);
+                    }
+                }
+                if (half == N2 / 64 - 1) {   // the accumulator has been read completely: the leader may start the next tile's G2
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_leader(d2_empty);
+                }
+                if (store_ok) {
+#pragma unroll
+                    for (int ch = 0; ch < 8; ++ch) op[half * 8 + ch] = make_uint4(w[4 * ch], w[4 * ch + 1], w[4 * ch + 2], w[4 * ch + 3]);
+                }
             }
         }
         (void)l;
@@ -635,6 +679,39 @@ __global__ void __launch_bounds__(kL1Threads, 1) l1_block_kernel(const __grid_co
         };
         auto e0 = [&](int t) {
             lap(11);
+            if constexpr (SH) {
+                // shifted taps: the accumulator already holds the nine taps summed per output pixel - one TMEM load, no shuffles
+                mbar_wait(&d0b_full[t & 1], (t >> 1) & 1u);
+                lap(0);
+                tc_fence_after();
+                uint32_t v[16];
+                tmem_ld_32x16(lane_base + kD0 + static_cast<uint32_t>((t & 1) * 64 + cg * 16), v);
+                tmem_ld_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_leader(&d0b_empty[t & 1]);
+                uint32_t w[8];
+                const float* bp = bias_s + 256 + cg * 16;
+#pragma unroll
+                for (int c = 0; c < 16; c += 2) {
+                    const float2 a = add2(make_float2(__uint_as_float(v[c]), __uint_as_float(v[c + 1])),
+                                          *reinterpret_cast<const float2*>(bp + c));
+                    __nv_bfloat162 h = __floats2bfloat162_rn(a.x, a.y);
+                    h = __hmax2(h, __floats2bfloat162_rn(0.0f, 0.0f));
+                    w[c >> 1] = *reinterpret_cast<const uint32_t*>(&h);
+                }
+                lap(1);
+                mbar_wait(t2_free, (t & 1u) ^ 1u);
+                lap(2);
+                uint8_t* rp = t2_tile + l * 128;
+                *reinterpret_cast<uint4*>(rp + (((2 * cg) ^ (l & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+                *reinterpret_cast<uint4*>(rp + (((2 * cg + 1) ^ (l & 7)) << 4)) = make_uint4(w[4], w[5], w[6], w[7]);
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_leader(t2_ready);
+                lap(1);
+                return;
+            }
             mbar_wait(d0_full, t & 1u);
             etrace(t, 8);    // d0_full seen
             lap(0);

@@ -20,7 +20,12 @@ def _ref(x_nhwc, w, b, pad):
 @pytest.mark.parametrize("B,H", [(1, 30), (3, 30), (2, 60), (2, 120), (20, 60), (5, 90)],
                          ids=["tiny", "b3h30", "h60", "h120", "persistent", "h90"])
 @pytest.mark.parametrize("integer", [True, False], ids=["int", "gauss"])
-def test_l1_block(B, H, integer):
+@pytest.mark.parametrize("form", ["tap192_n64", "shifted_n64", "shifted_n128"])
+def test_l1_block(B, H, integer, form, monkeypatch):
+    """form: the tap-fused N = 192 3x3 GEMM (default), the shifted-tap form of it (nine N = 64 MMAs, BV_L1_SH=1), and the
+    shifted-tap kernel with a 128-wide chained conv1 (the layer's last block, whose successor is layer2's conv1)."""
+    monkeypatch.setenv("BV_L1_SH", "1" if form == "shifted_n64" else "0")
+    n2 = 128 if form == "shifted_n128" else 64
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
     from incremental_multimodal_medical_learning_ii_b200 import _native as N
@@ -41,8 +46,8 @@ def test_l1_block(B, H, integer):
     if integer:
         w3 = (w3 * (torch.rand(w3.shape, generator=g) < 0.25)).to(torch.bfloat16)
     b3 = rnd((256,), -2, 3, 1.0)
-    w1 = rnd((64, 256, 1, 1), -1, 2, 256 ** -0.5).to(torch.bfloat16)
-    b1 = rnd((64,), -2, 3, 1.0)
+    w1 = rnd((n2, 256, 1, 1), -1, 2, 256 ** -0.5).to(torch.bfloat16)
+    b1 = rnd((n2,), -2, 3, 1.0)
     res = rnd((B, H, H, 256), -2, 3, 1.0).to(torch.bfloat16).to(dev)
     c2 = packing.pack_single_conv(w2, b2, 1, 1, dev)
     c3 = packing.pack_single_conv(w3, b3, 1, 0, dev)
@@ -55,7 +60,7 @@ def test_l1_block(B, H, integer):
         assert t2.float().abs().max() <= 256 and y.float().abs().max() <= 256, "test data must stay exact in bf16"
 
     out1 = torch.full((B, H, H, 256), float("nan"), device=dev, dtype=torch.bfloat16)
-    out2 = torch.full((B, H, H, 64), float("nan"), device=dev, dtype=torch.bfloat16)
+    out2 = torch.full((B, H, H, n2), float("nan"), device=dev, dtype=torch.bfloat16)
     N.check(lib.bv_l1_block_nhwc(N.ptr(t1), B, H, H, ctypes.byref(c2[0]), ctypes.byref(c3[0]), N.ptr(res), N.ptr(out1),
                                  ctypes.byref(c1[0]), N.ptr(out2), N.current_stream_handle(dev)))
     torch.cuda.synchronize()
@@ -87,9 +92,11 @@ def test_l1_block_rejects_other_widths():
 @pytest.mark.parametrize("B,H", [(1, 30), (3, 30), (2, 60), (2, 120), (20, 60), (5, 90)],
                          ids=["tiny", "b3h30", "h60", "h120", "persistent", "h90"])
 @pytest.mark.parametrize("integer", [True, False], ids=["int", "gauss"])
-def test_l1_block_downsample_form(B, H, integer):
+@pytest.mark.parametrize("shifted", [False, True], ids=["tap192", "shifted"])
+def test_l1_block_downsample_form(B, H, integer, shifted, monkeypatch):
     """First block of layer1 (Bottleneck with a downsample branch): conv2 -> conv3 + downsample_1x1(x0) -> next conv1 in
     one CTA-pair kernel; the downsample is a second K segment of the conv3 accumulation, no identity tensor is read."""
+    monkeypatch.setenv("BV_L1_SH", "1" if shifted else "0")
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
     from incremental_multimodal_medical_learning_ii_b200 import _native as N
