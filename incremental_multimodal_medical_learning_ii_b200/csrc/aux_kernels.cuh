@@ -351,16 +351,24 @@ __global__ void __launch_bounds__(128) head_global_kernel(const HeadParams hp) {
     }
 }
 
+// Patch path.  The two halves of the CTA (128 threads = 128 output channels each) take the even / odd patches; kHeadPB
+// patches per half are in flight per iteration (their 128-float hidden rows are staged in shared memory by one coalesced
+// load, every projector weight is read once per iteration and reused for all of them), so an image needs
+// ceil(225 / 16) = 15 load -> compute -> normalise rounds instead of 113.  Arithmetic (FMA order over k, the order in
+// which patches are added into the mean, the reduction trees) is exactly that of the one-patch-at-a-time formulation.
+constexpr int kHeadPB = 8;
+constexpr int kHeadSmemBytes = (kEmbDim * kEmbDim + 2 * (2 * kHeadPB) * kEmbDim + 2 * kHeadPB * 4 + 2 * kEmbDim) * 4;
+
 __global__ void __launch_bounds__(256) head_kernel(const HeadParams hp) {
     extern __shared__ float hsm[];
-    float* w2t = hsm;                         // 128*128
-    float* hrow = w2t + kEmbDim * kEmbDim;    // 2 * 128 (two patches in flight)
-    float* red = hrow + 2 * kEmbDim;          // 2 * 4 partial sums of squares
-    float* gsum = red + 8;                    // 2 * 128
-    float* prow = gsum + 2 * kEmbDim;         // 2 * 128 projected rows (for heat-maps)
+    float* w2t = hsm;                                   // 128 * 128
+    float* hrow = w2t + kEmbDim * kEmbDim;              // [2 * PB][128] hidden rows of the patches in flight
+    float* prow = hrow + 2 * kHeadPB * kEmbDim;         // [2 * PB][128] projected (normalised) rows, for the heat-maps
+    float* red = prow + 2 * kHeadPB * kEmbDim;          // [2 * PB][4] partial sums of squares
+    float* gsum = red + 2 * kHeadPB * 4;                // 2 * 128
     const int b = blockIdx.x;
     const int tid = threadIdx.x;
-    const int half = tid >> 7;  // which of the two patches in flight
+    const int half = tid >> 7;
     const int d = tid & 127;
     const int lane = tid & 31;
     const int wq = (tid >> 5) & 3;  // warp within the half
@@ -369,44 +377,74 @@ __global__ void __launch_bounds__(256) head_kernel(const HeadParams hp) {
     float gacc = 0.0f;
     asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");   // programmatic dependent launch, see ptx.cuh
     asm volatile("griddepcontrol.wait;\n" ::: "memory");                 // weights above are constants; hid is not
-    __syncthreads();
-    for (int p0 = 0; p0 < hp.P; p0 += 2) {
-        const int pidx = p0 + half;
-        const bool ok = pidx < hp.P;
-        hrow[tid] = ok ? __ldg(hp.hid + (static_cast<size_t>(b) * hp.P + pidx) * kEmbDim + d) : 0.0f;
-        __syncthreads();
-        float acc = bias;
-        const float* hr = hrow + half * kEmbDim;
-#pragma unroll 8
-        for (int k = 0; k < kEmbDim; ++k) acc = fmaf(hr[k], w2t[k * kEmbDim + d], acc);
-        if (ok) gacc += acc;
-        const bool need_norm = (hp.patch_out && hp.normalize_patch) || hp.heat_out;
-        float inv = 1.0f;
-        if (need_norm) {
-            float ss = acc * acc;
+    const bool need_norm = (hp.patch_out && hp.normalize_patch) || hp.heat_out;
+    const float* hid_b = hp.hid + static_cast<size_t>(b) * hp.P * kEmbDim;
+    for (int p0 = 0; p0 < hp.P; p0 += 2 * kHeadPB) {
+        __syncthreads();   // the previous round's hrow / prow / red have been consumed (and w2t is complete)
 #pragma unroll
-            for (int off = 16; off > 0; off >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, off);
-            if (lane == 0) red[half * 4 + wq] = ss;
-            __syncthreads();
-            const float tot = red[half * 4] + red[half * 4 + 1] + red[half * 4 + 2] + red[half * 4 + 3];
-            inv = 1.0f / fmaxf(sqrtf(tot), 1e-12f);
+        for (int i = 0; i < kHeadPB; ++i) {   // slot s = 2 j + half holds patch p0 + s
+            const int idx = tid + i * 256;
+            const int pidx = p0 + (idx >> 7);
+            hrow[idx] = pidx < hp.P ? __ldg(hid_b + static_cast<size_t>(pidx) * kEmbDim + (idx & 127)) : 0.0f;
         }
-        if (ok && hp.patch_out)
-            hp.patch_out[(static_cast<size_t>(b) * hp.P + pidx) * kEmbDim + d] = hp.normalize_patch ? acc * inv : acc;
-        if (hp.heat_out) {
-            prow[tid] = acc * inv;
+        __syncthreads();
+        float acc[kHeadPB];
+#pragma unroll
+        for (int jj = 0; jj < kHeadPB; ++jj) acc[jj] = bias;
+        const float* hr = hrow + half * kEmbDim;
+#pragma unroll 4
+        for (int k = 0; k < kEmbDim; ++k) {
+            const float w = w2t[k * kEmbDim + d];
+#pragma unroll
+            for (int jj = 0; jj < kHeadPB; ++jj) acc[jj] = fmaf(hr[2 * jj * kEmbDim + k], w, acc[jj]);
+        }
+#pragma unroll
+        for (int jj = 0; jj < kHeadPB; ++jj)
+            if (p0 + 2 * jj + half < hp.P) gacc += acc[jj];
+        float inv[kHeadPB];
+#pragma unroll
+        for (int jj = 0; jj < kHeadPB; ++jj) inv[jj] = 1.0f;
+        if (need_norm) {
+#pragma unroll
+            for (int jj = 0; jj < kHeadPB; ++jj) {
+                float ss = acc[jj] * acc[jj];
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, off);
+                if (lane == 0) red[(2 * jj + half) * 4 + wq] = ss;
+            }
             __syncthreads();
-            // 8 warps: warp w of half h handles labels wq, wq+4, ...
-            for (int l = wq; l < hp.L; l += 4) {
-                const float4 pv = reinterpret_cast<const float4*>(prow + half * kEmbDim)[lane];
+#pragma unroll
+            for (int jj = 0; jj < kHeadPB; ++jj) {
+                const float* r4 = red + (2 * jj + half) * 4;
+                const float tot = r4[0] + r4[1] + r4[2] + r4[3];
+                inv[jj] = 1.0f / fmaxf(sqrtf(tot), 1e-12f);
+            }
+        }
+        if (hp.patch_out) {
+#pragma unroll
+            for (int jj = 0; jj < kHeadPB; ++jj) {
+                const int pidx = p0 + 2 * jj + half;
+                if (pidx < hp.P)
+                    hp.patch_out[(static_cast<size_t>(b) * hp.P + pidx) * kEmbDim + d] = hp.normalize_patch ? acc[jj] * inv[jj] : acc[jj];
+            }
+        }
+        if (hp.heat_out) {
+#pragma unroll
+            for (int jj = 0; jj < kHeadPB; ++jj) prow[(2 * jj + half) * kEmbDim + d] = acc[jj] * inv[jj];
+            __syncthreads();
+            // (patch slot, label) pairs dealt over the 8 warps
+            const int warp = tid >> 5;
+            for (int pr = warp; pr < 2 * kHeadPB * hp.L; pr += 8) {
+                const int s = pr / hp.L, l = pr - s * hp.L;
+                const int pidx = p0 + s;
+                const float4 pv = reinterpret_cast<const float4*>(prow + s * kEmbDim)[lane];
                 const float4 tv = reinterpret_cast<const float4*>(hp.heat_t + static_cast<size_t>(l) * kEmbDim)[lane];
                 float dsum = pv.x * tv.x + pv.y * tv.y + pv.z * tv.z + pv.w * tv.w;
 #pragma unroll
                 for (int off = 16; off > 0; off >>= 1) dsum += __shfl_xor_sync(0xffffffffu, dsum, off);
-                if (lane == 0 && ok) hp.heat_out[(static_cast<size_t>(b) * hp.P + pidx) * hp.L + l] = dsum;
+                if (lane == 0 && pidx < hp.P) hp.heat_out[(static_cast<size_t>(b) * hp.P + pidx) * hp.L + l] = dsum;
             }
         }
-        __syncthreads();
     }
     gsum[tid] = gacc;
     __syncthreads();

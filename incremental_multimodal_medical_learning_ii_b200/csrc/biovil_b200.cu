@@ -296,7 +296,7 @@ int set_kernel_attributes() {
                                  bv::L1Cfg<64, true, true>::kSmemBytes));
     BV_CUDA(cudaFuncSetAttribute(bv::l1_block_kernel<128, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  bv::L1Cfg<128, false, true>::kSmemBytes));
-    BV_CUDA(cudaFuncSetAttribute(bv::head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
+    BV_CUDA(cudaFuncSetAttribute(bv::head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bv::kHeadSmemBytes));
     BV_CUDA(cudaFuncSetAttribute(bv::stem_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  bv::kStemSmemRequest));
     BV_CUDA(cudaFuncSetAttribute(bv::stem_rows_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1430,7 +1430,7 @@ int forward_impl(bv_handle* h, const void* frames, int32_t dtype, int32_t B, int
         hp.score = bv::ScoreOut{out->sim, out->prob, out->pred, out->score};
         hp.heat_out = out->heat;
         hp.heat_t = h->heat_t;
-        const size_t smem = (size_t)(bv::kEmbDim * bv::kEmbDim + 2 * bv::kEmbDim + 8 + 4 * bv::kEmbDim) * sizeof(float);
+        const size_t smem = bv::kHeadSmemBytes;
         if (!out->patch_emb && !out->heat)
             launch_ex(bv::head_global_kernel, B, 128, 0, st, 1, hp);
         else
