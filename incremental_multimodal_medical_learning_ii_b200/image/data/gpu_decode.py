@@ -30,6 +30,8 @@ class GpuJpegDecoder:
         if self.device.type != "cuda":
             raise RuntimeError("GpuJpegDecoder needs a CUDA device (the host path is the reference's own PIL decode)")
         self.lib = N.lib()
+        self._pool = None
+        self._pool_threads = 0
 
     @staticmethod
     def _buffer(data: Bytes):
@@ -54,17 +56,33 @@ class GpuJpegDecoder:
                                                     N.current_stream_handle(self.device)))
         return out
 
-    def decode_batch(self, datas: Sequence[Bytes]) -> List[torch.Tensor]:
-        return [self.decode(d) for d in datas]
+    def decode_batch(self, datas: Sequence[Bytes], threads: int = 0) -> List[torch.Tensor]:
+        """Decode a list of streams (order kept).  nvJPEG's default backend entropy-decodes on the host, so one host
+        thread tops out near 2k frames/s; ``threads`` > 1 decodes on a pool (the native call releases the GIL and every
+        host thread owns its nvJPEG state; all of them enqueue on the caller's current stream)."""
+        if threads <= 1 or len(datas) < 2:
+            return [self.decode(d) for d in datas]
+        from concurrent.futures import ThreadPoolExecutor
+        stream = torch.cuda.current_stream(self.device)
+
+        def work(d):
+            with torch.cuda.stream(stream):          # worker threads start on the default stream: use the caller's
+                return self.decode(d)
+
+        if self._pool is None or self._pool_threads != threads:
+            self._pool = ThreadPoolExecutor(max_workers=threads)
+            self._pool_threads = threads
+        return list(self._pool.map(work, datas))
 
 
 class GpuJpegPipeline:
     """``read_image -> Resize(size) -> CenterCrop(crop)`` of the reference's dataset pipeline (DataRetrieval.py:70-96,
     175-180) on the device: JPEG bytes in, the ``[n,1,crop,crop]`` uint8 batch ``ImageModel`` takes out."""
 
-    def __init__(self, device="cuda:0", resize: int = 512, center_crop_size: int = 512):
+    def __init__(self, device="cuda:0", resize: int = 512, center_crop_size: int = 512, threads: int = 0):
         self.decoder = GpuJpegDecoder(device)
         self.transform = GpuResizeCenterCrop(resize, center_crop_size)
+        self.threads = threads
 
     def __call__(self, datas: Sequence[Bytes]) -> torch.Tensor:
-        return self.transform(self.decoder.decode_batch(datas))
+        return self.transform(self.decoder.decode_batch(datas, threads=self.threads))

@@ -46,6 +46,19 @@ def test_decode_matches_pil_within_idct_rounding(h, w, quality):
     assert diff.max() <= 2 and diff.mean() <= 0.25
 
 
+def test_threaded_decode_keeps_order_and_bits():
+    """decode_batch(threads=N): every host thread owns its nvJPEG state and enqueues on the caller's stream; the result is
+    the frame list in input order, bit-identical to the single-thread decode."""
+    from incremental_multimodal_medical_learning_ii_b200.image.data.gpu_decode import GpuJpegDecoder
+    datas = [_jpeg_bytes(_radiograph_like(120 + 8 * (i % 5), 150 - 6 * (i % 7), seed=i), 85) for i in range(40)]
+    dec = GpuJpegDecoder(DEV)
+    one = dec.decode_batch(datas)
+    many = dec.decode_batch(datas, threads=6)
+    assert len(one) == len(many) == 40
+    for a, b in zip(one, many):
+        assert a.shape == b.shape and torch.equal(a, b)
+
+
 def test_decode_rejects_garbage_and_wrong_device():
     from incremental_multimodal_medical_learning_ii_b200._native import NativeError
     from incremental_multimodal_medical_learning_ii_b200.image.data.gpu_decode import GpuJpegDecoder
