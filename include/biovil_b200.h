@@ -145,6 +145,11 @@ int32_t bv_pairwise_cosine(const float* x, const float* y, int32_t batch, int32_
 int32_t bv_jpeg_info(const uint8_t* host_data, size_t length, int32_t* width, int32_t* height, int32_t* components);
 int32_t bv_jpeg_decode_gray_u8(const uint8_t* host_data, size_t length, uint8_t* out, int32_t width, int32_t height,
                                int32_t pitch, bv_stream stream);
+/* n streams in ONE call through nvjpegDecodeBatched: backend 3 = hardware JPEG engines, 2 = GPU-assisted Huffman decode,
+ * 0 = try 3 then 2.  outs[i] / pitches[i]: device buffers sized from bv_jpeg_info.  Returns the backend used (> 0) or a
+ * negative bv_status when no batched backend takes the batch (callers then use bv_jpeg_decode_gray_u8 per image). */
+int32_t bv_jpeg_decode_batch_gray_u8(const uint8_t* const* host_datas, const size_t* lengths, int32_t n, uint8_t* const* outs,
+                                     const int32_t* pitches, int32_t backend, bv_stream stream);
 
 /* Resize(size) -> CenterCrop(crop) of n same-sized 8-bit grayscale frames src [n,h,w] -> out [n,crop,crop] with the
  * integer arithmetic of Pillow's 8bpc bilinear resampler (short side -> size, long side int(size*long/short), centre

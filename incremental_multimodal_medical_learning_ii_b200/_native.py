@@ -68,7 +68,7 @@ EXPORTED_SYMBOLS = (
     "bv_conv2d_nhwc", "bv_conv_chain_nhwc", "bv_smooth_heatmaps",
     "bv_resize_workspace_bytes", "bv_resize_center_crop_u8", "bv_pair_gemm_test", "bv_l1_block_nhwc",
     "bv_stem_u8_nhwc", "bv_stem_conv1_u8_nhwc", "bv_forward_graph", "bv_pairwise_cosine", "bv_quantize_frames_f32",
-    "bv_jpeg_info", "bv_jpeg_decode_gray_u8", "bv_l1_block_ds_nhwc", "bv_pair_chain_nhwc",
+    "bv_jpeg_info", "bv_jpeg_decode_gray_u8", "bv_l1_block_ds_nhwc", "bv_pair_chain_nhwc", "bv_jpeg_decode_batch_gray_u8",
 )
 
 _lib = None
@@ -183,6 +183,8 @@ def lib() -> ctypes.CDLL:
     l.bv_quantize_frames_f32.argtypes = [c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p]
     l.bv_jpeg_info.restype = c_int32
     l.bv_jpeg_info.argtypes = [c_void_p, c_size_t, POINTER(c_int32), POINTER(c_int32), POINTER(c_int32)]
+    l.bv_jpeg_decode_batch_gray_u8.restype = c_int32
+    l.bv_jpeg_decode_batch_gray_u8.argtypes = [c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_int32, c_void_p]
     l.bv_jpeg_decode_gray_u8.restype = c_int32
     l.bv_jpeg_decode_gray_u8.argtypes = [c_void_p, c_size_t, c_void_p, c_int32, c_int32, c_int32, c_void_p]
     _lib = l

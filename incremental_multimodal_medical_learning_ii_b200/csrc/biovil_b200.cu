@@ -1553,6 +1553,42 @@ int32_t bv_jpeg_decode_gray_u8(const uint8_t* host_data, size_t length, uint8_t*
     return BV_OK;
 }
 
+int32_t bv_jpeg_decode_batch_gray_u8(const uint8_t* const* host_datas, const size_t* lengths, int32_t n, uint8_t* const* outs,
+                                     const int32_t* pitches, int32_t backend, bv_stream stream) {
+    if (!host_datas || !lengths || !outs || !pitches || n <= 0) return fail(BV_ERR_INVALID, "bad JPEG batch arguments");
+    int rc = device_setup();
+    if (rc) return rc;
+    const char* why = nullptr;
+    const jpeg_stage::Api* a = jpeg_stage::api(&why);
+    if (!a) return fail(BV_ERR_CUDA, "nvJPEG unavailable: %s", why);
+    int dev = 0;
+    BV_CUDA(cudaGetDevice(&dev));
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lock(mu);
+    // backend: 3 = hardware JPEG engines, 2 = GPU-assisted Huffman decode; 0 = try 3, then 2
+    const int order[2] = {backend == 0 ? 3 : backend, backend == 0 ? 2 : -1};
+    for (int oi = 0; oi < 2; ++oi) {
+        if (order[oi] < 0) break;
+        jpeg_stage::BatchDecoder* d = jpeg_stage::batch_decoder(dev, order[oi], a);
+        if (!d) continue;
+        if (d->batch != n) {
+            if (a->BatchedInitialize(d->handle, d->state, n, 1, NVJPEG_OUTPUT_Y) != NVJPEG_STATUS_SUCCESS) continue;
+            d->batch = n;
+        }
+        std::vector<nvjpegImage_t> imgs(n);
+        for (int i = 0; i < n; ++i) {
+            memset(&imgs[i], 0, sizeof(nvjpegImage_t));
+            imgs[i].channel[0] = outs[i];
+            imgs[i].pitch[0] = static_cast<size_t>(pitches[i]);
+        }
+        const nvjpegStatus_t st = a->Batched(d->handle, d->state, host_datas, lengths, imgs.data(), reinterpret_cast<cudaStream_t>(stream));
+        if (st == NVJPEG_STATUS_SUCCESS) return order[oi];
+        d->batch = 0;   // the state may be unusable for this batch shape: re-initialise next time
+        cudaGetLastError();
+    }
+    return fail(BV_ERR_INVALID, "no batched nvJPEG backend could decode this batch (use the per-image path)");
+}
+
 int32_t bv_quantize_frames_f32(const float* x, int32_t B, int32_t C, int32_t H, int32_t W, uint8_t* out, int32_t* bad,
                                bv_stream stream) {
     if (!x || !out || !bad || B <= 0 || (C != 1 && C != 3) || H <= 0 || W <= 0) return fail(BV_ERR_INVALID, "bad frame arguments");

@@ -23,6 +23,11 @@ struct Api {
                                    int*) = nullptr;
     nvjpegStatus_t (*Decode)(nvjpegHandle_t, nvjpegJpegState_t, const unsigned char*, size_t, nvjpegOutputFormat_t,
                              nvjpegImage_t*, cudaStream_t) = nullptr;
+    // batched decode (GPU-assisted Huffman / hardware JPEG engines); optional: older libraries may lack them
+    nvjpegStatus_t (*CreateEx)(nvjpegBackend_t, nvjpegDevAllocator_t*, nvjpegPinnedAllocator_t*, unsigned int, nvjpegHandle_t*) = nullptr;
+    nvjpegStatus_t (*BatchedInitialize)(nvjpegHandle_t, nvjpegJpegState_t, int, int, nvjpegOutputFormat_t) = nullptr;
+    nvjpegStatus_t (*Batched)(nvjpegHandle_t, nvjpegJpegState_t, const unsigned char* const*, const size_t*, nvjpegImage_t*,
+                              cudaStream_t) = nullptr;
 };
 
 inline const Api* api(const char** why) {
@@ -48,6 +53,9 @@ inline const Api* api(const char** why) {
             JS_SYM(GetImageInfo, "nvjpegGetImageInfo")
             JS_SYM(Decode, "nvjpegDecode")
 #undef JS_SYM
+            a.CreateEx = reinterpret_cast<decltype(a.CreateEx)>(dlsym(a.lib, "nvjpegCreateEx"));
+            a.BatchedInitialize = reinterpret_cast<decltype(a.BatchedInitialize)>(dlsym(a.lib, "nvjpegDecodeBatchedInitialize"));
+            a.Batched = reinterpret_cast<decltype(a.Batched)>(dlsym(a.lib, "nvjpegDecodeBatched"));
         }
     }
     if (why) *why = err;
@@ -81,6 +89,29 @@ inline Decoder* decoder(int device, const Api* a, const char** why) {
         }
     }
     return d;
+}
+
+// Batched decoders, one per (device, backend), shared by all host threads (guarded by a mutex: a batch is one call).
+struct BatchDecoder {
+    nvjpegHandle_t handle = nullptr;
+    nvjpegJpegState_t state = nullptr;
+    int tried = 0;       // 0 = not yet, 1 = available, -1 = this backend cannot be created on this device / library
+    int batch = 0;       // batch size the state was initialised for
+};
+
+inline BatchDecoder* batch_decoder(int device, int backend, const Api* a) {
+    static BatchDecoder dec[64][8];
+    if (device < 0 || device >= 64 || backend < 0 || backend >= 8) return nullptr;
+    BatchDecoder* d = &dec[device][backend];
+    if (d->tried == 0) {
+        d->tried = -1;
+        if (a->CreateEx && a->BatchedInitialize && a->Batched &&
+            a->CreateEx(static_cast<nvjpegBackend_t>(backend), nullptr, nullptr, 0, &d->handle) == NVJPEG_STATUS_SUCCESS) {
+            if (a->JpegStateCreate(d->handle, &d->state) == NVJPEG_STATUS_SUCCESS) d->tried = 1;
+            else a->Destroy(d->handle);
+        }
+    }
+    return d->tried == 1 ? d : nullptr;
 }
 
 }  // namespace jpeg_stage

@@ -32,6 +32,7 @@ class GpuJpegDecoder:
         self.lib = N.lib()
         self._pool = None
         self._pool_threads = 0
+        self.last_backend = 0
 
     @staticmethod
     def _buffer(data: Bytes):
@@ -55,6 +56,29 @@ class GpuJpegDecoder:
             N.check(self.lib.bv_jpeg_decode_gray_u8(buf, n, N.ptr(out), w.value, h.value, w.value,
                                                     N.current_stream_handle(self.device)))
         return out
+
+    def decode_batched(self, datas: Sequence[Bytes], backend: int = 0) -> List[torch.Tensor]:
+        """All streams in ONE ``nvjpegDecodeBatched`` call (``backend`` 3 = hardware JPEG engines, 2 = GPU-assisted Huffman
+        decode, 0 = try 3 then 2).  Raises ``NativeError`` when no batched backend takes the batch; ``self.last_backend``
+        records which one decoded it."""
+        n = len(datas)
+        bufs = [self._buffer(d) for d in datas]
+        outs, ws = [], []
+        w, h, c = ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32()
+        with torch.cuda.device(self.device):
+            for buf, ln in bufs:
+                N.check(self.lib.bv_jpeg_info(buf, ln, ctypes.byref(w), ctypes.byref(h), ctypes.byref(c)))
+                outs.append(torch.empty(h.value, w.value, dtype=torch.uint8, device=self.device))
+                ws.append(w.value)
+            ptrs = (ctypes.c_void_p * n)(*[ctypes.addressof(b) for b, _ in bufs])
+            lens = (ctypes.c_size_t * n)(*[ln for _, ln in bufs])
+            optr = (ctypes.c_void_p * n)(*[o.data_ptr() for o in outs])
+            pit = (ctypes.c_int32 * n)(*ws)
+            rc = self.lib.bv_jpeg_decode_batch_gray_u8(ptrs, lens, n, optr, pit, backend, N.current_stream_handle(self.device))
+            if rc < 0:
+                N.check(rc)
+        self.last_backend = rc
+        return outs
 
     def decode_batch(self, datas: Sequence[Bytes], threads: int = 0) -> List[torch.Tensor]:
         """Decode a list of streams (order kept).  nvJPEG's default backend entropy-decodes on the host, so one host

@@ -59,6 +59,25 @@ def test_threaded_decode_keeps_order_and_bits():
         assert a.shape == b.shape and torch.equal(a, b)
 
 
+def test_batched_decode_gpu_huffman_backend():
+    """decode_batched: all streams in one nvjpegDecodeBatched call with GPU-assisted Huffman decode (one host thread feeds
+    9k frames/s instead of 2.4k).  Same tolerance against Pillow as the per-image path; mixed frame sizes in one batch."""
+    from PIL import Image
+    from incremental_multimodal_medical_learning_ii_b200._native import NativeError
+    from incremental_multimodal_medical_learning_ii_b200.image.data.gpu_decode import GpuJpegDecoder
+    datas = [_jpeg_bytes(_radiograph_like(96 + 16 * (i % 4), 128 + 8 * (i % 3), seed=100 + i), 88) for i in range(24)]
+    dec = GpuJpegDecoder(DEV)
+    try:
+        outs = dec.decode_batched(datas, backend=2)
+    except NativeError as e:
+        pytest.skip(f"this nvJPEG build has no GPU-hybrid batched backend: {e}")
+    assert dec.last_backend == 2 and len(outs) == 24
+    for d, o in zip(datas, outs):
+        ref = np.asarray(Image.open(io.BytesIO(d)).convert("L"))
+        diff = np.abs(o.cpu().numpy().astype(np.int16) - ref.astype(np.int16))
+        assert o.shape == ref.shape and diff.max() <= 2 and diff.mean() <= 0.25
+
+
 def test_decode_rejects_garbage_and_wrong_device():
     from incremental_multimodal_medical_learning_ii_b200._native import NativeError
     from incremental_multimodal_medical_learning_ii_b200.image.data.gpu_decode import GpuJpegDecoder
