@@ -195,7 +195,9 @@ __device__ __forceinline__ void score_image_warp(const float4 xn, const float* _
                 o.sim[2 * i + 1] = neg;
             }
             if (o.prob) o.prob[i] = 1.0f / (1.0f + expf(-(pos - neg)));
-            if (o.pred) o.pred[i] = (pos > neg) ? 1 : 0;
+            // torch.argmax(cat([neg, pos])) (Trainer.py:836): NaN counts as the maximum, the FIRST maximum wins - a zero
+            // embedding or prompt (0/0 cosine) must give the reference's label, not just "pos > neg"
+            if (o.pred) o.pred[i] = (pos != pos) ? ((neg != neg) ? 0 : 1) : ((pos > neg) ? 1 : 0);
             if (o.score) o.score[i] = (pos + 1.0f) * 0.5f;
         }
     }

@@ -219,6 +219,8 @@ class _Engine:
         prob = torch.empty(B, L, dtype=torch.float32, device=self.device)
         pred = torch.empty(B, L, dtype=torch.uint8, device=self.device)
         score = torch.empty(B, L, dtype=torch.float32, device=self.device)
+        if B == 0:          # empty shard / empty batch: empty results, no launch (the C ABI rejects B <= 0)
+            return {"sim": sim, "prob": prob, "pred": pred, "score": score}
         with torch.cuda.device(self.device):
             N.check(self.lib.bv_score(self.handle, N.ptr(emb), B, N.ptr(sim), N.ptr(prob), N.ptr(pred), N.ptr(score),
                                       N.current_stream_handle(self.device)))
@@ -446,6 +448,8 @@ class ImageModel(nn.Module):
             raise RuntimeError(f"input is on {x.device} but the model is on {device}")
         if x.shape[2] % 32 or x.shape[3] % 32:
             raise ValueError(f"frame size {x.shape[2]}x{x.shape[3]} must be a multiple of 32")
+        if x.shape[0] == 0:
+            return x[:, :1].contiguous()
         if x.dtype == torch.uint8:
             if x.shape[1] == 3:
                 if not bool((x[:, :1] == x).all()):
@@ -491,6 +495,8 @@ class ImageModel(nn.Module):
                 shapes["score"] = ((B, L), torch.float32)
             if heat:
                 shapes["heat"] = ((B, gh, gw, L), torch.float32)
+            if B == 0:      # an empty batch gives empty outputs (what the reference's torch ops do), no launch
+                return {k: torch.empty(shape, dtype=dt, device=dev) for k, (shape, dt) in shapes.items()}
             graphs = self.cuda_graphs
             if (graphs is True or (graphs == "auto" and B <= self.GRAPH_MAX_BATCH)) and B <= self.MAX_BATCH:
                 return eng.forward_graphed(frames, shapes, normalize_patch)

@@ -64,6 +64,11 @@ class ZeroShotScorer:
             raise RuntimeError("call set_prompts() first")
         emb = emb.to(self.device, torch.float32).contiguous()
         B, L = emb.shape[0], self.num_labels
+        if B == 0:
+            out = {"sim": emb.new_empty(0, L, 2), "prob": emb.new_empty(0, L), "pred": torch.empty(0, L, dtype=torch.uint8, device=self.device),
+                   "score": emb.new_empty(0, L)}
+            out["logit"] = out["sim"][..., 0] - out["sim"][..., 1]
+            return out
         out = {"sim": torch.empty(B, L, 2, dtype=torch.float32, device=self.device),
                "prob": torch.empty(B, L, dtype=torch.float32, device=self.device),
                "pred": torch.empty(B, L, dtype=torch.uint8, device=self.device),
@@ -101,6 +106,8 @@ def my_cosine_similarity(x: torch.Tensor, y: torch.Tensor, use_grad: bool = Fals
     B, P = x.shape[0], y.shape[0]
     reduce_max = bool(max_emb and not to_plot)
     out = torch.empty((B,) if reduce_max else (B, P), dtype=torch.float32, device=dev)
+    if B == 0:
+        return out
     with torch.cuda.device(dev):
         N.check(N.lib().bv_pairwise_cosine(N.ptr(x), N.ptr(y), B, P, 1 if reduce_max else 0, N.ptr(out),
                                            N.current_stream_handle(dev)))
