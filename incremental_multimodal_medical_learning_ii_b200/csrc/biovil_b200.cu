@@ -221,8 +221,8 @@ struct ChainLaunch {
     int k1;  // total K of the first GEMM (for cost accounting)
 };
 
-const int kL1ShiftedDefault = 0;   // shifted-tap 3x3 GEMM in the 64-wide forms of the layer1 block kernel (BV_L1_SH)
-const int kL1LastBlockDefault = 0; // the layer's last block (128-wide successor) on the block kernel (BV_L1_LAST)
+const int kL1ShiftedDefault = 1;   // shifted-tap 3x3 GEMM in the 64-wide forms of the layer1 block kernel (BV_L1_SH)
+const int kL1LastBlockDefault = 1; // the layer's last block (128-wide successor) on the block kernel (BV_L1_LAST)
 
 // Fused layer1 block on CTA pairs (l1_block.cuh): conv2 3x3 + conv3 + identity + next conv1.
 struct L1Launch {
@@ -484,6 +484,10 @@ int build_conv(ConvLaunch* L, int B, const ConvOperand* ops, int nops, const voi
     p.out = out;
     p.relu = relu;
     p.out_fp32 = out_fp32;
+    {
+        static const int res_prefetch = getenv("BV_RES_PREFETCH") ? atoi(getenv("BV_RES_PREFETCH")) : 0;
+        p.res_prefetch = residual ? res_prefetch : 0;
+    }
     L->bn = bn;
     L->cfg = cfg;
     // Partial TMEM accumulators (K steps dealt round-robin, summed in the epilogue).  Measured with
@@ -605,7 +609,8 @@ int build_chain(ChainLaunch* L, int B, const ConvOperand* ops, int nops, const v
     p.has_res = residual ? 1 : 0;
     // Measured (ncu dram__bytes_read, profiles/r1n): pulling the next tile into L2 one tile ahead makes the DRAM read
     // traffic 14-40 % LARGER (lines are evicted again before the smem pipeline reaches them) and the kernel slower.
-    p.l2_prefetch = env_flag("BV_L2_PREFETCH") ? 1 : 0;
+    // BV_L2_PREFETCH = n > 1: only the residual, n sub-tiles (16 KB each) ahead of the one being loaded into smem
+    p.l2_prefetch = getenv("BV_L2_PREFETCH") ? atoi(getenv("BV_L2_PREFETCH")) : 0;
     L->n2 = N2;
     L->cfg = (N2 == 64) ? ((nops == 2 && !env_flag("BV_CHAIN_NO_DEEP")) ? 3 : 0) : (N2 == 128 ? 1 : 2);
     if (N2 == 128 && N1 == 512 && env_flag("BV_CHAIN_L2_DEEPSTG")) L->cfg = 4;
@@ -807,6 +812,7 @@ int build_pair_chain(PairChainLaunch* L, int B, int H, int W, const void* x, con
     p.N1 = N1;
     p.num_m_blocks = (int)((M + bv::kBlockM - 1) / bv::kBlockM);
     p.num_pair_tiles = (p.num_m_blocks + 1) / 2;
+    p.res_prefetch = getenv("BV_RES_PREFETCH") ? atoi(getenv("BV_RES_PREFETCH")) : 0;
     L->cfg = cfg;
     if (cfg == 0) {   // experiment: ring / staging split of the layer3 class
         static const int v = getenv("BV_PC_VARIANT") ? atoi(getenv("BV_PC_VARIANT")) : 0;

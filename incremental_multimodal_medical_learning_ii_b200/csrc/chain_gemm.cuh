@@ -217,7 +217,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_gemm_kernel(const __gr
             const int rem = m0 - img * hw;
             const int op = rem / p.Wo;
             const int oq = rem - op * p.Wo;
-            if (p.l2_prefetch && c == 0 && it + 1 < my_tiles && p.seg[0].mode == kSegTiled && elect_one()) {
+            if (p.l2_prefetch == 1 && c == 0 && it + 1 < my_tiles && p.seg[0].mode == kSegTiled && elect_one()) {
                 // next tile's conv3 input: start its HBM fetch now, one whole tile ahead of the smem ring
                 const int m1 = m0 + static_cast<int>(gridDim.x) * kBlockM;
                 for (int cb = 0; cb < p.seg[0].cblocks; ++cb) tma_prefetch_l2_2d(&p.tmA[0], cb * kBlockK, m1);
@@ -381,7 +381,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_gemm_kernel(const __gr
                     tma_prefetch_l2_2d(&p.tmRes, col0, row0);
                 }
             };
-            const int ahead = 2 * C;  // sub-tiles per tile
+            const int ahead = p.l2_prefetch > 1 ? p.l2_prefetch : 2 * C;  // default: sub-tiles per tile
             for (int g = 0; g < NB1 + ahead; ++g) {
                 if (g < NB1) {
                     if (g < total) prepare(g);

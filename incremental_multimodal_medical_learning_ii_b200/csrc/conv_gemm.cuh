@@ -78,6 +78,7 @@ struct ConvGemmParams {
     int out_fp32;
     long long* dbg;  // optional [gridDim][4] cycle counters: MMA warp {total, wait tmem_empty, wait full}, producer {wait empty}
     int nacc;  // independent TMEM accumulators the K steps are dealt over (1 .. 256/BN); summed in the epilogue
+    int res_prefetch;  // > 0: pull the residual sub-tile this many sub-tiles beyond the staging ring into L2 (experiment)
 };
 
 // BN = output channels per tile; STAGES = depth of the A/B smem ring; NBUF = epilogue staging tiles.
@@ -474,6 +475,10 @@ __global__ void __launch_bounds__(gemm_threads(EPI), 1) conv_gemm_kernel(const _
                     coords(g, row0, col0);
                     mbar_arrive_expect_tx(&buf_ready[b], kStagingBytes);
                     tma_load_2d(&p.tmRes, &buf_ready[b], staging + b * kStagingBytes, col0, row0, kEvictFirst);
+                    if (p.res_prefetch > 0 && g + p.res_prefetch < total) {   // short-distance L2 prefetch of the identity rows
+                        coords(g + p.res_prefetch, row0, col0);
+                        tma_prefetch_l2_2d(&p.tmRes, col0, row0);
+                    }
                 } else {
                     mbar_arrive(&buf_ready[b]);
                 }

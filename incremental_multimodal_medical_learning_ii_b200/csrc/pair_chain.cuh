@@ -48,6 +48,7 @@ struct PairChainParams {
     int M, N1;
     int num_m_blocks;    // ceil(M / 128)
     int num_pair_tiles;  // ceil(num_m_blocks / 2)
+    int res_prefetch;    // > 0: pull the identity sub-tile this many sub-tiles beyond the staging ring into L2 (experiment)
 };
 
 template <int N2, int KB1, int STAGES, int NSTG>
@@ -304,6 +305,10 @@ __global__ void __launch_bounds__(kPcThreads, 1) pair_chain_kernel(const __grid_
                 coords(g, row0, col0);
                 mbar_arrive_expect_tx(&stg_ready[b], kStagingBytes);
                 tma_load_2d(&p.tmRes, &stg_ready[b], stg + b * kStagingBytes, col0, row0, kEvictFirst);
+                if (p.res_prefetch > 0 && g + p.res_prefetch < total) {
+                    coords(g + p.res_prefetch, row0, col0);
+                    tma_prefetch_l2_2d(&p.tmRes, col0, row0);
+                }
             };
             for (int g = 0; g < NSTG && g < total; ++g) prepare(g);
             constexpr int kLag = 2;
