@@ -1569,8 +1569,6 @@ int32_t bv_jpeg_decode_batch_gray_u8(const uint8_t* const* host_datas, const siz
     if (!a) return fail(BV_ERR_CUDA, "nvJPEG unavailable: %s", why);
     int dev = 0;
     BV_CUDA(cudaGetDevice(&dev));
-    static std::mutex mu;
-    std::lock_guard<std::mutex> lock(mu);
     // backend: 3 = hardware JPEG engines, 2 = GPU-assisted Huffman decode; 0 = try 3, then 2
     const int order[2] = {backend == 0 ? 3 : backend, backend == 0 ? 2 : -1};
     for (int oi = 0; oi < 2; ++oi) {

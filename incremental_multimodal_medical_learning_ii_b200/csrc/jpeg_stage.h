@@ -91,7 +91,8 @@ inline Decoder* decoder(int device, const Api* a, const char** why) {
     return d;
 }
 
-// Batched decoders, one per (device, backend), shared by all host threads (guarded by a mutex: a batch is one call).
+// Batched decoders, one per (host thread, device, backend): several host threads may each push their own sub-batch
+// (own nvJPEG handle + state, own stream), which is how the GPU-assisted Huffman backend is kept fed.
 struct BatchDecoder {
     nvjpegHandle_t handle = nullptr;
     nvjpegJpegState_t state = nullptr;
@@ -100,7 +101,7 @@ struct BatchDecoder {
 };
 
 inline BatchDecoder* batch_decoder(int device, int backend, const Api* a) {
-    static BatchDecoder dec[64][8];
+    thread_local BatchDecoder dec[64][8];
     if (device < 0 || device >= 64 || backend < 0 || backend >= 8) return nullptr;
     BatchDecoder* d = &dec[device][backend];
     if (d->tried == 0) {

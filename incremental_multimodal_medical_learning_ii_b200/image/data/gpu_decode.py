@@ -32,6 +32,7 @@ class GpuJpegDecoder:
         self.lib = N.lib()
         self._pool = None
         self._pool_threads = 0
+        self._streams: List[torch.cuda.Stream] = []
         self.last_backend = 0
 
     @staticmethod
@@ -57,11 +58,40 @@ class GpuJpegDecoder:
                                                     N.current_stream_handle(self.device)))
         return out
 
-    def decode_batched(self, datas: Sequence[Bytes], backend: int = 0) -> List[torch.Tensor]:
+    def decode_batched(self, datas: Sequence[Bytes], backend: int = 0, threads: int = 1) -> List[torch.Tensor]:
         """All streams in ONE ``nvjpegDecodeBatched`` call (``backend`` 3 = hardware JPEG engines, 2 = GPU-assisted Huffman
         decode, 0 = try 3 then 2).  Raises ``NativeError`` when no batched backend takes the batch; ``self.last_backend``
-        records which one decoded it."""
+        records which one decoded it.  ``threads`` > 1 splits the batch into that many contiguous sub-batches, each pushed
+        by its own host thread (own nvJPEG handle and state) on its own CUDA stream; the caller's stream waits for all of
+        them - header parsing, the pinned staging copy and the Huffman kernels of different sub-batches overlap."""
         n = len(datas)
+        if threads > 1 and n >= 2 * threads:
+            from concurrent.futures import ThreadPoolExecutor
+            if self._pool is None or self._pool_threads != threads:
+                self._pool = ThreadPoolExecutor(max_workers=threads)
+                self._pool_threads = threads
+            if len(self._streams) < threads:
+                self._streams += [torch.cuda.Stream(self.device) for _ in range(threads - len(self._streams))]
+            caller = torch.cuda.current_stream(self.device)
+            start = torch.cuda.Event()
+            start.record(caller)
+            step = (n + threads - 1) // threads
+
+            def work(i):
+                st = self._streams[i]
+                st.wait_event(start)
+                with torch.cuda.stream(st):
+                    outs = self.decode_batched(datas[i * step:(i + 1) * step], backend=backend)
+                    done = torch.cuda.Event()
+                    done.record(st)
+                for o in outs:
+                    o.record_stream(caller)
+                return outs, done
+
+            res = list(self._pool.map(work, range((n + step - 1) // step)))
+            for _, done in res:
+                caller.wait_event(done)
+            return [o for outs, _ in res for o in outs]
         bufs = [self._buffer(d) for d in datas]
         outs, ws = [], []
         w, h, c = ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32()
@@ -103,10 +133,14 @@ class GpuJpegPipeline:
     """``read_image -> Resize(size) -> CenterCrop(crop)`` of the reference's dataset pipeline (DataRetrieval.py:70-96,
     175-180) on the device: JPEG bytes in, the ``[n,1,crop,crop]`` uint8 batch ``ImageModel`` takes out."""
 
-    def __init__(self, device="cuda:0", resize: int = 512, center_crop_size: int = 512, threads: int = 0):
+    def __init__(self, device="cuda:0", resize: int = 512, center_crop_size: int = 512, threads: int = 0,
+                 batched: bool = False):
         self.decoder = GpuJpegDecoder(device)
         self.transform = GpuResizeCenterCrop(resize, center_crop_size)
         self.threads = threads
+        self.batched = batched          # nvjpegDecodeBatched (GPU-assisted Huffman) sub-batches instead of per-image calls
 
     def __call__(self, datas: Sequence[Bytes]) -> torch.Tensor:
+        if self.batched:
+            return self.transform(self.decoder.decode_batched(datas, threads=max(1, self.threads)))
         return self.transform(self.decoder.decode_batch(datas, threads=self.threads))

@@ -102,3 +102,54 @@ class HostFramePipeline:
         for out, ev in pending:
             ev.synchronize()
             yield out
+
+
+class JpegBytesPipeline:
+    """Compressed radiographs in, embeddings + scores out, with nothing but the JPEG bytes crossing PCIe.
+
+    The reference's loader decodes and resizes on the host (``read_image`` -> PIL, DataRetrieval.py:70-96, 175-180; about
+    730 frames/s per core) and ships 1 MB of float pixels per frame.  Here batch i+1 is entropy-decoded by nvJPEG's
+    GPU-assisted Huffman backend (``threads`` host threads, each pushing a contiguous sub-batch through its own handle on
+    its own stream) and resized on the device (PIL-exact ``bv_resize_center_crop_u8``) on a side stream while
+    ``model.embed_and_score`` runs batch i on the caller's stream.  ``run(batches)`` takes an iterable of lists of JPEG
+    byte strings and yields the DEVICE result dict of every batch, in order.
+    """
+
+    def __init__(self, model, resize: int = 512, center_crop_size: int = 480, threads: int = 2, batched: bool = True):
+        from concurrent.futures import ThreadPoolExecutor
+        from .image.data.gpu_decode import GpuJpegPipeline
+        self.model = model
+        self.device = next(model.parameters()).device
+        if self.device.type != "cuda":
+            raise RuntimeError("JpegBytesPipeline needs the model on a CUDA device")
+        self.stage = GpuJpegPipeline(self.device, resize, center_crop_size, threads=threads, batched=batched)
+        self.decode_stream = torch.cuda.Stream(self.device)
+        self._worker = ThreadPoolExecutor(max_workers=1)
+
+    def _decode(self, datas):
+        from ._native import NativeError
+        with torch.cuda.device(self.device), torch.cuda.stream(self.decode_stream):
+            try:
+                frames = self.stage(datas)
+            except NativeError:
+                if not self.stage.batched:
+                    raise
+                self.stage.batched = False      # this nvJPEG build has no batched GPU backend: per-image calls on the thread pool
+                frames = self.stage(datas)
+            ready = torch.cuda.Event()
+            ready.record(self.decode_stream)
+        return frames, ready
+
+    def run(self, batches: Iterable[Sequence[bytes]], heat: bool = False, patch: bool = False) -> Iterator[Dict[str, torch.Tensor]]:
+        compute = torch.cuda.current_stream(self.device)
+        it = iter(batches)
+        first = next(it, None)
+        fut = self._worker.submit(self._decode, first) if first is not None else None
+        while fut is not None:
+            frames, ready = fut.result()
+            nxt = next(it, None)
+            fut = self._worker.submit(self._decode, nxt) if nxt is not None else None     # batch i+1 decodes under batch i
+            compute.wait_event(ready)
+            res = self.model.embed_and_score(frames, heat=heat, patch=patch)
+            frames.record_stream(compute)
+            yield res

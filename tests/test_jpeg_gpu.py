@@ -78,6 +78,37 @@ def test_batched_decode_gpu_huffman_backend():
         assert o.shape == ref.shape and diff.max() <= 2 and diff.mean() <= 0.25
 
 
+def test_threaded_batched_decode_equals_one_batch():
+    """decode_batched(threads=N): N host threads push contiguous sub-batches through their own nvJPEG handles on their own
+    streams; the caller's stream waits for all of them.  Same frames, same order, same bits as one batched call."""
+    from incremental_multimodal_medical_learning_ii_b200._native import NativeError
+    from incremental_multimodal_medical_learning_ii_b200.image.data.gpu_decode import GpuJpegDecoder, GpuJpegPipeline
+    datas = [_jpeg_bytes(_radiograph_like(96 + 16 * (i % 4), 128 + 8 * (i % 3), seed=300 + i), 88) for i in range(50)]
+    dec = GpuJpegDecoder(DEV)
+    try:
+        one = dec.decode_batched(datas, backend=2)
+    except NativeError as e:
+        pytest.skip(f"this nvJPEG build has no GPU-hybrid batched backend: {e}")
+    for th in (2, 3, 7):
+        many = dec.decode_batched(datas, backend=2, threads=th)
+        step = (50 + th - 1) // th
+        seq = [o for i in range(0, 50, step) for o in dec.decode_batched(datas[i:i + step], backend=2)]
+        assert len(many) == 50
+        for a, b, c in zip(one, many, seq):
+            assert a.shape == b.shape and torch.equal(b, c)           # threads change nothing: same bits as the same sub-batches in turn
+            assert (a.int() - b.int()).abs().max().item() <= 1        # nvJPEG rounds a few pixels differently for other batch sizes
+    side = torch.cuda.Stream(DEV)                      # a caller on a non-default stream
+    with torch.cuda.stream(side):
+        many = dec.decode_batched(datas, backend=2, threads=4)
+        total = sum(int(o.long().sum()) for o in many)
+    step = (50 + 3) // 4
+    assert total == sum(int(o.long().sum()) for i in range(0, 50, step) for o in dec.decode_batched(datas[i:i + step], backend=2))
+    a = GpuJpegPipeline(DEV, resize=128, center_crop_size=96)(datas)
+    b = GpuJpegPipeline(DEV, resize=128, center_crop_size=96, threads=4, batched=True)(datas)
+    assert a.shape == b.shape == (50, 1, 96, 96)
+    assert (a.int() - b.int()).abs().max().item() <= 2          # two nvJPEG backends: IDCT rounding may differ by a grey level
+
+
 def test_decode_rejects_garbage_and_wrong_device():
     from incremental_multimodal_medical_learning_ii_b200._native import NativeError
     from incremental_multimodal_medical_learning_ii_b200.image.data.gpu_decode import GpuJpegDecoder
@@ -111,3 +142,30 @@ def test_jpeg_to_embedding_pipeline():
     cos = F.cosine_similarity(a, b, dim=-1).min().item()
     print(f"decode-path embedding cosine vs host-decode path: {cos:.6f}")
     assert cos >= 0.9999
+
+
+def test_jpeg_bytes_pipeline_equals_batch_by_batch():
+    """JpegBytesPipeline.run: batch i+1 decodes + resizes on a side stream (2 host threads, batched nvJPEG) while the model
+    runs batch i.  Every yielded result must be bit-identical to decoding and scoring that batch on its own, in order,
+    including a ragged last batch."""
+    from incremental_multimodal_medical_learning_ii_b200 import frames as FR
+    from incremental_multimodal_medical_learning_ii_b200 import synthetic_weights as SW
+    from incremental_multimodal_medical_learning_ii_b200.image import get_biovil_resnet
+    from incremental_multimodal_medical_learning_ii_b200.pipeline import JpegBytesPipeline
+    model = get_biovil_resnet(None)
+    model.load_state_dict(SW.make_state_dict(27))
+    model.eval().to(DEV)
+    model.set_prompts(FR.synthetic_prompt_embeddings(14, 1, 128, seed=29), reduce="mean")
+    datas = [_jpeg_bytes(_radiograph_like(150 + 6 * (i % 5), 170 - 4 * (i % 3), seed=500 + i), 90) for i in range(44)]
+    batches = [datas[0:16], datas[16:32], datas[32:44]]
+    jp = JpegBytesPipeline(model, resize=128, center_crop_size=96, threads=2)
+    got = [{k: v.clone() for k, v in r.items()} for r in jp.run(batches)]
+    assert len(got) == 3
+    for b, g in zip(batches, got):
+        ref = model.embed_and_score(jp.stage(b))
+        for k in ("global", "prob", "pred"):
+            assert torch.equal(g[k], ref[k]), k
+    assert got[2]["global"].shape == (12, 128)
+    assert list(jp.run([])) == []
+    with pytest.raises(RuntimeError):
+        JpegBytesPipeline(get_biovil_resnet(None))          # model on the CPU

@@ -73,7 +73,47 @@ for backend, bname in ((3, "hardware JPEG engines"), (2, "GPU-assisted Huffman")
                           "images_per_s": round(n / dt), "max_abs_diff_vs_default_backend": diff}))
     except Exception as e:
         print(json.dumps({"stage": f"GPU: nvjpegDecodeBatched ({bname})", "unavailable": str(e)[:160]}))
-print(json.dumps({"stage": "GPU: ImageModel on the decoded batch", "frames": n, "images_per_s": round(n / t_emb)}))
+for th in (2, 4, 8):
+    try:
+        pipe_b = GpuJpegPipeline(dev, resize=512, center_crop_size=480, threads=th, batched=True)
+        pipe_b(datas)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        fr_b = pipe_b(datas)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        diff = (fr_b.int() - frames.int()).abs().max().item()
+        print(json.dumps({"stage": f"GPU: nvjpegDecodeBatched (GPU-assisted Huffman), {th} host threads x {n // th} frames, + resize on the device",
+                          "frames": n, "images_per_s": round(n / dt), "max_abs_diff_vs_default_backend": diff}))
+    except Exception as e:
+        print(json.dumps({"stage": f"GPU: threaded nvjpegDecodeBatched, {th} threads", "unavailable": str(e)[:160]}))
+from incremental_multimodal_medical_learning_ii_b200 import frames as FR  # noqa: E402
+from incremental_multimodal_medical_learning_ii_b200.pipeline import JpegBytesPipeline  # noqa: E402
+model.set_prompts(FR.synthetic_prompt_embeddings(14, 1, 128, seed=29), reduce="mean")
+for _ in range(2):
+    model.embed_and_score(frames)
+torch.cuda.synchronize()
+t0 = time.perf_counter()
+for _ in range(4):
+    model.embed_and_score(frames)
+torch.cuda.synchronize()
+t_emb = (time.perf_counter() - t0) / 4
+print(json.dumps({"stage": "GPU: ImageModel.embed_and_score on a decoded batch (warm)", "frames": n, "images_per_s": round(n / t_emb)}))
+for th in (2, 4):
+    jp = JpegBytesPipeline(model, resize=512, center_crop_size=480, threads=th)
+    for _ in jp.run([datas] * 2):
+        pass
+    torch.cuda.synchronize()
+    nb = 10
+    t0 = time.perf_counter()
+    chk = 0
+    for res in jp.run([datas] * nb):
+        last = res
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    print(json.dumps({"stage": f"GPU: JPEG bytes -> embeddings + scores, decode of batch i+1 ({th} host threads, GPU-assisted Huffman) under the model on batch i",
+                      "frames": nb * n, "images_per_s": round(nb * n / dt), "batched_backend": jp.stage.batched,
+                      "h2d_bytes_per_frame": int(np.mean([len(d) for d in datas]))}))
 from torchvision import transforms  # noqa: E402
 tf = transforms.Compose([transforms.Resize(512), transforms.CenterCrop(480)])
 t0 = time.perf_counter()
