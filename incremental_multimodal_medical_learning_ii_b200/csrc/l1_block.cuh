@@ -46,7 +46,13 @@
 namespace bv {
 
 constexpr int kL1Threads = 24 * 32;
-constexpr int kL1Stages = 2;      // A ring (a tile needs three stages: the third load waits for the first MMA group)
+#ifndef BV_L1_STAGES
+#define BV_L1_STAGES 3
+#endif
+// A ring.  A tile needs three stages (one per filter row).  With two, the third load waits for the first MMA group of the SAME
+// tile and its latency is exposed once per tile; with three, all loads of tile t+1 are issued while tile t is still in its
+// epilogues - paid for with one y / identity staging sub-tile (shared memory is full).
+constexpr int kL1Stages = BV_L1_STAGES;
 // y / identity staging sub-tiles (L1Cfg::kYBufs): 4 per tile + 1 with an identity stream, so that the identity rows of the
 // next tile's sub-tile j only wait for THIS tile's sub-tile j-1 to drain; 3 in the downsample form (nothing is prefetched
 // into them)
@@ -71,7 +77,7 @@ constexpr int kL1OffW1 = kL1OffW3 + 128 * 128;             // 4 k-blocks x [N2/2
 template <int N2, bool DS = false, bool SH = false>
 struct L1Cfg {
     static_assert(N2 == 64 || (N2 == 128 && SH && !DS), "TMEM plan: D1 256 + D0 192 + D2 64, or (shifted taps) D1 256 + D0 2 x 64 + D2 <= 128");
-    static constexpr int kYBufs = DS ? 4 : (N2 == 64 ? 6 : 5);   // (t1' leaves through direct stores: no staging tile for it)
+    static constexpr int kYBufs = (DS ? 4 : (N2 == 64 ? 6 : 5)) - (kL1Stages - 2);   // (t1' leaves through direct stores: no staging tile for it)
     static constexpr int kW1Bytes = 4 * (N2 / 2) * 128;
     static constexpr int kWdBytes = DS ? 128 * 128 : 0;          // this CTA's half of the downsample weights [128 rows x 128 B]
     static constexpr int kOffWd = kL1OffW1 + kW1Bytes;
