@@ -24,4 +24,4 @@ fr = torch.cat([FR.synthetic_frames_u8(o, min(64, B - o), 480, kind="structured"
 for _ in range(n):
     res = m.embed_and_score(fr)
 torch.cuda.synchronize()
-print("ok", float(res["prob"].sum()))
+print("ok", float(res["prob"].sum()), "launches_per_forward", m._get_engine().launches())
