@@ -100,10 +100,22 @@ __device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t pa
         : "memory");
     return ok != 0;
 }
+__device__ __forceinline__ bool mbar_try_wait_cluster_hint(uint64_t* bar, uint32_t parity) {
+    if constexpr (kMbarHintNs == 0) return mbar_try_wait_cluster(bar, parity);
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(kMbarHintNs)
+        : "memory");
+    return ok != 0;
+}
 __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
     if (mbar_try_wait_cluster(bar, parity)) return;
     const long long t0 = clock64();
-    while (!mbar_try_wait_cluster(bar, parity)) {
+    while (!mbar_try_wait_cluster_hint(bar, parity)) {
         if (clock64() - t0 > 4000000000LL) __trap();
     }
 }

@@ -68,6 +68,14 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
 }
 
+// BV_MBAR_HINT_NS > 0: the waits pass a suspend-time hint, so a waiting warp stays suspended (it is woken when the phase
+// completes) instead of returning to the spin loop after the short system-dependent limit: every poll is a shared-memory
+// wavefront on the LSU data pipe (ncu: about a fifth of l1_block's LSU wavefronts are polls).
+#ifndef BV_MBAR_HINT_NS
+#define BV_MBAR_HINT_NS 0
+#endif
+constexpr uint32_t kMbarHintNs = BV_MBAR_HINT_NS;
+
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
@@ -79,13 +87,25 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
+__device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parity) {
+    if constexpr (kMbarHintNs == 0) return mbar_try_wait(bar, parity);
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(kMbarHintNs)
+        : "memory");
+    return ok != 0;
+}
 
 // Spin until the phase with the given parity completes.  A wait that lasts longer than ~2 s of SM clocks can only
 // be a protocol bug (lost arrival / wrong byte count); trap instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
     const long long t0 = clock64();
-    while (!mbar_try_wait(bar, parity)) {
+    while (!mbar_try_wait_hint(bar, parity)) {
         if (clock64() - t0 > 4000000000LL) __trap();
     }
 }
