@@ -631,9 +631,26 @@ bool l1_ds_supported(const bv_conv& ds) {
 
 // t1 [B,H,W,64] -> out1 = relu(conv3(relu(conv2(t1))) + residual) [B,H,W,256], out2 = relu(next(out1)) [B,H,W,64]
 // With a downsample branch (x0 [B,H,W,64], ds 64 -> 256 1x1) instead of a residual: out1 = relu(conv3(..) + ds(x0)).
+// fp32 bias vectors on the HOST (kernels that take their biases by value, i.e. in the constant bank): the handle copies every
+// convolution's bias once at bv_create - outside any stream capture, where a synchronous copy would be illegal - and the
+// plan builder looks them up by device pointer; the unit-test entry points have no handle and copy here.
+using HostBiasMap = std::map<const float*, std::vector<float>>;
+int fetch_bias(const HostBiasMap* cache, const float* dev, int n, float* dst) {
+    if (!dev) return fail(BV_ERR_INVALID, "convolution without a bias vector");
+    if (cache) {
+        auto it = cache->find(dev);
+        if (it != cache->end() && static_cast<int>(it->second.size()) >= n) {
+            memcpy(dst, it->second.data(), sizeof(float) * n);
+            return BV_OK;
+        }
+    }
+    BV_CUDA(cudaMemcpy(dst, dev, sizeof(float) * n, cudaMemcpyDeviceToHost));
+    return BV_OK;
+}
+
 int build_l1_block(L1Launch* L, int B, int H, int W, const void* t1, const bv_conv& c2, const bv_conv& c3,
                    const void* residual, void* out1, const bv_conv& next, void* out2, const void* x0 = nullptr,
-                   const bv_conv* ds = nullptr) {
+                   const bv_conv* ds = nullptr, const HostBiasMap* bias_cache = nullptr) {
     if (!l1_block_supported(c2, c3, next, W))
         return fail(BV_ERR_INVALID, "unsupported shapes for the fused layer1 block (64->64 3x3, 64->256, 256->64, width %% 30 == 0)");
     const bool use_ds = x0 != nullptr && ds != nullptr;
@@ -650,16 +667,23 @@ int build_l1_block(L1Launch* L, int B, int H, int W, const void* t1, const bv_co
     if (use_ds) {
         if ((rc = make_tmap_lines(&p.tmX0, x0, B * H, W, 64, 32))) return rc;
         if ((rc = make_tmap_2d(&p.tmWd, ds->w, 64, 256, bv::kBlockK, 128))) return rc;
-        p.bias_ds = ds->bias;
     } else {
         if ((rc = make_tmap_lines(&p.tmRes, residual, B * H, W, 256, 32))) return rc;
     }
     if ((rc = make_tmap_2d(&p.tmW2, c2.w, 576, 64, bv::kBlockK, 32))) return rc;
     if ((rc = make_tmap_2d(&p.tmW3, c3.w, 64, 256, bv::kBlockK, 128))) return rc;
     if ((rc = make_tmap_2d(&p.tmW1, next.w, 256, (uint64_t)next.cout, bv::kBlockK, (uint32_t)(next.cout / 2)))) return rc;
-    p.bias2 = c2.bias;
-    p.bias3 = c3.bias;
-    p.bias1 = next.bias;
+    {   // biases by value: bias3 (+ downsample bias) [256] | bias2 [64] | bias1 [next.cout]
+        float* bc = reinterpret_cast<float*>(p.bias_c);
+        if ((rc = fetch_bias(bias_cache, c3.bias, 256, bc))) return rc;
+        if (use_ds) {
+            float bd[256];
+            if ((rc = fetch_bias(bias_cache, ds->bias, 256, bd))) return rc;
+            for (int i = 0; i < 256; ++i) bc[i] += bd[i];
+        }
+        if ((rc = fetch_bias(bias_cache, c2.bias, 64, bc + 256))) return rc;
+        if ((rc = fetch_bias(bias_cache, next.bias, next.cout, bc + 320))) return rc;
+    }
     if ((rc = make_tmap_lines(&p.tmOut1, out1, B * H, W, 256, bv::kTap3Group))) return rc;
     // shifted-tap 3x3 GEMM: required by the 128-wide successor; for the 64-wide forms an A/B switch (BV_L1_SH, default on/off below)
     const int sh_mode = getenv("BV_L1_SH") ? atoi(getenv("BV_L1_SH")) : kL1ShiftedDefault;
@@ -889,6 +913,7 @@ Layout make_layout(int B, int C, int H, int W) {
 struct bv_handle {
     bv_weights w;
     int device;
+    HostBiasMap host_bias;    // host copies of the bias vectors (see fetch_bias)
     // prompts
     float* yn = nullptr;      // [L][2][P][128] unit vectors
     float* heat_t = nullptr;  // [L][128]
@@ -1026,6 +1051,28 @@ int32_t bv_create(bv_handle** out, const bv_weights* w, int32_t device) {
     bv_handle* h = new bv_handle();
     h->w = *w;
     h->device = device;
+    // host copies of the layer1 bias vectors (the block kernel takes them by value): the packing kernels that wrote them may
+    // still be running on any stream of the caller
+    {
+        bool any = false;
+        for (int i = 0; i < BV_NUM_BLOCKS && !any; ++i) any = w->conv2[i].bias != nullptr;
+        if (any) {
+            if (cudaDeviceSynchronize() != cudaSuccess) {
+                delete h;
+                return fail(BV_ERR_CUDA, "cudaDeviceSynchronize failed: %s", cudaGetErrorString(cudaGetLastError()));
+            }
+            for (int i = 0; i < BV_NUM_BLOCKS; ++i)
+                for (const bv_conv* c : {&w->conv1[i], &w->conv2[i], &w->conv3[i], &w->downsample[i]}) {
+                    if (!c->bias || c->cout <= 0 || c->cout > 256) continue;     // only layer1-sized vectors are ever looked up
+                    std::vector<float>& v = h->host_bias[c->bias];
+                    v.resize(c->cout);
+                    if (cudaMemcpy(v.data(), c->bias, sizeof(float) * c->cout, cudaMemcpyDeviceToHost) != cudaSuccess) {
+                        delete h;
+                        return fail(BV_ERR_CUDA, "copying a bias vector to the host failed: %s", cudaGetErrorString(cudaGetLastError()));
+                    }
+                }
+        }
+    }
     *out = h;
     return BV_OK;
 }
@@ -1196,8 +1243,8 @@ static int build_plan(bv_handle* h, const void* frames, int dtype, int B, int C,
                 (!l1_wide_next || (l1_last && ds.w == nullptr)) && l1_block_supported(c2, c3, h->w.conv1[blk + 1], cw)) {
                 PlanStep s;
                 s.l1 = true;
-                if (l1_ds) rc = build_l1_block(&s.l1b, B, ch, cw, t1, c2, c3, nullptr, nxt, h->w.conv1[blk + 1], t2, cur, &ds);
-                else rc = build_l1_block(&s.l1b, B, ch, cw, t1, c2, c3, cur, nxt, h->w.conv1[blk + 1], t2);
+                if (l1_ds) rc = build_l1_block(&s.l1b, B, ch, cw, t1, c2, c3, nullptr, nxt, h->w.conv1[blk + 1], t2, cur, &ds, &h->host_bias);
+                else rc = build_l1_block(&s.l1b, B, ch, cw, t1, c2, c3, cur, nxt, h->w.conv1[blk + 1], t2, nullptr, nullptr, &h->host_bias);
                 if (rc) return rc;
                 h->steps.push_back(s);
                 // the next block's conv1 output went to t2: swap the roles of the two scratch buffers

@@ -86,8 +86,7 @@ struct L1Cfg {
     static constexpr int kOffStg1 = kOffT2 + kABytes;            // kYBufs sub-tiles x 16 KB
     static constexpr int kOffBars = kOffStg1 + kYBufs * kStagingBytes;
     static constexpr int kNumBars = 2 * kL1Stages + 1 + 8 + 24 + kYBufs + 2 + 2 + 4;
-    static constexpr int kOffBias = (kOffBars + kNumBars * 8 + 16 + 15) / 16 * 16;               // fp32: bias3[256] | bias2[64] | bias1[N2]
-    static constexpr int kSmemBytes = kOffBias + (256 + 64 + N2) * 4;
+    static constexpr int kSmemBytes = kOffBars + kNumBars * 8 + 16;
     static constexpr uint32_t kWeightBytes = 3 * 96 * 128 + 128 * 128 + kW1Bytes + kWdBytes;
     static_assert(kOffWd % 1024 == 0 && kOffX0 % 1024 == 0 && kOffT2 % 1024 == 0 && kOffStg1 % 1024 == 0,
                   "operand tiles need 1024-byte alignment");
@@ -102,13 +101,14 @@ struct L1BlockParams {
     CUtensorMap tmW1;   // [N2, 256]  box 64 x N2/2
     CUtensorMap tmX0;   // DS: block input x0 as (64, W, B*H), tiled, box 64 channels x 32 pixels x 1 line
     CUtensorMap tmWd;   // DS: downsample weights [256, 64], box 64 x 128
-    const float* bias_ds;   // DS: added to bias3
     CUtensorMap tmOut1; // y   as (256, W, B*H), tiled, box 64 channels x 30 pixels x 1 line
     __nv_bfloat16* out2; // t1' [B*H][W][N2]: written with direct 128-byte-per-thread stores by the second-GEMM epilogue
     int lines;           // B * H
-    const float* bias2;
-    const float* bias3;
-    const float* bias1;
+    // BatchNorm biases BY VALUE, i.e. in the kernel's constant bank: bias3 (+ downsample bias) [256] | bias2 [64] | bias1 [N2].
+    // The epilogues read them with indexed constant loads (LDC): a broadcast LDS.128 costs two wavefronts on the LSU data
+    // pipe, which made the bias the largest single consumer of that pipe (ncu source page: 43 M of 118 M shared-memory
+    // wavefronts of the identity form) although it carries 1.5 KB.
+    float4 bias_c[(256 + 64 + 128) / 4];
     int Ho, Wo;
     int groups_per_line;  // Wo / 30
     int num_groups;       // B * Ho * Wo / 30 lane quarters of work
@@ -167,41 +167,13 @@ __device__ __forceinline__ float2 add2(float2 a, float2 b) {
     return d;
 }
 
-// y sub-tile epilogue for 32 accumulator columns (half of a 64-column sub-tile) of one row: + bias + residual (in place
-// in the swizzled staging row), ReLU after the bf16 rounding (max commutes with the rounding), bf16 pack.
-// `bias_s` points into shared memory at the first of the 32 columns.
-__device__ __forceinline__ void l1_convert_row32(const uint32_t (&v)[32], const float* __restrict__ bias_s, uint8_t* row_ptr,
-                                                 int l, int half) {
-    const float4* bp = reinterpret_cast<const float4*>(bias_s);
-    const __nv_bfloat162 zero2 = __floats2bfloat162_rn(0.0f, 0.0f);
-#pragma unroll
-    for (int j4 = 0; j4 < 4; ++j4) {  // 16-byte group = 8 channels
-        const int jj = half * 4 + j4;
-        uint4* sp = reinterpret_cast<uint4*>(row_ptr + ((jj ^ (l & 7)) << 4));
-        const uint4 rv = *sp;
-        const uint32_t r[4] = {rv.x, rv.y, rv.z, rv.w};
-        const float4 b0 = bp[2 * j4], b1 = bp[2 * j4 + 1];
-        const float2 bb[4] = {make_float2(b0.x, b0.y), make_float2(b0.z, b0.w), make_float2(b1.x, b1.y), make_float2(b1.z, b1.w)};
-        uint32_t w[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            float2 a = make_float2(__uint_as_float(v[8 * j4 + 2 * e]), __uint_as_float(v[8 * j4 + 2 * e + 1]));
-            a = add2(a, bb[e]);
-            a = add2(a, make_float2(__uint_as_float(r[e] << 16), __uint_as_float(r[e] & 0xFFFF0000u)));
-            __nv_bfloat162 h = __floats2bfloat162_rn(a.x, a.y);
-            h = __hmax2(h, zero2);
-            w[e] = *reinterpret_cast<const uint32_t*>(&h);
-        }
-        *sp = make_uint4(w[0], w[1], w[2], w[3]);
-    }
-}
-
-// 16 accumulator columns (two 16-byte groups, index g2 = 0..3 inside the 64-column sub-tile) of one row; RES = the staging
-// row holds the identity values to add (otherwise it is only written)
+// y sub-tile epilogue for 16 accumulator columns (two 16-byte groups, index g2 = 0..3 inside the 64-column sub-tile) of one
+// row: + bias (`bp` = the four float4 of these columns) + residual (in place in the swizzled staging row), ReLU after the bf16
+// rounding (max commutes with the rounding), bf16 pack.  RES = the staging row holds the identity values to add (otherwise it
+// is only written)
 template <bool RES = true>
-__device__ __forceinline__ void l1_convert_row16(const uint32_t (&v)[16], const float* __restrict__ bias_s, uint8_t* row_ptr,
+__device__ __forceinline__ void l1_convert_row16(const uint32_t (&v)[16], const float4 (&bp)[4], uint8_t* row_ptr,
                                                  int l, int g2) {
-    const float4* bp = reinterpret_cast<const float4*>(bias_s);
     const __nv_bfloat162 zero2 = __floats2bfloat162_rn(0.0f, 0.0f);
 #pragma unroll
     for (int j2 = 0; j2 < 2; ++j2) {
@@ -266,10 +238,6 @@ __global__ void __launch_bounds__(kL1Threads, 1) l1_block_kernel(const __grid_co
     uint64_t* d0b_full = x0_free + 1;             // SH: [2] per CTA, double-buffered 64-column conv2 accumulator
     uint64_t* d0b_empty = d0b_full + 2;           // SH: [2] leader, 32
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + Cfg::kNumBars);
-    float* bias_s = reinterpret_cast<float*>(smem + Cfg::kOffBias);
-    for (int i = threadIdx.x; i < 256 + 64 + N2; i += kL1Threads)
-        bias_s[i] = (i < 256) ? __ldg(p.bias3 + i) + (DS ? __ldg(p.bias_ds + i) : 0.0f)
-                              : (i < 320 ? __ldg(p.bias2 + i - 256) : __ldg(p.bias1 + i - 320));
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -639,11 +607,13 @@ __global__ void __launch_bounds__(kL1Threads, 1) l1_block_kernel(const __grid_co
                     uint32_t v[16];
                     tmem_ld_32x16(lane_base + kD2 + static_cast<uint32_t>(half * 64 + c16 * 16), v);
                     tmem_ld_wait();
-                    const float* bp = bias_s + 320 + half * 64 + c16 * 16;
+                    const int bi = (320 + half * 64 + c16 * 16) >> 2;
+                    const float4 bq[4] = {p.bias_c[bi], p.bias_c[bi + 1], p.bias_c[bi + 2], p.bias_c[bi + 3]};
 #pragma unroll
                     for (int c = 0; c < 16; c += 2) {
+                        const float4 b4 = bq[c >> 2];
                         const float2 a = add2(make_float2(__uint_as_float(v[c]), __uint_as_float(v[c + 1])),
-                                              *reinterpret_cast<const float2*>(bp + c));
+                                              (c & 2) ? make_float2(b4.z, b4.w) : make_float2(b4.x, b4.y));
                         __nv_bfloat162 h = __floats2bfloat162_rn(a.x, a.y);
                         h = __hmax2(h, zero2);
                         w[c16 * 8 + (c >> 1)] = *reinterpret_cast<const uint32_t*>(&h);
@@ -697,11 +667,13 @@ __global__ void __launch_bounds__(kL1Threads, 1) l1_block_kernel(const __grid_co
                 __syncwarp();
                 if (lane == 0) mbar_arrive_leader(&d0b_empty[t & 1]);
                 uint32_t w[8];
-                const float* bp = bias_s + 256 + cg * 16;
+                const int bi = (256 + cg * 16) >> 2;
+                const float4 bq[4] = {p.bias_c[bi], p.bias_c[bi + 1], p.bias_c[bi + 2], p.bias_c[bi + 3]};
 #pragma unroll
                 for (int c = 0; c < 16; c += 2) {
+                    const float4 b4 = bq[c >> 2];
                     const float2 a = add2(make_float2(__uint_as_float(v[c]), __uint_as_float(v[c + 1])),
-                                          *reinterpret_cast<const float2*>(bp + c));
+                                          (c & 2) ? make_float2(b4.z, b4.w) : make_float2(b4.x, b4.y));
                     __nv_bfloat162 h = __floats2bfloat162_rn(a.x, a.y);
                     h = __hmax2(h, __floats2bfloat162_rn(0.0f, 0.0f));
                     w[c >> 1] = *reinterpret_cast<const uint32_t*>(&h);
@@ -732,16 +704,18 @@ __global__ void __launch_bounds__(kL1Threads, 1) l1_block_kernel(const __grid_co
             __syncwarp();
             if (lane == 0) mbar_arrive_leader(d0_empty);
             uint32_t w[8];
-            const float* bp = bias_s + 256 + cg * 16;
+            const int bi = (256 + cg * 16) >> 2;
+            const float4 bq[4] = {p.bias_c[bi], p.bias_c[bi + 1], p.bias_c[bi + 2], p.bias_c[bi + 3]};
 #pragma unroll
             for (int c = 0; c < 16; c += 2) {
+                const float4 b4 = bq[c >> 2];
                 float2 u1, u2;
                 u1.x = __shfl_down_sync(0xffffffffu, __uint_as_float(v1[c]), 1);
                 u1.y = __shfl_down_sync(0xffffffffu, __uint_as_float(v1[c + 1]), 1);
                 u2.x = __shfl_down_sync(0xffffffffu, __uint_as_float(v2[c]), 2);
                 u2.y = __shfl_down_sync(0xffffffffu, __uint_as_float(v2[c + 1]), 2);
                 const float2 a = add2(make_float2(__uint_as_float(v0[c]), __uint_as_float(v0[c + 1])), u1);
-                const float2 b = add2(u2, *reinterpret_cast<const float2*>(bp + c));
+                const float2 b = add2(u2, (c & 2) ? make_float2(b4.z, b4.w) : make_float2(b4.x, b4.y));
                 const float2 f2 = add2(a, b);
                 const float f[2] = {f2.x, f2.y};
                 __nv_bfloat162 h = __floats2bfloat162_rn(f[0], f[1]);
@@ -786,7 +760,9 @@ __global__ void __launch_bounds__(kL1Threads, 1) l1_block_kernel(const __grid_co
                     __syncwarp();
                     if (lane == 0) mbar_arrive_leader(d1_empty);
                 }
-                l1_convert_row16<!DS>(v, bias_s + j * kChunkCols + cg * 16, sub + l * 128, l, cg);
+                const int bi = (j * kChunkCols + cg * 16) >> 2;
+                const float4 bq[4] = {p.bias_c[bi], p.bias_c[bi + 1], p.bias_c[bi + 2], p.bias_c[bi + 3]};
+                l1_convert_row16<!DS>(v, bq, sub + l * 128, l, cg);
                 fence_proxy_async_smem();
                 __syncwarp();
                 if (lane == 0) {
