@@ -374,6 +374,37 @@ bool pair_launchable() {
 }
 
 // Build the kernel parameters (tensor maps included) for one fused convolution.
+// fp32 bias vectors on the HOST (kernels that take their biases by value, i.e. in the constant bank): the handle copies every
+// convolution's bias once at bv_create - outside any stream capture, where a synchronous copy would be illegal - and the
+// plan builder looks them up by device pointer; the unit-test entry points have no handle and copy here.
+using HostBiasMap = std::map<const float*, std::vector<float>>;
+thread_local const HostBiasMap* t_bias_cache = nullptr;   // the cache of the handle whose plan is being built (set by build_plan)
+int fetch_bias(const HostBiasMap* cache, const float* dev, int n, float* dst) {
+    if (!dev) return fail(BV_ERR_INVALID, "convolution without a bias vector");
+    if (!cache) cache = t_bias_cache;
+    if (cache) {
+        auto it = cache->find(dev);
+        if (it != cache->end() && static_cast<int>(it->second.size()) >= n) {
+            memcpy(dst, it->second.data(), sizeof(float) * n);
+            return BV_OK;
+        }
+    }
+    BV_CUDA(cudaMemcpy(dst, dev, sizeof(float) * n, cudaMemcpyDeviceToHost));
+    return BV_OK;
+}
+
+// sum of the operands' bias vectors (the fused downsample branch adds its own), as the epilogues used to add them on the device
+int fetch_summed_bias(const ConvOperand* ops, int nops, int n, float* dst) {
+    int rc = fetch_bias(nullptr, ops[0].c.bias, n, dst);
+    if (rc) return rc;
+    for (int i = 1; i < nops; ++i) {
+        std::vector<float> b(n);
+        if ((rc = fetch_bias(nullptr, ops[i].c.bias, n, b.data()))) return rc;
+        for (int j = 0; j < n; ++j) dst[j] += b[j];
+    }
+    return BV_OK;
+}
+
 int build_conv(ConvLaunch* L, int B, const ConvOperand* ops, int nops, const void* residual, int relu, void* out,
                int out_fp32) {
     if (nops < 1 || nops > 2) return fail(BV_ERR_INVALID, "conv needs 1 or 2 operand pairs");
@@ -463,6 +494,11 @@ int build_conv(ConvLaunch* L, int B, const ConvOperand* ops, int nops, const voi
                           (uint32_t)(kCfgPair[cfg] ? bn / 2 : bn));
         if (rc) return rc;
         p.bias[i] = c.bias;
+    }
+    if (N > bv::kMaxBiasN) return fail(BV_ERR_INVALID, "more than %d output channels", bv::kMaxBiasN);
+    {
+        int rc = fetch_summed_bias(ops, nops, N, reinterpret_cast<float*>(p.bias_c));
+        if (rc) return rc;
     }
     p.Wwide = wide ? Wo + 2 : 0;
     if (!out_fp32 && !wide) {
@@ -590,7 +626,6 @@ int build_chain(ChainLaunch* L, int B, const ConvOperand* ops, int nops, const v
         if (rc) return rc;
         rc = make_tmap_2d(&p.tmB1[i], c.w, (uint64_t)c.r * c.s * c.cin, (uint64_t)N1, bv::kBlockK, bv::kChainBN1);
         if (rc) return rc;
-        p.bias1[i] = c.bias;
         k1 += sg.kblocks * 64;
     }
     int rc = make_tmap_2d(&p.tmB2, next.w, (uint64_t)N1, (uint64_t)N2, bv::kBlockK, (uint32_t)N2);
@@ -599,7 +634,8 @@ int build_chain(ChainLaunch* L, int B, const ConvOperand* ops, int nops, const v
     if ((rc = make_tmap_2d(&p.tmOut2, out2, (uint64_t)N2, (uint64_t)M, bv::kChunkCols, bv::kBlockM))) return rc;
     if (residual && (rc = make_tmap_2d(&p.tmRes, residual, (uint64_t)N1, (uint64_t)M, bv::kChunkCols, bv::kBlockM)))
         return rc;
-    p.bias2 = next.bias;
+    if ((rc = fetch_summed_bias(ops, nops, N1, reinterpret_cast<float*>(p.bias1_c)))) return rc;
+    if ((rc = fetch_bias(nullptr, next.bias, N2, reinterpret_cast<float*>(p.bias2_c)))) return rc;
     p.nseg = nops;
     p.Ho = Ho;
     p.Wo = Wo;
@@ -631,23 +667,6 @@ bool l1_ds_supported(const bv_conv& ds) {
 
 // t1 [B,H,W,64] -> out1 = relu(conv3(relu(conv2(t1))) + residual) [B,H,W,256], out2 = relu(next(out1)) [B,H,W,64]
 // With a downsample branch (x0 [B,H,W,64], ds 64 -> 256 1x1) instead of a residual: out1 = relu(conv3(..) + ds(x0)).
-// fp32 bias vectors on the HOST (kernels that take their biases by value, i.e. in the constant bank): the handle copies every
-// convolution's bias once at bv_create - outside any stream capture, where a synchronous copy would be illegal - and the
-// plan builder looks them up by device pointer; the unit-test entry points have no handle and copy here.
-using HostBiasMap = std::map<const float*, std::vector<float>>;
-int fetch_bias(const HostBiasMap* cache, const float* dev, int n, float* dst) {
-    if (!dev) return fail(BV_ERR_INVALID, "convolution without a bias vector");
-    if (cache) {
-        auto it = cache->find(dev);
-        if (it != cache->end() && static_cast<int>(it->second.size()) >= n) {
-            memcpy(dst, it->second.data(), sizeof(float) * n);
-            return BV_OK;
-        }
-    }
-    BV_CUDA(cudaMemcpy(dst, dev, sizeof(float) * n, cudaMemcpyDeviceToHost));
-    return BV_OK;
-}
-
 int build_l1_block(L1Launch* L, int B, int H, int W, const void* t1, const bv_conv& c2, const bv_conv& c3,
                    const void* residual, void* out1, const bv_conv& next, void* out2, const void* x0 = nullptr,
                    const bv_conv* ds = nullptr, const HostBiasMap* bias_cache = nullptr) {
@@ -1051,7 +1070,7 @@ int32_t bv_create(bv_handle** out, const bv_weights* w, int32_t device) {
     bv_handle* h = new bv_handle();
     h->w = *w;
     h->device = device;
-    // host copies of the layer1 bias vectors (the block kernel takes them by value): the packing kernels that wrote them may
+    // host copies of the bias vectors (the convolution kernels take them by value): the packing kernels that wrote them may
     // still be running on any stream of the caller
     {
         bool any = false;
@@ -1061,16 +1080,18 @@ int32_t bv_create(bv_handle** out, const bv_weights* w, int32_t device) {
                 delete h;
                 return fail(BV_ERR_CUDA, "cudaDeviceSynchronize failed: %s", cudaGetErrorString(cudaGetLastError()));
             }
+            std::vector<const bv_conv*> convs = {&w->stem_u8, &w->stem_f1, &w->stem_f3, &w->proj0};
             for (int i = 0; i < BV_NUM_BLOCKS; ++i)
-                for (const bv_conv* c : {&w->conv1[i], &w->conv2[i], &w->conv3[i], &w->downsample[i]}) {
-                    if (!c->bias || c->cout <= 0 || c->cout > 256) continue;     // only layer1-sized vectors are ever looked up
-                    std::vector<float>& v = h->host_bias[c->bias];
-                    v.resize(c->cout);
-                    if (cudaMemcpy(v.data(), c->bias, sizeof(float) * c->cout, cudaMemcpyDeviceToHost) != cudaSuccess) {
-                        delete h;
-                        return fail(BV_ERR_CUDA, "copying a bias vector to the host failed: %s", cudaGetErrorString(cudaGetLastError()));
-                    }
+                for (const bv_conv* c : {&w->conv1[i], &w->conv2[i], &w->conv3[i], &w->downsample[i]}) convs.push_back(c);
+            for (const bv_conv* c : convs) {
+                if (!c->bias || c->cout <= 0) continue;
+                std::vector<float>& v = h->host_bias[c->bias];
+                v.resize(c->cout);
+                if (cudaMemcpy(v.data(), c->bias, sizeof(float) * c->cout, cudaMemcpyDeviceToHost) != cudaSuccess) {
+                    delete h;
+                    return fail(BV_ERR_CUDA, "copying a bias vector to the host failed: %s", cudaGetErrorString(cudaGetLastError()));
                 }
+            }
         }
     }
     *out = h;
@@ -1179,6 +1200,10 @@ int32_t bv_get_profile(bv_handle* h, bv_launch_info* out, int32_t capacity) {
 static int build_plan(bv_handle* h, const void* frames, int dtype, int B, int C, int H, int W, uint8_t* ws) {
     const Layout lay = make_layout(B, C, H, W);
     h->steps.clear();
+    struct BiasCacheScope {   // the builders below look the bias vectors up in this handle's host copies
+        explicit BiasCacheScope(const HostBiasMap* m) { t_bias_cache = m; }
+        ~BiasCacheScope() { t_bias_cache = nullptr; }
+    } bias_scope(&h->host_bias);
     const bool fuse_ds = !env_flag("BV_NO_FUSE_DS");
     const bool use_chain = !env_flag("BV_NO_CHAIN");
     uint8_t* buf_a = ws + lay.buf_a;

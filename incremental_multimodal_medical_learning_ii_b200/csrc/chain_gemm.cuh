@@ -50,8 +50,9 @@ struct ChainParams {
     int Ho, Wo;
     int M, N1;
     int num_m_blocks;
-    const float* bias1[2];
-    const float* bias2;
+    // biases by value (constant bank; see ConvGemmParams::bias_c): the first GEMM's summed segment biases, the second GEMM's
+    float4 bias1_c[1024 / 4];
+    float4 bias2_c[256 / 4];
     int has_res;
     int l2_prefetch;      // producer / DMA pull the next tile's A and residual into L2 ahead of the smem pipeline
 };
@@ -69,21 +70,14 @@ struct ChainCfg {
 
 // bias (+ second bias of the fused downsample) + optional in-place residual + ReLU + bf16 pack of
 // 16 accumulator columns (16-byte groups 2 cg and 2 cg + 1 of the 64-column sub-tile) of one row
-__device__ __forceinline__ void chain_convert_row16(const uint32_t (&v)[16], const float* __restrict__ bias_a,
-                                                    const float* __restrict__ bias_b, bool has_res, uint8_t* row_ptr,
-                                                    int cg, int r_in_tile) {
-    const float4* bp = reinterpret_cast<const float4*>(bias_a);
-    const float4* bp2 = reinterpret_cast<const float4*>(bias_b);
+__device__ __forceinline__ void chain_convert_row16(const uint32_t (&v)[16], const float4 (&bq)[4], bool has_res,
+                                                    uint8_t* row_ptr, int cg, int r_in_tile) {
 #pragma unroll
     for (int j = 0; j < 2; ++j) {
         float f[8];
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
-            float4 bb = __ldg(bp + 2 * j + q);
-            if (bias_b) {
-                const float4 b2 = __ldg(bp2 + 2 * j + q);
-                bb.x += b2.x; bb.y += b2.y; bb.z += b2.z; bb.w += b2.w;
-            }
+            const float4 bb = bq[2 * j + q];
             f[4 * q + 0] = __uint_as_float(v[8 * j + 4 * q + 0]) + bb.x;
             f[4 * q + 1] = __uint_as_float(v[8 * j + 4 * q + 1]) + bb.y;
             f[4 * q + 2] = __uint_as_float(v[8 * j + 4 * q + 2]) + bb.z;
@@ -445,8 +439,9 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_gemm_kernel(const __gr
                 chain_tmem_ld_32x16(lane_base + 256u + static_cast<uint32_t>(acc2 * 128 + sub * kChunkCols + cg * 16), v);
                 mbar_wait(&buf2_ready[sub], it & 1u);
                 tmem_ld_wait();
-                chain_convert_row16(v, p.bias2 + sub * kChunkCols + cg * 16, nullptr, false,
-                                    stg2 + sub * kStagingBytes + r_in_tile * 128, cg, r_in_tile);
+                const int b4 = (sub * kChunkCols + cg * 16) >> 2;
+                const float4 bq[4] = {p.bias2_c[b4], p.bias2_c[b4 + 1], p.bias2_c[b4 + 2], p.bias2_c[b4 + 3]};
+                chain_convert_row16(v, bq, false, stg2 + sub * kStagingBytes + r_in_tile * 128, cg, r_in_tile);
                 fence_proxy_async_smem();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&buf2_written[sub]);
@@ -468,9 +463,9 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_gemm_kernel(const __gr
                 chain_tmem_ld_32x16(lane_base + static_cast<uint32_t>(d * kChainBN1 + sub * kChunkCols + cg * 16), v);
                 mbar_wait(&buf_ready[b], (g / NB1) & 1u);
                 tmem_ld_wait();
-                const int col = c * kChainBN1 + sub * kChunkCols + cg * 16;
-                chain_convert_row16(v, p.bias1[0] + col, (p.nseg > 1) ? p.bias1[1] + col : nullptr, has_res,
-                                    stg1 + b * kStagingBytes + r_in_tile * 128, cg, r_in_tile);
+                const int b4 = (c * kChainBN1 + sub * kChunkCols + cg * 16) >> 2;
+                const float4 bq[4] = {p.bias1_c[b4], p.bias1_c[b4 + 1], p.bias1_c[b4 + 2], p.bias1_c[b4 + 3]};
+                chain_convert_row16(v, bq, has_res, stg1 + b * kStagingBytes + r_in_tile * 128, cg, r_in_tile);
                 fence_proxy_async_smem();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&buf_written[b]);

@@ -60,6 +60,8 @@ struct ConvSeg {
     int lower;    // -padding (window origin of output pixel 0)
 };
 
+constexpr int kMaxBiasN = 2048;   // widest layer (layer4 conv3)
+
 struct ConvGemmParams {
     CUtensorMap tmA[2];
     CUtensorMap tmB[2];  // per-segment weights [N, taps*Cin], K-major
@@ -79,6 +81,10 @@ struct ConvGemmParams {
     long long* dbg;  // optional [gridDim][4] cycle counters: MMA warp {total, wait tmem_empty, wait full}, producer {wait empty}
     int nacc;  // independent TMEM accumulators the K steps are dealt over (1 .. 256/BN); summed in the epilogue
     int res_prefetch;  // > 0: pull the residual sub-tile this many sub-tiles beyond the staging ring into L2 (experiment)
+    // The summed per-segment biases BY VALUE (the kernel's constant bank; kernel parameters may be 32 KB since CUDA 12.1).
+    // The staged epilogue reads them with indexed constant loads: broadcast loads through L1 / shared memory cost LSU
+    // data-pipe wavefronts, and in the epilogues with an identity stream that pipe is the in-step bound.
+    float4 bias_c[kMaxBiasN / 4];
 };
 
 // BN = output channels per tile; STAGES = depth of the A/B smem ring; NBUF = epilogue staging tiles.
@@ -576,19 +582,13 @@ __global__ void __launch_bounds__(gemm_threads(EPI), 1) conv_gemm_kernel(const _
 #pragma unroll
                         for (int j = 0; j < kWarpCols; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(w2[j]));
                     }
-                    const int col = n_blk * BN + c * kChunkCols + cg * kWarpCols;
-                    const float4* bp = reinterpret_cast<const float4*>(p.bias[0] + col);
-                    const float4* bp2 = (p.nseg > 1) ? reinterpret_cast<const float4*>(p.bias[1] + col) : nullptr;
+                    const int col4 = (n_blk * BN + c * kChunkCols + cg * kWarpCols) >> 2;
 #pragma unroll
                     for (int j = 0; j < kWarpCols / 8; ++j) {  // 16-byte group = 8 channels
                         float f[8];
 #pragma unroll
                         for (int q = 0; q < 2; ++q) {
-                            float4 bb = __ldg(bp + 2 * j + q);
-                            if (bp2) {
-                                const float4 b2 = __ldg(bp2 + 2 * j + q);
-                                bb.x += b2.x; bb.y += b2.y; bb.z += b2.z; bb.w += b2.w;
-                            }
+                            const float4 bb = p.bias_c[col4 + 2 * j + q];   // bias[0] (+ bias[1]), summed on the host
                             f[4 * q + 0] = __uint_as_float(v[8 * j + 4 * q + 0]) + bb.x;
                             f[4 * q + 1] = __uint_as_float(v[8 * j + 4 * q + 1]) + bb.y;
                             f[4 * q + 2] = __uint_as_float(v[8 * j + 4 * q + 2]) + bb.z;

@@ -379,8 +379,9 @@ __global__ void __launch_bounds__(kPcThreads, 1) pair_chain_kernel(const __grid_
                 chain_tmem_ld_32x16(lane_base + static_cast<uint32_t>(d * kChainBN1 + sub * kChunkCols + cg * 16), v);
                 mbar_wait(&stg_ready[b], (g / NSTG) & 1u);
                 tmem_ld_wait();
-                chain_convert_row16(v, p.bias1 + c * kChainBN1 + sub * kChunkCols + cg * 16, nullptr, true,
-                                    stg + b * kStagingBytes + r_in_tile * 128, cg, r_in_tile);
+                const float4* bp1 = reinterpret_cast<const float4*>(p.bias1 + c * kChainBN1 + sub * kChunkCols + cg * 16);
+                const float4 bq[4] = {__ldg(bp1), __ldg(bp1 + 1), __ldg(bp1 + 2), __ldg(bp1 + 3)};
+                chain_convert_row16(v, bq, true, stg + b * kStagingBytes + r_in_tile * 128, cg, r_in_tile);
                 fence_proxy_async_smem();   // generic-proxy writes -> visible to the pair MMA and the TMA store
                 __syncwarp();
                 if (lane == 0) {
