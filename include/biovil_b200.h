@@ -102,6 +102,10 @@ const char* bv_version(void);
 size_t bv_workspace_bytes(int32_t batch, int32_t channels, int32_t height, int32_t width);
 int32_t bv_patch_grid(int32_t size); /* size / 32 */
 
+/* `host_weights` is a host struct of DEVICE pointers (packed bf16 weights, fp32 biases).  The pointers must stay valid and
+ * their contents unchanged for the life of the handle: bv_create synchronises the device once and keeps host copies of
+ * the bias vectors, which the convolution kernels receive by value (constant bank) - create a new handle after changing
+ * parameters (what ImageModel does when a parameter's version counter moves). */
 int32_t bv_create(bv_handle** out, const bv_weights* host_weights, int32_t device);
 void bv_destroy(bv_handle* h);
 
