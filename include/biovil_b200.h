@@ -22,6 +22,7 @@
  *   bv_resize_center_crop_u8  transforms.Resize + CenterCrop on 8-bit frames (Pillow 8bpc bilinear, bit-exact)
  *                     DataRetrieval.py:175-180; health_multimodal/image/data/transforms.py:30-41
  *   bv_smooth_heatmaps  gaussian_filter(sigma) of the similarity maps health_multimodal/vlp/inference_engine.py:107-109
+ *   bv_heatmaps_to_image_size  convert_similarity_to_image_size (nearest upsample + NaN pad)  health_multimodal/vlp/inference_engine.py:113-155
  *   bv_set_profile / bv_get_profile   (measurement only; no reference counterpart)
  *   bv_conv2d_nhwc    one Conv2d+BatchNorm2d(+ReLU)(+residual)   (unit-test entry for the tcgen05 kernel)
  *   bv_conv_chain_nhwc  Bottleneck tail (conv3+bn3+identity/downsample+ReLU) chained with the next Bottleneck's
@@ -166,6 +167,15 @@ int32_t bv_resize_center_crop_u8(const uint8_t* src, int32_t n, int32_t height, 
  * (order 0, mode 'reflect', truncate 4.0, separable, same sigma on both axes); gh*gw <= 1024, radius <= 16. */
 int32_t bv_smooth_heatmaps(const float* heat, int32_t batch, int32_t grid_h, int32_t grid_w, int32_t num_labels,
                            float sigma, float* out, bv_stream stream);
+
+/* Patch-grid similarity maps heat [B,gh,gw,L] -> out [B,L,height,width] in the ORIGINAL image's pixels, as
+ * ImageTextInferenceEngine.convert_similarity_to_image_size does with interpolation="nearest" (its default;
+ * health_multimodal/vlp/inference_engine.py:113-155): the grid is stretched (F.interpolate nearest) over the centre-crop
+ * square of int(crop_size * min(height, width) / resize_size) pixels (crop_size pixels when resize_size == 0; the whole
+ * image when crop_size == 0) and everything outside it is NaN (F.pad).  B * L <= 65535 maps per call. */
+int32_t bv_heatmaps_to_image_size(const float* heat, int32_t batch, int32_t grid_h, int32_t grid_w, int32_t num_labels,
+                                  int32_t height, int32_t width, int32_t resize_size, int32_t crop_size, float* out,
+                                  bv_stream stream);
 
 /* Number of kernels the last bv_forward launched (for launch accounting in the benchmark). */
 int32_t bv_last_forward_launches(const bv_handle* h);

@@ -69,6 +69,7 @@ EXPORTED_SYMBOLS = (
     "bv_resize_workspace_bytes", "bv_resize_center_crop_u8", "bv_pair_gemm_test", "bv_l1_block_nhwc",
     "bv_stem_u8_nhwc", "bv_stem_conv1_u8_nhwc", "bv_forward_graph", "bv_pairwise_cosine", "bv_quantize_frames_f32",
     "bv_jpeg_info", "bv_jpeg_decode_gray_u8", "bv_l1_block_ds_nhwc", "bv_pair_chain_nhwc", "bv_jpeg_decode_batch_gray_u8",
+    "bv_heatmaps_to_image_size",
 )
 
 _lib = None
@@ -172,6 +173,9 @@ def lib() -> ctypes.CDLL:
     l.bv_pair_gemm_test.argtypes = [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p]
     l.bv_smooth_heatmaps.restype = c_int32
     l.bv_smooth_heatmaps.argtypes = [c_void_p, c_int32, c_int32, c_int32, c_int32, c_float, c_void_p, c_void_p]
+    l.bv_heatmaps_to_image_size.restype = c_int32
+    l.bv_heatmaps_to_image_size.argtypes = [c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32,
+                                            c_void_p, c_void_p]
     l.bv_conv_chain_nhwc.restype = c_int32
     l.bv_conv_chain_nhwc.argtypes = [c_void_p, c_int32, c_int32, c_int32, POINTER(BvConv), c_void_p, c_int32, c_int32,
                                      POINTER(BvConv), c_void_p, c_void_p, POINTER(BvConv), c_void_p, c_void_p]

@@ -513,4 +513,41 @@ __global__ void __launch_bounds__(256) heat_smooth_kernel(const SmoothParams p) 
     }
 }
 
+// ----------------------------------------------------------------------------------------------
+// Patch-grid similarity maps -> image size (vlp/inference_engine.py:113-155 with interpolation="nearest", the
+// reference's default): F.interpolate(mode="nearest") of the [gh, gw] grid to a `side_h x side_w` window (the centre
+// crop expressed in the original image's pixels) placed at (`top`, `left`) of the [height, width] image, NaN everywhere
+// else (F.pad(value=NaN); negative margins crop, as F.pad does).  PyTorch's nearest index: dst == src size -> identity,
+// dst == 2 * src -> dst >> 1, else min(int(floorf(dst * (float(src) / dst_size))), src - 1) - reproduced exactly.
+// heat [B, gh, gw, L] (channel-last, as bv_forward writes it) -> out [B, L, height, width]; one thread per output pixel.
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ int nearest_src_index(int dst, int src_size, int dst_size, float scale) {
+    if (dst_size == src_size) return dst;
+    if (dst_size == 2 * src_size) return dst >> 1;
+    return min(static_cast<int>(floorf(static_cast<float>(dst) * scale)), src_size - 1);
+}
+
+__global__ void __launch_bounds__(256) heat_to_image_kernel(const float* __restrict__ heat, float* __restrict__ out, int gh,
+                                                           int gw, int L, int height, int width, int side_h, int side_w,
+                                                           int top, int left) {
+    const int map = blockIdx.y;                 // b * L + l
+    const int b = map / L, l = map - b * L;
+    const float scale_h = static_cast<float>(gh) / static_cast<float>(side_h);
+    const float scale_w = static_cast<float>(gw) / static_cast<float>(side_w);
+    const float* src = heat + static_cast<size_t>(b) * gh * gw * L + l;
+    float* dst = out + static_cast<size_t>(map) * height * width;
+    const int total = height * width;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int y = i / width, x = i - y * width;
+        const int yy = y - top, xx = x - left;
+        float v = __int_as_float(0x7fc00000);   // NaN
+        if (yy >= 0 && yy < side_h && xx >= 0 && xx < side_w) {
+            const int sy = nearest_src_index(yy, gh, side_h, scale_h);
+            const int sx = nearest_src_index(xx, gw, side_w, scale_w);
+            v = __ldg(src + (static_cast<size_t>(sy) * gw + sx) * L);
+        }
+        dst[i] = v;
+    }
+}
+
 }  // namespace bv

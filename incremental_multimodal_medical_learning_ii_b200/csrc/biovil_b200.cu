@@ -1936,6 +1936,30 @@ int32_t bv_smooth_heatmaps(const float* heat, int32_t B, int32_t gh, int32_t gw,
     return BV_OK;
 }
 
+int32_t bv_heatmaps_to_image_size(const float* heat, int32_t B, int32_t gh, int32_t gw, int32_t L, int32_t height,
+                                  int32_t width, int32_t resize_size, int32_t crop_size, float* out, bv_stream stream) {
+    if (!heat || !out || B <= 0 || L <= 0 || gh <= 0 || gw <= 0 || height <= 0 || width <= 0 || resize_size < 0 || crop_size < 0)
+        return fail(BV_ERR_INVALID, "bad heat-map arguments");
+    if ((long long)B * L > 65535) return fail(BV_ERR_INVALID, "more than 65535 maps in one call");
+    int rc = device_setup();
+    if (rc) return rc;
+    // vlp/inference_engine.py:133-154: with a crop the grid covers a square of `side` original pixels, centred
+    int side_h = height, side_w = width, top = 0, left = 0;
+    if (crop_size > 0) {
+        const int smallest = std::min(height, width);
+        const int side = resize_size > 0 ? (int)((double)crop_size * smallest / resize_size) : crop_size;   // int(crop * min / resize)
+        if (side <= 0) return fail(BV_ERR_INVALID, "the crop covers no pixel of a %dx%d image", height, width);
+        side_h = side_w = side;
+        left = (int)std::floor((width - side) / 2.0);     // F.pad margins: (floor(mw / 2), ceil(mw / 2), floor(mh / 2), ceil(mh / 2))
+        top = (int)std::floor((height - side) / 2.0);
+    }
+    const int blocks_x = std::min((height * width + 255) / 256, 64);
+    bv::heat_to_image_kernel<<<dim3(blocks_x, B * L), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        heat, out, gh, gw, L, height, width, side_h, side_w, top, left);
+    BV_CUDA(cudaGetLastError());
+    return BV_OK;
+}
+
 int32_t bv_l1_block_nhwc(const void* t1, int32_t B, int32_t H, int32_t W, const bv_conv* c2, const bv_conv* c3,
                          const void* residual, void* out1, const bv_conv* next, void* out2, bv_stream stream) {
     if (!t1 || !c2 || !c3 || !residual || !out1 || !next || !out2) return fail(BV_ERR_INVALID, "null argument");

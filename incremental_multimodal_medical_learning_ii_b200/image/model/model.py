@@ -387,6 +387,23 @@ class ImageModel(nn.Module):
                                                N.current_stream_handle(heat.device)))
         return out
 
+    def heatmaps_to_image_size(self, heat: torch.Tensor, width: int, height: int, resize_size: Optional[int],
+                               crop_size: Optional[int]) -> torch.Tensor:  # `self` is not used
+        """``[B,H',W',L]`` similarity maps -> ``[B,L,height,width]`` in the original image's pixels on the GPU:
+        ``ImageTextInferenceEngine.convert_similarity_to_image_size`` with its default ``interpolation="nearest"``
+        (vlp/inference_engine.py:113-155; nearest upsampling over the centre-crop square, NaN outside it), batched."""
+        if heat.dim() != 4 or not heat.is_cuda:
+            raise ValueError("expected CUDA similarity maps [B, H', W', L]")
+        heat = heat.float().contiguous()
+        B, gh, gw, L = heat.shape
+        out = torch.empty(B, L, int(height), int(width), dtype=torch.float32, device=heat.device)
+        if B == 0 or L == 0:
+            return out
+        with torch.cuda.device(heat.device):
+            N.check(N.lib().bv_heatmaps_to_image_size(N.ptr(heat), B, gh, gw, L, int(height), int(width), int(resize_size or 0),
+                                                      int(crop_size or 0), N.ptr(out), N.current_stream_handle(heat.device)))
+        return out
+
     @torch.no_grad()
     def score_embeddings(self, emb: torch.Tensor) -> Dict[str, torch.Tensor]:
         """Score cached ``[B,128]`` embeddings (the ``Trainer.val/test`` path) against the installed prompts."""

@@ -75,14 +75,23 @@ class ImageTextInferenceEngine:
 
     @torch.no_grad()
     def get_similarity_maps_from_tensor(self, frames: torch.Tensor, text_embeddings: torch.Tensor,
-                                        sigma: Optional[float] = 1.5) -> torch.Tensor:
+                                        sigma: Optional[float] = 1.5,
+                                        image_size: Optional[tuple] = None) -> torch.Tensor:
         """Batched: frames ``[B,1|3,H,W]`` on the model's device, ``text_embeddings`` ``[L, D]`` (un-normalised) ->
-        similarity maps ``[B, H', W', L]``, smoothed with ``sigma`` (``None``: raw)."""
+        similarity maps ``[B, H', W', L]``, smoothed with ``sigma`` (``None``: raw).  With ``image_size = (width, height)``
+        of the ORIGINAL images the maps come back as ``[B, L, height, width]`` in their pixels, NaN outside the centre crop:
+        ``convert_similarity_to_image_size`` (nearest) on the GPU for the whole batch (reference :113-155)."""
         model = self.image_inference_engine.model
         patches = model.get_patchwise_projected_embeddings(frames, normalize=True)
         t = F.normalize(text_embeddings.to(patches.device).float(), dim=-1)
         heat = (patches @ t.t()).contiguous()
-        return heat if sigma is None else model.smooth_heatmaps(heat, sigma)
+        if sigma is not None:
+            heat = model.smooth_heatmaps(heat, sigma)
+        if image_size is None:
+            return heat
+        width, height = image_size
+        return model.heatmaps_to_image_size(heat, width, height, self.image_inference_engine.resize_size,
+                                            self.image_inference_engine.crop_size)
 
     @staticmethod
     def convert_similarity_to_image_size(similarity_map: torch.Tensor, width: int, height: int,

@@ -141,3 +141,4 @@ def test_image_text_inference_engine_vs_oracle(tmp_path):
     assert np.nanmax(np.abs(got_full - ref_full)) <= 5e-3                           # bf16 trunk vs fp32 oracle (patch level)
     maps = engine.get_similarity_maps_from_tensor((x[:, :1] * 255).round().to(torch.uint8).cuda(), te, sigma=1.5)
     assert maps.shape == (1, 3, 3, 1) and float((maps[0, :, :, 0].cpu() - ref_map).abs().max()) <= 5e-3
+

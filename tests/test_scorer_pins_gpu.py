@@ -153,3 +153,36 @@ def test_image_text_engine_vs_reference_vlp_engine(golden, vlp):
     d = np.abs(sm - vlp["smoothed_maps"]).max()
     print(f"smoothed similarity maps, full path: max abs diff vs the reference engine {d:.2e}")
     assert d <= 5e-3
+
+
+def test_heatmaps_to_image_size_vs_reference_function(vlp):
+    """bv_heatmaps_to_image_size (nearest upsample of the patch grid over the centre-crop square + NaN pad, batched) against
+    ``convert_similarity_to_image_size`` - the host function that tests/test_scorer_pins_cpu.py pins bit-equal to the
+    reference's (vlp/inference_engine.py:113-155) on the same cases - and against the reference's own recorded outputs."""
+    from incremental_multimodal_medical_learning_ii_b200.image.model.model import ImageModel
+    from incremental_multimodal_medical_learning_ii_b200.vlp.inference_engine import ImageTextInferenceEngine as E
+    grid = torch.arange(15 * 15, dtype=torch.float32).reshape(15, 15) / 7.0          # the grid of the golden cases
+    g = torch.Generator().manual_seed(4)
+    heat = torch.randn(3, 15, 15, 5, generator=g)
+    heat[0, :, :, 0] = grid
+    for k, (w, h, rs, cs) in enumerate(vlp["resize_cases"].tolist()):
+        got = ImageModel.heatmaps_to_image_size(None, heat.cuda(), w, h, rs or None, cs or None).cpu().numpy()
+        assert got.shape == (3, 5, h, w)
+        ref0 = vlp[f"resize_{k}_nearest"]                                             # the reference's own output
+        assert np.array_equal(np.isnan(got[0, 0]), np.isnan(ref0)) and np.array_equal(np.nan_to_num(got[0, 0]), np.nan_to_num(ref0)), k
+        for b, l in ((1, 3), (2, 4)):
+            ref = E.convert_similarity_to_image_size(heat[b, :, :, l], width=w, height=h, resize_size=rs or None, crop_size=cs or None)
+            assert np.array_equal(np.isnan(got[b, l]), np.isnan(ref)) and np.array_equal(np.nan_to_num(got[b, l]), np.nan_to_num(ref)), (k, b, l)
+    # other grid sizes / scale factors (identity, exact doubling, fractional), a crop larger than the image (F.pad crops)
+    for gh, gw, w, h, rs, cs in ((16, 16, 16, 16, None, None), (16, 16, 32, 32, None, None), (7, 9, 333, 201, None, None),
+                                 (15, 15, 400, 300, None, 480), (15, 15, 390, 320, 512, 480), (4, 4, 37, 91, 64, 48)):
+        hm = torch.randn(2, gh, gw, 3, generator=g)
+        got = ImageModel.heatmaps_to_image_size(None, hm.cuda(), w, h, rs, cs).cpu().numpy()
+        for b in range(2):
+            for l in range(3):
+                ref = E.convert_similarity_to_image_size(hm[b, :, :, l], width=w, height=h, resize_size=rs, crop_size=cs)
+                assert got[b, l].shape == ref.shape
+                assert np.array_equal(np.isnan(got[b, l]), np.isnan(ref)) and np.array_equal(np.nan_to_num(got[b, l]), np.nan_to_num(ref)), (gh, gw, w, h, rs, cs)
+    assert ImageModel.heatmaps_to_image_size(None, torch.empty(0, 15, 15, 14, device="cuda"), 64, 48, 512, 480).shape == (0, 14, 48, 64)
+    with pytest.raises(ValueError):
+        ImageModel.heatmaps_to_image_size(None, torch.zeros(1, 15, 15, 14), 64, 48, 512, 480)      # CPU tensor: no CPU path
