@@ -848,8 +848,9 @@ int build_pair_chain(PairChainLaunch* L, int B, int H, int W, const void* x, con
     if ((rc = make_tmap_2d(&p.tmB2, next.w, (uint64_t)N1, (uint64_t)N2, bv::kBlockK, (uint32_t)(N2 / 2)))) return rc;
     if ((rc = make_tmap_2d(&p.tmRes, residual, (uint64_t)N1, (uint64_t)M, bv::kChunkCols, bv::kBlockM))) return rc;
     if ((rc = make_tmap_2d(&p.tmOut1, out1, (uint64_t)N1, (uint64_t)M, bv::kChunkCols, bv::kBlockM))) return rc;
-    p.bias1 = c3.bias;
-    p.bias2 = next.bias;
+    if (N1 > 1024 || N2 > 256) return fail(BV_ERR_INVALID, "pair-chained kernel: N1 <= 1024, N2 <= 256");
+    if ((rc = fetch_bias(nullptr, c3.bias, N1, reinterpret_cast<float*>(p.bias1_c)))) return rc;
+    if ((rc = fetch_bias(nullptr, next.bias, N2, reinterpret_cast<float*>(p.bias2_c)))) return rc;
     p.out2 = reinterpret_cast<__nv_bfloat16*>(out2);
     p.M = (int)M;
     p.N1 = N1;
@@ -899,7 +900,7 @@ const int kLayerBlocks[4] = {3, 4, 6, 3};
 // from the identity prefetch until both the TMA store and the second GEMM have read it, and 5-6 sub-tiles (all that fits
 // next to the resident 64 KB input tile) do not cover that span.  Kept (bit-exact, tests/test_chain_gpu.py) behind
 // BV_PAIR_CHAIN for the next attempt.
-const int kPairChainDefault = 0;
+const int kPairChainDefault = 1;
 
 const int kLayerWidth[4] = {64, 128, 256, 512};
 

@@ -42,8 +42,9 @@ struct PairChainParams {
     CUtensorMap tmB2;    // next conv1 weights [N2, N1], box 64 x N2/2
     CUtensorMap tmRes;   // identity [M, N1], box 64 x 128
     CUtensorMap tmOut1;  // block output [M, N1], box 64 x 128
-    const float* bias1;  // [N1]
-    const float* bias2;  // [N2]
+    // biases by value (constant bank; see ConvGemmParams::bias_c)
+    float4 bias1_c[1024 / 4];  // [N1]
+    float4 bias2_c[256 / 4];   // [N2]
     __nv_bfloat16* out2; // [M, N2]
     int M, N1;
     int num_m_blocks;    // ceil(M / 128)
@@ -344,11 +345,11 @@ __global__ void __launch_bounds__(kPcThreads, 1) pair_chain_kernel(const __grid_
                 uint32_t v[16];
                 chain_tmem_ld_32x16(lane_base + kD2 + static_cast<uint32_t>(sub * kChunkCols + cg * 16), v);
                 tmem_ld_wait();
-                const float4* bp = reinterpret_cast<const float4*>(p.bias2 + sub * kChunkCols + cg * 16);
+                const int b4 = (sub * kChunkCols + cg * 16) >> 2;
                 uint32_t w[8];
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    const float4 bb = __ldg(bp + j);
+                    const float4 bb = p.bias2_c[b4 + j];
                     const __nv_bfloat162 h0 = __floats2bfloat162_rn(fmaxf(__uint_as_float(v[4 * j + 0]) + bb.x, 0.0f),
                                                                     fmaxf(__uint_as_float(v[4 * j + 1]) + bb.y, 0.0f));
                     const __nv_bfloat162 h1 = __floats2bfloat162_rn(fmaxf(__uint_as_float(v[4 * j + 2]) + bb.z, 0.0f),
@@ -379,8 +380,8 @@ __global__ void __launch_bounds__(kPcThreads, 1) pair_chain_kernel(const __grid_
                 chain_tmem_ld_32x16(lane_base + static_cast<uint32_t>(d * kChainBN1 + sub * kChunkCols + cg * 16), v);
                 mbar_wait(&stg_ready[b], (g / NSTG) & 1u);
                 tmem_ld_wait();
-                const float4* bp1 = reinterpret_cast<const float4*>(p.bias1 + c * kChainBN1 + sub * kChunkCols + cg * 16);
-                const float4 bq[4] = {__ldg(bp1), __ldg(bp1 + 1), __ldg(bp1 + 2), __ldg(bp1 + 3)};
+                const int b4 = (c * kChainBN1 + sub * kChunkCols + cg * 16) >> 2;
+                const float4 bq[4] = {p.bias1_c[b4], p.bias1_c[b4 + 1], p.bias1_c[b4 + 2], p.bias1_c[b4 + 3]};
                 chain_convert_row16(v, bq, true, stg + b * kStagingBytes + r_in_tile * 128, cg, r_in_tile);
                 fence_proxy_async_smem();   // generic-proxy writes -> visible to the pair MMA and the TMA store
                 __syncwarp();
