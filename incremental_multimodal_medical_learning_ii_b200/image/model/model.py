@@ -180,7 +180,7 @@ class _Engine:
         """Small-batch path: static input / output buffers per call signature, the whole forward replayed as ONE CUDA
         graph launch (``bv_forward_graph``), results returned as copies of the static outputs (one packed buffer, one
         copy).  The reference's extraction loop calls the model with batch size 1 (chexpert-get-embedding.py:47-49):
-        45 launches of a few microseconds each are launch-bound, a graph replay is not."""
+        about 40 launches of a few microseconds each are launch-bound, a graph replay is not."""
         B, C, H, W = frames.shape
         key = (B, C, H, W, frames.dtype, tuple(sorted(shapes)), bool(normalize_patch), self.num_labels)
         st = self._static.get(key)
@@ -413,7 +413,7 @@ class ImageModel(nn.Module):
         return eng.score(emb.to(eng.device, torch.float32).contiguous())
 
     # ---- machinery ----------------------------------------------------------------------------------------
-    GRAPH_MAX_BATCH = 32     # "auto": batches up to this size are launch-bound (45 launches of a few microseconds each)
+    GRAPH_MAX_BATCH = 32     # "auto": batches up to this size are launch-bound (about 40 launches of a few microseconds each)
 
     def _apply(self, fn, *args, **kwargs):
         self._engine = None
