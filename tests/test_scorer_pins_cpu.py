@@ -62,6 +62,29 @@ def test_convert_similarity_to_image_size_matches_reference(vlp):
             assert np.array_equal(np.nan_to_num(got), np.nan_to_num(ref)), (k, interp)   # vlp/inference_engine.py:113-155
 
 
+def test_heatmap_oracle_matches_reference_outputs(vlp):
+    """oracle/heatmap_oracle.py (the restatement the CUDA heat-map resize kernel is checked against) reproduces the
+    reference's own ``convert_similarity_to_image_size`` outputs bit for bit (nearest mode, vlp/inference_engine.py:113-155),
+    and agrees with the host function on shapes the fixtures do not hold (identity, exact doubling, a crop larger than the
+    image)."""
+    import heatmap_oracle as HO
+    from incremental_multimodal_medical_learning_ii_b200.vlp.inference_engine import ImageTextInferenceEngine as E
+    grid = (torch.arange(15 * 15, dtype=torch.float32).reshape(15, 15) / 7.0).numpy()
+    for k, (w, h, rs, cs) in enumerate(vlp["resize_cases"].tolist()):
+        got = HO.heatmap_to_image_size(grid, w, h, rs or None, cs or None)
+        ref = vlp[f"resize_{k}_nearest"]
+        assert got.shape == ref.shape
+        assert np.array_equal(np.isnan(got), np.isnan(ref)) and np.array_equal(np.nan_to_num(got), np.nan_to_num(ref)), k
+    g = torch.Generator().manual_seed(4)
+    for gh, gw, w, h, rs, cs in ((16, 16, 16, 16, None, None), (16, 16, 32, 32, None, None), (7, 9, 133, 101, None, None),
+                                 (15, 15, 200, 150, None, 240), (4, 4, 37, 91, 64, 48)):
+        hm = torch.randn(gh, gw, generator=g)
+        got = HO.heatmap_to_image_size(hm.numpy(), w, h, rs, cs)
+        ref = E.convert_similarity_to_image_size(hm, width=w, height=h, resize_size=rs, crop_size=cs)
+        assert got.shape == ref.shape
+        assert np.array_equal(np.isnan(got), np.isnan(ref)) and np.array_equal(np.nan_to_num(got), np.nan_to_num(ref))
+
+
 def test_oracle_label_loop_matches_reference_trainer(trainer_golden):
     tg = trainer_golden
     assert len(tg["cases"]) == 12

@@ -183,6 +183,11 @@ def test_heatmaps_to_image_size_vs_reference_function(vlp):
                 ref = E.convert_similarity_to_image_size(hm[b, :, :, l], width=w, height=h, resize_size=rs, crop_size=cs)
                 assert got[b, l].shape == ref.shape
                 assert np.array_equal(np.isnan(got[b, l]), np.isnan(ref)) and np.array_equal(np.nan_to_num(got[b, l]), np.nan_to_num(ref)), (gh, gw, w, h, rs, cs)
+    import heatmap_oracle as HO                                                   # the numpy restatement (pinned on the CPU side)
+    hm = torch.randn(2, 15, 15, 3, generator=g)
+    got = ImageModel.heatmaps_to_image_size(None, hm.cuda(), 390, 320, 512, 480).cpu().numpy()
+    ref = HO.heatmaps_to_image_size(hm.numpy(), 390, 320, 512, 480)
+    assert np.array_equal(np.isnan(got), np.isnan(ref)) and np.array_equal(np.nan_to_num(got), np.nan_to_num(ref))
     assert ImageModel.heatmaps_to_image_size(None, torch.empty(0, 15, 15, 14, device="cuda"), 64, 48, 512, 480).shape == (0, 14, 48, 64)
     with pytest.raises(ValueError):
         ImageModel.heatmaps_to_image_size(None, torch.zeros(1, 15, 15, 14), 64, 48, 512, 480)      # CPU tensor: no CPU path
